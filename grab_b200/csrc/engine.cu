@@ -1,0 +1,637 @@
+// engine.cu -- host side of libgscan.so: contexts, batch planning, staging, kernel orchestration and
+// the extern "C" surface declared in include/gscan.h.
+//
+// Mirrors the reference's ownership model: a gscan_ctx is what a FileGrep object is in
+// /root/reference/src/grab.cc (one per host thread, main.cc:195-199) -- it owns its stream, its
+// device buffers and its last error string (FileGrep::why, grab.h:61-64).  Errors never throw
+// across the ABI and never abort: int 0 / -1 + message.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gscan.h"
+#include "device_types.h"
+#include "kernels.h"
+#include "pattern.h"
+
+using namespace gscan;
+
+// ------------------------------------------------------------------------------------------
+// objects behind the opaque handles
+// ------------------------------------------------------------------------------------------
+struct gscan_pattern {
+	Program prog;
+	// host images of the device tables (FIXED engine)
+	std::vector<uint16_t> seq_len;
+	std::vector<uint32_t> seq_off, seq_pos, cls_bm;
+	FixedParams fixed; // device pointers filled per context
+	RunParams run;
+	uint32_t pre = 16, post = 32;
+};
+
+template <class T>
+struct DevBuf {
+	T *p = nullptr;
+	size_t cap = 0; // elements
+	cudaError_t ensure(size_t n)
+	{
+		if (n <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = std::max<size_t>(n, 1024);
+		cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinnedBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t bytes)
+	{
+		if (bytes <= cap) return cudaSuccess;
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = std::max<size_t>(bytes, 1 << 16);
+		cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct gscan_batch {
+	struct HostUnit { uint64_t base_off; uint32_t file_id; uint32_t len; };
+	std::vector<HostUnit> units; // device-unit order (zero-length units dropped), == caller order
+	TileDesc *d_tiles = nullptr;
+	DevUnit *d_units = nullptr;
+	uint8_t *d_arena = nullptr;  // staged copies of host units (owned)
+	uint32_t n_tiles = 0;
+	uint64_t bytes = 0;
+	float h2d_ms = 0;
+};
+
+struct gscan_ctx {
+	int device = 0;
+	int num_sms = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	std::string err;
+	gscan_stats stats;
+
+	DevBuf<SegEntry> segs;
+	DevBuf<Cand> cand;
+	DevBuf<Cand> scratch;
+	DevBuf<OutRec> ord, out;
+	DevBuf<uint32_t> unit_start, blk;
+	DevBuf<unsigned long long> cursor; // [0] cursor, then 2 x u32 totals behind it
+	DevBuf<uint8_t> pat_tables;
+	uint64_t pat_id = 0;
+	FixedParams pat_fixed; // with this context's device pointers
+	PinnedBuf readback, out_host, stage[2];
+	DevBuf<unsigned long long> probe_sum;
+	DevBuf<uint8_t> needle;
+};
+
+static thread_local std::string g_last_error;
+
+static int fail(gscan_ctx *ctx, const std::string &msg)
+{
+	if (ctx) ctx->err = msg;
+	g_last_error = msg;
+	return -1;
+}
+
+#define CK(ctx, call)                                                                                  \
+	do {                                                                                               \
+		cudaError_t e__ = (call);                                                                      \
+		if (e__ != cudaSuccess)                                                                        \
+			return fail(ctx, std::string("gscan: ") + #call + ": " + cudaGetErrorString(e__));        \
+	} while (0)
+
+static inline uint32_t rep4(uint8_t b) { return (uint32_t)b * 0x01010101u; }
+static inline uint32_t round16(uint32_t x) { return (x + 15u) & ~15u; }
+
+// ------------------------------------------------------------------------------------------
+// pattern
+// ------------------------------------------------------------------------------------------
+extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gscan_pattern **out)
+{
+	if (!pattern || !out) { g_last_error = "gscan_compile: null argument"; return -1; }
+	*out = nullptr;
+	gscan_pattern *p = new (std::nothrow) gscan_pattern;
+	if (!p) { g_last_error = "gscan_compile: out of memory"; return -1; }
+	std::string err;
+	if (!compile_pattern(pattern, len, flags, p->prog, err)) {
+		g_last_error = "gscan_compile: " + err;
+		delete p;
+		return -1;
+	}
+	const Program &pr = p->prog;
+	memset(&p->fixed, 0, sizeof(p->fixed));
+	memset(&p->run, 0, sizeof(p->run));
+	if (pr.kind == ENGINE_FIXED) {
+		FixedParams &F = p->fixed;
+		F.ntests = (uint32_t)pr.tests.size();
+		for (int k = 0; k < 8; k++) { // unused slots: a test no byte can pass
+			F.m0[k] = 0; F.v0[k] = 0xffffffffu; F.m1[k] = 0; F.v1[k] = 0;
+		}
+		for (size_t k = 0; k < pr.tests.size(); k++) {
+			F.m0[k] = rep4(pr.tests[k].m0); F.v0[k] = rep4(pr.tests[k].v0);
+			F.m1[k] = rep4(pr.tests[k].m1); F.v1[k] = rep4(pr.tests[k].v1);
+		}
+		F.anchor = (uint32_t)pr.anchor;
+		F.nseq = (uint32_t)pr.seqs.size();
+		F.maxlen = (uint32_t)pr.maxlen;
+		bool uniform = true;
+		for (auto &s : pr.seqs) uniform = uniform && s.size() == pr.seqs[0].size();
+		F.uniform_len = uniform ? (uint32_t)pr.seqs[0].size() : 0u;
+		std::vector<ByteSet> classes;
+		for (auto &s : pr.seqs) {
+			p->seq_len.push_back((uint16_t)s.size());
+			p->seq_off.push_back((uint32_t)p->seq_pos.size());
+			for (auto &cls : s) {
+				MaskedEq e = masked_superset(cls);
+				if (e.exact) {
+					p->seq_pos.push_back((uint32_t)e.mask | ((uint32_t)e.val << 8) | (0xffffu << 16));
+				} else {
+					size_t id = 0;
+					for (; id < classes.size(); id++) if (classes[id] == cls) break;
+					if (id == classes.size()) classes.push_back(cls);
+					p->seq_pos.push_back((uint32_t)id << 16);
+				}
+			}
+		}
+		for (auto &c : classes) for (int i = 0; i < 8; i++) p->cls_bm.push_back(c.w[i]);
+		p->pre = std::max(16u, round16((uint32_t)pr.anchor));
+		p->post = round16((uint32_t)std::max(pr.maxlen - pr.anchor, 4) + 16u);
+	} else if (pr.kind == ENGINE_RUN) {
+		RunParams &R = p->run;
+		R.nlo = (uint32_t)pr.ranges_low.size();
+		R.nhi = (uint32_t)pr.ranges_high.size();
+		for (size_t i = 0; i < pr.ranges_low.size(); i++) {
+			R.add_ge_lo[i] = rep4((uint8_t)(0x80 - pr.ranges_low[i].lo));
+			R.add_gt_lo[i] = rep4((uint8_t)(0x7f - pr.ranges_low[i].hi));
+		}
+		for (size_t i = 0; i < pr.ranges_high.size(); i++) {
+			R.add_ge_hi[i] = rep4((uint8_t)(0x80 - (pr.ranges_high[i].lo - 0x80)));
+			R.add_gt_hi[i] = rep4((uint8_t)(0x7f - (pr.ranges_high[i].hi - 0x80)));
+		}
+		R.run_min = (uint32_t)pr.run_min;
+		for (int i = 0; i < 8; i++) R.bitmap[i] = pr.run_class.w[i];
+		p->pre = 16;
+		p->post = round16((uint32_t)pr.run_min + 32u);
+	}
+	if (p->pre > (uint32_t)kPreMax || p->post > (uint32_t)kPostMax) {
+		g_last_error = "gscan_compile: pattern too long for the shared-memory halo";
+		delete p;
+		return -1;
+	}
+	*out = p;
+	return 0;
+}
+
+extern "C" void gscan_free_pattern(gscan_pattern *p) { delete p; }
+extern "C" int gscan_minlen(const gscan_pattern *p) { return p ? p->prog.minlen : -1; }
+extern "C" const char *gscan_last_error(void) { return g_last_error.c_str(); }
+extern "C" int gscan_abi_version(void) { return GSCAN_ABI_VERSION; }
+
+extern "C" int gscan_pattern_get_info(const gscan_pattern *p, gscan_pattern_info *o)
+{
+	if (!p || !o) return -1;
+	o->minlen = p->prog.minlen;
+	o->maxlen = p->prog.maxlen;
+	o->captures = p->prog.captures;
+	o->engine = (int32_t)p->prog.kind;
+	o->n_sequences = (int32_t)p->prog.seqs.size();
+	o->n_filter_tests = (int32_t)p->prog.tests.size();
+	o->filter_anchor = p->prog.anchor;
+	o->filter_delta = p->prog.delta;
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+extern "C" gscan_ctx *gscan_open(int device)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		g_last_error = std::string("gscan_open: no CUDA device (") + cudaGetErrorString(e) +
+		               "): the scan has no CPU fallback";
+		return nullptr;
+	}
+	if (device < 0 || device >= n) { g_last_error = "gscan_open: bad device index"; return nullptr; }
+	gscan_ctx *c = new (std::nothrow) gscan_ctx;
+	if (!c) { g_last_error = "gscan_open: out of memory"; return nullptr; }
+	c->device = device;
+	memset(&c->stats, 0, sizeof(c->stats));
+	cudaDeviceProp prop;
+	if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+	    (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+		g_last_error = std::string("gscan_open: ") + cudaGetErrorString(e);
+		delete c;
+		return nullptr;
+	}
+	if (prop.major != 10) {
+		g_last_error = "gscan_open: this library is built for sm_100a (B200) only; device is sm_" +
+		               std::to_string(prop.major) + std::to_string(prop.minor);
+		cudaStreamDestroy(c->stream);
+		delete c;
+		return nullptr;
+	}
+	c->num_sms = prop.multiProcessorCount;
+	for (auto &ev : c->ev) cudaEventCreate(&ev);
+	return c;
+}
+
+extern "C" void gscan_close(gscan_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	c->segs.release(); c->cand.release(); c->scratch.release(); c->ord.release(); c->out.release();
+	c->unit_start.release(); c->blk.release(); c->cursor.release(); c->pat_tables.release();
+	c->probe_sum.release(); c->needle.release();
+	c->readback.release(); c->out_host.release(); c->stage[0].release(); c->stage[1].release();
+	for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" const char *gscan_why(const gscan_ctx *c) { return c ? c->err.c_str() : g_last_error.c_str(); }
+
+extern "C" int gscan_last_stats(const gscan_ctx *c, gscan_stats *o)
+{
+	if (!c || !o) return -1;
+	*o = c->stats;
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// batches
+// ------------------------------------------------------------------------------------------
+extern "C" void gscan_batch_free(gscan_ctx *ctx, gscan_batch *b)
+{
+	if (!b) return;
+	if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+	if (b->d_tiles) cudaFree(b->d_tiles);
+	if (b->d_units) cudaFree(b->d_units);
+	if (b->d_arena) cudaFree(b->d_arena);
+	delete b;
+}
+
+extern "C" int gscan_batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units, gscan_batch **out)
+{
+	if (!ctx || !out || (n_units && !units)) return fail(ctx, "gscan_batch_create: null argument");
+	*out = nullptr;
+	CK(ctx, cudaSetDevice(ctx->device));
+	gscan_batch *b = new (std::nothrow) gscan_batch;
+	if (!b) return fail(ctx, "gscan_batch_create: out of memory");
+	struct Guard { gscan_ctx *c; gscan_batch *b; ~Guard() { if (b) gscan_batch_free(c, b); } } guard{ctx, b};
+
+	// pass 1: validate, size the staging arena
+	uint64_t arena_bytes = 0, n_tiles64 = 0;
+	std::vector<uint64_t> arena_off(n_units, 0);
+	for (size_t i = 0; i < n_units; i++) {
+		const gscan_unit &u = units[i];
+		if (u.len == 0) continue;
+		if (u.len > (1ull << 31)) return fail(ctx, "gscan_batch_create: unit longer than 2 GiB (the reference's chunks are <= 1 GiB, grab.h:48)");
+		if (!u.ptr) return fail(ctx, "gscan_batch_create: unit with null pointer");
+		if (u.flags & GSCAN_UNIT_DEVICE) {
+			if ((uintptr_t)u.ptr & 15u) return fail(ctx, "gscan_batch_create: device unit pointer must be 16-byte aligned");
+		} else {
+			arena_off[i] = arena_bytes;
+			arena_bytes += (u.len + 255u) & ~255ull;
+		}
+		n_tiles64 += (u.len + kTileBytes - 1) / kTileBytes;
+	}
+	if (n_tiles64 >= (1ull << 27)) return fail(ctx, "gscan_batch_create: batch too large (more than 4 TiB of tiles)");
+	if (arena_bytes) CK(ctx, cudaMalloc(&b->d_arena, arena_bytes + 256));
+
+	// pass 2: stage host units, build tile and unit tables
+	std::vector<TileDesc> tiles;
+	std::vector<DevUnit> dunits;
+	tiles.reserve((size_t)n_tiles64);
+	auto t0 = std::chrono::steady_clock::now();
+	int sb = 0;
+	bool staged[2] = {false, false};
+	cudaEvent_t sev[2] = {ctx->ev[2], ctx->ev[3]};
+	for (size_t i = 0; i < n_units; i++) {
+		const gscan_unit &u = units[i];
+		if (u.len == 0) continue;
+		const uint8_t *dptr;
+		if (u.flags & GSCAN_UNIT_DEVICE) {
+			dptr = u.ptr;
+		} else {
+			uint8_t *dst = b->d_arena + arena_off[i];
+			dptr = dst;
+			cudaPointerAttributes attr;
+			bool pinned = cudaPointerGetAttributes(&attr, u.ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+			cudaGetLastError();
+			if (pinned) {
+				CK(ctx, cudaMemcpyAsync(dst, u.ptr, u.len, cudaMemcpyHostToDevice, ctx->stream));
+			} else {
+				// pageable memory (the reference's mmap windows): bounce through two pinned buffers
+				const size_t kChunk = 16u << 20;
+				for (uint64_t o = 0; o < u.len; o += kChunk) {
+					const size_t n = (size_t)std::min<uint64_t>(kChunk, u.len - o);
+					CK(ctx, ctx->stage[sb].ensure(kChunk));
+					if (staged[sb]) CK(ctx, cudaEventSynchronize(sev[sb]));
+					memcpy(ctx->stage[sb].p, u.ptr + o, n);
+					CK(ctx, cudaMemcpyAsync(dst + o, ctx->stage[sb].p, n, cudaMemcpyHostToDevice, ctx->stream));
+					CK(ctx, cudaEventRecord(sev[sb], ctx->stream));
+					staged[sb] = true;
+					sb ^= 1;
+				}
+			}
+		}
+		DevUnit du;
+		du.ptr = (uint64_t)(uintptr_t)dptr;
+		du.len = (uint32_t)u.len;
+		du.first_tile = (uint32_t)tiles.size();
+		const uint32_t unit_index = (uint32_t)dunits.size();
+		dunits.push_back(du);
+		b->units.push_back(gscan_batch::HostUnit{u.base_off, u.file_id, (uint32_t)u.len});
+		for (uint64_t off = 0; off < u.len; off += kTileBytes) {
+			TileDesc t;
+			t.src = du.ptr + off;
+			t.unit = unit_index;
+			t.off = (uint32_t)off;
+			t.len = (uint32_t)std::min<uint64_t>(kTileBytes, u.len - off);
+			t.ulen = (uint32_t)u.len;
+			t.pad[0] = t.pad[1] = 0;
+			tiles.push_back(t);
+		}
+		b->bytes += u.len;
+	}
+	b->n_tiles = (uint32_t)tiles.size();
+	if (!tiles.empty()) {
+		CK(ctx, cudaMalloc(&b->d_tiles, tiles.size() * sizeof(TileDesc)));
+		CK(ctx, cudaMalloc(&b->d_units, dunits.size() * sizeof(DevUnit)));
+		CK(ctx, cudaMemcpyAsync(b->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, ctx->stream));
+		CK(ctx, cudaMemcpyAsync(b->d_units, dunits.data(), dunits.size() * sizeof(DevUnit), cudaMemcpyHostToDevice, ctx->stream));
+	}
+	CK(ctx, cudaStreamSynchronize(ctx->stream)); // host buffers are consumed when this returns (grab.cc:215)
+	b->h2d_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	guard.b = nullptr;
+	*out = b;
+	return 0;
+}
+
+static int ensure_pattern(gscan_ctx *ctx, const gscan_pattern *pat)
+{
+	if (ctx->pat_id == pat->prog.id) return 0;
+	if (pat->prog.kind == ENGINE_FIXED) {
+		const size_t b_len = (pat->seq_len.size() * 2 + 15) & ~(size_t)15;
+		const size_t b_off = pat->seq_off.size() * 4, b_pos = pat->seq_pos.size() * 4, b_bm = pat->cls_bm.size() * 4;
+		const size_t total = b_len + b_off + b_pos + b_bm + 64;
+		CK(ctx, ctx->pat_tables.ensure(total));
+		uint8_t *d = ctx->pat_tables.p;
+		CK(ctx, cudaMemcpyAsync(d, pat->seq_len.data(), pat->seq_len.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+		CK(ctx, cudaMemcpyAsync(d + b_len, pat->seq_off.data(), b_off, cudaMemcpyHostToDevice, ctx->stream));
+		CK(ctx, cudaMemcpyAsync(d + b_len + b_off, pat->seq_pos.data(), b_pos, cudaMemcpyHostToDevice, ctx->stream));
+		if (b_bm) CK(ctx, cudaMemcpyAsync(d + b_len + b_off + b_pos, pat->cls_bm.data(), b_bm, cudaMemcpyHostToDevice, ctx->stream));
+		CK(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors may die with the pattern
+		ctx->pat_fixed = pat->fixed;
+		ctx->pat_fixed.seq_len = reinterpret_cast<const uint16_t *>(d);
+		ctx->pat_fixed.seq_off = reinterpret_cast<const uint32_t *>(d + b_len);
+		ctx->pat_fixed.seq_pos = reinterpret_cast<const uint32_t *>(d + b_len + b_off);
+		ctx->pat_fixed.cls_bm = reinterpret_cast<const uint32_t *>(d + b_len + b_off + b_pos);
+	}
+	ctx->pat_id = pat->prog.id;
+	return 0;
+}
+
+extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_batch *b, uint32_t mode,
+                                gscan_match **out, size_t *n_out)
+{
+	if (!ctx || !pat || !b || !out || !n_out) return fail(ctx, "gscan_batch_scan: null argument");
+	if (mode > GSCAN_MODE_LINE) return fail(ctx, "gscan_batch_scan: bad mode");
+	*out = nullptr;
+	*n_out = 0;
+	auto t0 = std::chrono::steady_clock::now();
+	CK(ctx, cudaSetDevice(ctx->device));
+	gscan_stats &S = ctx->stats;
+	memset(&S, 0, sizeof(S));
+	S.bytes_scanned = b->bytes;
+	S.n_units = (uint32_t)b->units.size();
+	S.n_tiles = b->n_tiles;
+	S.h2d_ms = b->h2d_ms;
+	if (pat->prog.kind == ENGINE_NONE || b->n_tiles == 0) {
+		S.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		return 0;
+	}
+	if (ensure_pattern(ctx, pat) < 0) return -1;
+
+	const uint32_t n_segs = b->n_tiles * kConsumerWarps;
+	const int grid = (int)std::min<uint32_t>((uint32_t)ctx->num_sms, b->n_tiles);
+	CK(ctx, ctx->segs.ensure(n_segs));
+	CK(ctx, ctx->scratch.ensure((size_t)ctx->num_sms * kConsumerWarps * kSubTileMax));
+	CK(ctx, ctx->cursor.ensure(2));
+	CK(ctx, ctx->readback.ensure(64));
+	if (ctx->cand.cap == 0) {
+		size_t want = std::min<size_t>(std::max<size_t>(b->bytes / 2048, 1u << 20), 64u << 20);
+		CK(ctx, ctx->cand.ensure(want));
+	}
+
+	ScanArgs A;
+	A.tiles = b->d_tiles;
+	A.n_tiles = b->n_tiles;
+	A.pre = pat->pre;
+	A.post = pat->post;
+	A.cursor = ctx->cursor.p;
+	A.segs = ctx->segs.p;
+	A.scratch = ctx->scratch.p;
+
+	unsigned long long *h_cursor = reinterpret_cast<unsigned long long *>(ctx->readback.p);
+	unsigned long long total_cand = 0;
+	for (int attempt = 0;; attempt++) {
+		A.cand = ctx->cand.p;
+		A.cand_cap = (uint32_t)std::min<size_t>(ctx->cand.cap, 0xffffffffu);
+		CK(ctx, cudaMemsetAsync(ctx->cursor.p, 0, 16, ctx->stream));
+		CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+		if (pat->prog.kind == ENGINE_FIXED) CK(ctx, launch_scan_fixed(A, ctx->pat_fixed, pat->prog.delta, grid, ctx->stream));
+		else CK(ctx, launch_scan_run(A, pat->run, grid, ctx->stream));
+		CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+		CK(ctx, cudaMemcpyAsync(h_cursor, ctx->cursor.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+		S.scan_kernel_ms += ms;
+		S.scan_launches++;
+		S.total_launches++;
+		total_cand = *h_cursor;
+		if (total_cand <= A.cand_cap) break;
+		// candidate buffer too small: never truncate -- grow to what the kernel asked for and re-scan
+		if (attempt >= 2 || total_cand >= 0xffffffffull)
+			return fail(ctx, "gscan_batch_scan: candidate buffer overflow (pattern matches almost everywhere); split the batch");
+		CK(ctx, ctx->cand.ensure((size_t)(total_cand + total_cand / 8 + 1024)));
+	}
+	S.n_candidates = total_cand;
+
+	size_t n = 0;
+	const OutRec *h_recs = nullptr;
+	if (total_cand) {
+		const uint32_t nb_seg = (n_segs + 2047) / 2048, nb_ord = (uint32_t)((total_cand + 2047) / 2048);
+		CK(ctx, ctx->ord.ensure((size_t)total_cand));
+		CK(ctx, ctx->out.ensure((size_t)total_cand));
+		CK(ctx, ctx->unit_start.ensure(b->units.size() + 1));
+		CK(ctx, ctx->blk.ensure((size_t)nb_seg + nb_ord + 4));
+		CK(ctx, ctx->out_host.ensure((size_t)total_cand * sizeof(OutRec)));
+		ResolveArgs R;
+		R.tiles = b->d_tiles;
+		R.segs = ctx->segs.p;
+		R.n_segs = n_segs;
+		R.cand = ctx->cand.p;
+		R.units = b->d_units;
+		R.n_units = (uint32_t)b->units.size();
+		R.ord = ctx->ord.p;
+		R.out = ctx->out.p;
+		R.unit_start = ctx->unit_start.p;
+		R.blk = ctx->blk.p;
+		R.totals = reinterpret_cast<uint32_t *>(ctx->cursor.p + 1);
+		R.mode = mode;
+		R.minlen = (uint32_t)pat->prog.minlen;
+		R.engine = (uint32_t)pat->prog.kind;
+		R.run_min = (uint32_t)pat->prog.run_min;
+		for (int i = 0; i < 8; i++) R.bitmap[i] = pat->prog.run_class.w[i];
+		R.total_cand = (uint32_t)total_cand;
+		uint32_t nl = 0;
+		CK(ctx, launch_resolve(R, ctx->stream, &nl));
+		S.total_launches += nl;
+		CK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+		uint32_t *h_tot = reinterpret_cast<uint32_t *>((uint8_t *)ctx->readback.p + 16);
+		CK(ctx, cudaMemcpyAsync(h_tot, R.totals, 8, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaMemcpyAsync(ctx->out_host.p, ctx->out.p, (size_t)total_cand * sizeof(OutRec), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+		S.resolve_ms = ms;
+		n = h_tot[1];
+		if (h_tot[0] != (uint32_t)total_cand) return fail(ctx, "gscan_batch_scan: internal: segment counts disagree with the cursor");
+		h_recs = reinterpret_cast<const OutRec *>(ctx->out_host.p);
+	}
+	gscan_match *m = nullptr;
+	if (n) {
+		m = (gscan_match *)malloc(n * sizeof(gscan_match));
+		if (!m) return fail(ctx, "gscan_batch_scan: out of memory for results");
+		for (size_t i = 0; i < n; i++) {
+			const gscan_batch::HostUnit &hu = b->units[h_recs[i].unit];
+			m[i].start = hu.base_off + h_recs[i].pos; // grab.cc:186: off + (start - content) + ovector[0]
+			m[i].file_id = hu.file_id;
+			m[i].match_len = h_recs[i].len;
+		}
+	}
+	*out = m;
+	*n_out = n;
+	S.n_matches = n;
+	S.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	return 0;
+}
+
+extern "C" int gscan_scan_batch(gscan_ctx *ctx, const gscan_pattern *pat, const gscan_unit *units, size_t n_units,
+                                uint32_t mode, gscan_match **out, size_t *n_out)
+{
+	if (!ctx || !pat || !out || !n_out) return fail(ctx, "gscan_scan_batch: null argument");
+	auto t0 = std::chrono::steady_clock::now();
+	gscan_batch *b = nullptr;
+	if (gscan_batch_create(ctx, units, n_units, &b) < 0) return -1;
+	int rc = gscan_batch_scan(ctx, pat, b, mode, out, n_out);
+	gscan_batch_free(ctx, b);
+	ctx->stats.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	return rc;
+}
+
+extern "C" void gscan_free_matches(gscan_ctx *, gscan_match *m) { free(m); }
+
+// ------------------------------------------------------------------------------------------
+// utilities
+// ------------------------------------------------------------------------------------------
+extern "C" void *gscan_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+extern "C" void gscan_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" void *gscan_device_alloc(gscan_ctx *ctx, size_t bytes)
+{
+	if (!ctx) return nullptr;
+	void *p = nullptr;
+	if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMalloc(&p, bytes) != cudaSuccess) {
+		fail(ctx, std::string("gscan_device_alloc: ") + cudaGetErrorString(cudaGetLastError()));
+		return nullptr;
+	}
+	return p;
+}
+extern "C" void gscan_device_free(gscan_ctx *ctx, void *d)
+{
+	if (ctx) cudaSetDevice(ctx->device);
+	if (d) cudaFree(d);
+}
+extern "C" int gscan_memcpy_d2h(gscan_ctx *ctx, void *dst, const void *dsrc, size_t bytes)
+{
+	if (!ctx) return -1;
+	CK(ctx, cudaSetDevice(ctx->device));
+	CK(ctx, cudaMemcpyAsync(dst, dsrc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+extern "C" int gscan_memcpy_h2d(gscan_ctx *ctx, void *ddst, const void *src, size_t bytes)
+{
+	if (!ctx) return -1;
+	CK(ctx, cudaSetDevice(ctx->device));
+	CK(ctx, cudaMemcpyAsync(ddst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+extern "C" int gscan_synth_corpus(gscan_ctx *ctx, void *dptr, uint64_t seed, uint64_t first_file_id, uint64_t n_files,
+                                  uint64_t file_len, uint64_t stride, const uint8_t *needle, uint32_t needle_len,
+                                  uint32_t needle_every)
+{
+	if (!ctx || !dptr) return fail(ctx, "gscan_synth_corpus: null argument");
+	if ((file_len & 15u) || (stride & 15u) || ((uintptr_t)dptr & 15u)) return fail(ctx, "gscan_synth_corpus: lengths and pointer must be multiples of 16");
+	CK(ctx, cudaSetDevice(ctx->device));
+	const uint8_t *dn = nullptr;
+	if (needle && needle_len && needle_every) {
+		CK(ctx, ctx->needle.ensure(needle_len));
+		CK(ctx, cudaMemcpyAsync(ctx->needle.p, needle, needle_len, cudaMemcpyHostToDevice, ctx->stream));
+		dn = ctx->needle.p;
+	}
+	CK(ctx, launch_synth_corpus((uint8_t *)dptr, seed, first_file_id, n_files, file_len, stride, dn, needle_len, needle_every, ctx->stream));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+extern "C" int gscan_read_probe(gscan_ctx *ctx, const void *dptr, uint64_t bytes, float *ms, uint64_t *checksum)
+{
+	if (!ctx || !dptr) return fail(ctx, "gscan_read_probe: null argument");
+	CK(ctx, cudaSetDevice(ctx->device));
+	CK(ctx, ctx->probe_sum.ensure(1));
+	CK(ctx, cudaMemsetAsync(ctx->probe_sum.p, 0, 8, ctx->stream));
+	CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+	CK(ctx, launch_read_probe(dptr, bytes, ctx->probe_sum.p, ctx->num_sms * 4, ctx->stream));
+	CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+	unsigned long long h = 0;
+	CK(ctx, cudaMemcpyAsync(&h, ctx->probe_sum.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	float t = 0;
+	cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]);
+	if (ms) *ms = t;
+	if (checksum) *checksum = h;
+	return 0;
+}

@@ -1,0 +1,45 @@
+// kernels.h -- host-callable launchers of the CUDA kernels (scan_kernels.cu, resolve_kernels.cu,
+// corpus_gen.cu).  Internal to libgscan.so; the public surface is include/gscan.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "device_types.h"
+
+namespace gscan {
+
+size_t scan_smem_bytes();
+cudaError_t launch_scan_fixed(const ScanArgs &A, const FixedParams &P, int delta, int grid, cudaStream_t st);
+cudaError_t launch_scan_run(const ScanArgs &A, const RunParams &P, int grid, cudaStream_t st);
+
+struct DevUnit {
+	uint64_t ptr;        // device address of the unit's bytes
+	uint32_t len;
+	uint32_t first_tile; // index of the unit's first tile
+};
+
+struct ResolveArgs {
+	const TileDesc *tiles;
+	const SegEntry *segs;
+	uint32_t n_segs;
+	const Cand *cand;
+	const DevUnit *units;
+	uint32_t n_units;
+	OutRec *ord;          // candidates in (unit, pos) order; pad = keep flag after selection
+	OutRec *out;          // selected matches, same order
+	uint32_t *unit_start; // [n_units + 1]
+	uint32_t *blk;        // block-sum scratch
+	uint32_t *totals;     // [0] candidates, [1] matches
+	uint32_t mode, minlen, engine, run_min;
+	uint32_t bitmap[8];   // RUN class, for match-length extension
+	uint32_t total_cand;  // known on the host after the scan kernel
+};
+// returns the number of kernels launched through *launches
+cudaError_t launch_resolve(const ResolveArgs &R, cudaStream_t st, uint32_t *launches);
+
+cudaError_t launch_synth_corpus(uint8_t *dptr, uint64_t seed, uint64_t first_file_id, uint64_t n_files, uint64_t file_len,
+                                uint64_t stride, const uint8_t *d_needle, uint32_t needle_len, uint32_t needle_every,
+                                cudaStream_t st);
+cudaError_t launch_read_probe(const void *dptr, uint64_t bytes, unsigned long long *d_sum, int grid, cudaStream_t st);
+
+} // namespace gscan

@@ -1,0 +1,749 @@
+// pattern.cc -- see pattern.h.  Host C++ only (no CUDA).
+#include "pattern.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <memory>
+
+#include "../../include/gscan.h"
+
+namespace gscan {
+
+// ------------------------------------------------------------------------------------------
+// byte-class helpers
+// ------------------------------------------------------------------------------------------
+
+MaskedEq masked_superset(const ByteSet &s)
+{
+	MaskedEq r{0, 0, false, 256};
+	int first = -1;
+	unsigned varying = 0;
+	for (int c = 0; c < 256; c++) {
+		if (!s.has(c)) continue;
+		if (first < 0) first = c;
+		varying |= (unsigned)(c ^ first);
+	}
+	if (first < 0) { r.mask = 0xff; r.val = 0; r.size = 0; r.exact = false; return r; }
+	r.mask = (uint8_t)(~varying & 0xff);
+	r.val = (uint8_t)(first & r.mask);
+	r.size = 1 << __builtin_popcount(varying & 0xff);
+	r.exact = (r.size == s.count());
+	return r;
+}
+
+std::vector<ByteRange> to_ranges(const ByteSet &s)
+{
+	std::vector<ByteRange> out;
+	int c = 0;
+	while (c < 256) {
+		if (!s.has(c)) { c++; continue; }
+		int lo = c;
+		while (c < 256 && s.has(c)) c++;
+		out.push_back(ByteRange{(uint8_t)lo, (uint8_t)(c - 1)});
+	}
+	return out;
+}
+
+namespace {
+
+bool is_upper(unsigned c) { return c >= 'A' && c <= 'Z'; }
+bool is_lower(unsigned c) { return c >= 'a' && c <= 'z'; }
+bool is_alpha(unsigned c) { return is_upper(c) || is_lower(c); }
+bool is_digit(unsigned c) { return c >= '0' && c <= '9'; }
+bool is_alnum(unsigned c) { return is_alpha(c) || is_digit(c); }
+bool is_word(unsigned c) { return is_alnum(c) || c == '_'; }
+bool is_space(unsigned c) { return c == ' ' || (c >= 9 && c <= 13); }
+bool is_xdigit(unsigned c) { return is_digit(c) || (c >= 'a' && c <= 'f') || (c >= 'A' && c <= 'F'); }
+bool is_punct(unsigned c) { return c > 32 && c < 127 && !is_alnum(c); }
+bool is_print(unsigned c) { return c >= 32 && c < 127; }
+bool is_graph(unsigned c) { return c > 32 && c < 127; }
+bool is_cntrl(unsigned c) { return c < 32 || c == 127; }
+bool is_blank(unsigned c) { return c == ' ' || c == '\t'; }
+
+ByteSet from_pred(bool (*p)(unsigned), bool negate = false)
+{
+	ByteSet s;
+	for (unsigned c = 0; c < 256; c++)
+		if (p(c) != negate) s.add(c);
+	return s;
+}
+
+void fold_case(ByteSet &s)
+{
+	for (unsigned c = 'a'; c <= 'z'; c++) {
+		if (s.has(c)) s.add(c - 32);
+		if (s.has(c - 32)) s.add(c);
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// syntax tree
+// ------------------------------------------------------------------------------------------
+
+struct Node;
+typedef std::unique_ptr<Node> NodeP;
+
+struct Node {
+	enum Kind { SET, CAT, ALT, REP, GROUP, ASSERT, EMPTY } kind;
+	ByteSet set;
+	std::vector<NodeP> kids;
+	uint32_t rmin = 0, rmax = 0; // rmax == UINT32_MAX: unbounded
+	bool lazy = false, possessive = false;
+	bool capturing = false;
+	explicit Node(Kind k) : kind(k) {}
+};
+
+constexpr uint32_t kInf = UINT32_MAX;
+
+struct Flags { bool icase = false, dotall = false, multiline = false; };
+
+class Parser {
+public:
+	Parser(const uint8_t *p, size_t n) : p_(p), end_(p + n) {}
+	NodeP parse(std::string &err)
+	{
+		NodeP r = alternation(Flags());
+		if (ok_ && p_ < end_) fail("unmatched )");
+		if (!ok_) { err = err_; return nullptr; }
+		return r;
+	}
+	int captures() const { return captures_; }
+
+private:
+	const uint8_t *p_, *end_;
+	bool ok_ = true;
+	std::string err_;
+	int captures_ = 0, depth_ = 0;
+
+	void fail(const char *m) { if (ok_) { ok_ = false; err_ = m; } }
+	bool more() const { return p_ < end_; }
+
+	static int hex(int c)
+	{
+		if (c >= '0' && c <= '9') return c - '0';
+		if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+		if (c >= 'A' && c <= 'F') return c - 'A' + 10;
+		return -1;
+	}
+
+	// after '\': 1 = single byte in ch, 2 = class in set, 3 = assertion (unsupported by the device engines)
+	int escape(bool in_class, unsigned &ch, ByteSet &set)
+	{
+		if (!more()) { fail("\\ at end of pattern"); return 0; }
+		unsigned c = *p_++;
+		switch (c) {
+		case 'd': set = from_pred(is_digit); return 2;
+		case 'D': set = from_pred(is_digit, true); return 2;
+		case 'w': set = from_pred(is_word); return 2;
+		case 'W': set = from_pred(is_word, true); return 2;
+		case 's': set = from_pred(is_space); return 2;
+		case 'S': set = from_pred(is_space, true); return 2;
+		case 'h': set = ByteSet(); set.add(' '); set.add('\t'); set.add(0xa0); return 2;
+		case 'H': set = ByteSet(); set.add(' '); set.add('\t'); set.add(0xa0); set.invert(); return 2;
+		case 'v': set = ByteSet(); set.add_range(10, 13); set.add(0x85); return 2;
+		case 'V': set = ByteSet(); set.add_range(10, 13); set.add(0x85); set.invert(); return 2;
+		case 'N':
+			if (in_class) { fail("\\N is not allowed in a class"); return 0; }
+			set = ByteSet(); set.invert(); set.w[0] &= ~(1u << 10); return 2;
+		case 'n': ch = '\n'; return 1;
+		case 't': ch = '\t'; return 1;
+		case 'r': ch = '\r'; return 1;
+		case 'f': ch = '\f'; return 1;
+		case 'a': ch = 7; return 1;
+		case 'e': ch = 27; return 1;
+		case 'c': {
+			if (!more()) { fail("\\c at end of pattern"); return 0; }
+			unsigned x = *p_++;
+			if (is_lower(x)) x -= 32;
+			ch = x ^ 0x40;
+			return 1;
+		}
+		case 'x': {
+			unsigned v = 0;
+			if (more() && *p_ == '{') {
+				const uint8_t *q = p_ + 1;
+				int nd = 0;
+				while (q < end_ && hex(*q) >= 0) { v = v * 16 + (unsigned)hex(*q); q++; nd++; if (v > 255) break; }
+				if (q >= end_ || *q != '}' || nd == 0 || v > 255) { fail("bad \\x{..} (bytes only)"); return 0; }
+				p_ = q + 1;
+			} else {
+				for (int nd = 0; nd < 2 && more() && hex(*p_) >= 0; nd++) v = v * 16 + (unsigned)hex(*p_++);
+			}
+			ch = v;
+			return 1;
+		}
+		case '0': {
+			unsigned v = 0;
+			for (int nd = 0; nd < 2 && more() && *p_ >= '0' && *p_ <= '7'; nd++) v = v * 8 + (unsigned)(*p_++ - '0');
+			ch = v & 255;
+			return 1;
+		}
+		case 'b':
+			if (in_class) { ch = 8; return 1; }
+			return 3;
+		case 'B': case 'A': case 'z': case 'Z': case 'G':
+			if (in_class) { fail("assertion escape inside a class"); return 0; }
+			return 3;
+		default:
+			if (c >= '1' && c <= '9') { fail("back references are not supported"); return 0; }
+			if (is_alnum(c)) { fail("unsupported escape sequence"); return 0; }
+			ch = c;
+			return 1;
+		}
+	}
+
+	NodeP make_char(unsigned c, const Flags &f)
+	{
+		NodeP n(new Node(Node::SET));
+		n->set.add(c);
+		if (f.icase) fold_case(n->set);
+		return n;
+	}
+
+	NodeP char_class(const Flags &f)
+	{
+		static const struct { const char *name; bool (*pred)(unsigned); } posix[] = {
+			{"alpha", is_alpha}, {"digit", is_digit}, {"alnum", is_alnum}, {"upper", is_upper}, {"lower", is_lower},
+			{"space", is_space}, {"xdigit", is_xdigit}, {"punct", is_punct}, {"print", is_print},
+			{"graph", is_graph}, {"cntrl", is_cntrl}, {"blank", is_blank}, {"word", is_word}};
+		NodeP n(new Node(Node::SET));
+		bool negate = false, first = true;
+		if (more() && *p_ == '^') { negate = true; p_++; }
+		for (;;) {
+			if (!more()) { fail("missing terminating ] for character class"); return n; }
+			unsigned c = *p_;
+			if (c == ']' && !first) { p_++; break; }
+			first = false;
+			unsigned lo = 0;
+			if (c == '[' && p_ + 1 < end_ && p_[1] == ':') {
+				const uint8_t *q = p_ + 2;
+				bool neg = false;
+				if (q < end_ && *q == '^') { neg = true; q++; }
+				const uint8_t *name = q;
+				while (q < end_ && is_lower(*q)) q++;
+				if (q + 1 < end_ && q[0] == ':' && q[1] == ']') {
+					bool found = false;
+					for (auto &pc : posix)
+						if (strlen(pc.name) == (size_t)(q - name) && !memcmp(pc.name, name, (size_t)(q - name))) {
+							n->set.unite(from_pred(pc.pred, neg));
+							found = true;
+						}
+					if (!found) { fail("unknown POSIX class name"); return n; }
+					p_ = q + 2;
+					continue;
+				}
+			}
+			if (c == '\\') {
+				p_++;
+				ByteSet t;
+				unsigned ch = 0;
+				int k = escape(true, ch, t);
+				if (k == 0) return n;
+				if (k == 2) { n->set.unite(t); continue; }
+				lo = ch;
+			} else {
+				lo = c;
+				p_++;
+			}
+			if (p_ + 1 < end_ && p_[0] == '-' && p_[1] != ']') {
+				const uint8_t *save = p_;
+				p_++;
+				unsigned hi = 0;
+				if (*p_ == '\\') {
+					p_++;
+					ByteSet t;
+					int k = escape(true, hi, t);
+					if (k == 0) return n;
+					if (k == 2) { n->set.add(lo); n->set.add('-'); n->set.unite(t); continue; }
+				} else if (*p_ == '[' && p_ + 1 < end_ && p_[1] == ':') {
+					p_ = save;
+					n->set.add(lo);
+					continue;
+				} else {
+					hi = *p_++;
+				}
+				if (hi < lo) { fail("range out of order in character class"); return n; }
+				n->set.add_range(lo, hi);
+			} else {
+				n->set.add(lo);
+			}
+		}
+		if (f.icase) fold_case(n->set);
+		if (negate) n->set.invert();
+		return n;
+	}
+
+	// 1: quantifier consumed, 0: '{' is a literal, -1: error
+	int braces(uint32_t &mn, uint32_t &mx)
+	{
+		const uint8_t *q = p_ + 1;
+		if (q >= end_ || !is_digit(*q)) return 0;
+		unsigned long a = 0, b = 0;
+		while (q < end_ && is_digit(*q)) { a = a * 10 + (unsigned long)(*q++ - '0'); if (a > 65535) return -1; }
+		if (q < end_ && *q == '}') { mn = mx = (uint32_t)a; p_ = q + 1; return 1; }
+		if (q >= end_ || *q != ',') return 0;
+		q++;
+		if (q < end_ && *q == '}') { mn = (uint32_t)a; mx = kInf; p_ = q + 1; return 1; }
+		if (q >= end_ || !is_digit(*q)) return 0;
+		while (q < end_ && is_digit(*q)) { b = b * 10 + (unsigned long)(*q++ - '0'); if (b > 65535) return -1; }
+		if (q >= end_ || *q != '}') return 0;
+		if (b < a) return -1;
+		mn = (uint32_t)a; mx = (uint32_t)b; p_ = q + 1;
+		return 1;
+	}
+
+	// returns nullptr with flag_only set when the atom was an inline option like (?i)
+	NodeP atom(Flags &f, bool &flag_only)
+	{
+		flag_only = false;
+		unsigned c = *p_++;
+		switch (c) {
+		case '(': {
+			bool capturing = true;
+			Flags inner = f;
+			if (more() && *p_ == '?') {
+				p_++;
+				if (!more()) { fail("unterminated (?"); return nullptr; }
+				if (*p_ == ':') { capturing = false; p_++; }
+				else if (*p_ == 'P' && p_ + 1 < end_ && p_[1] == '<') {
+					p_ += 2;
+					while (more() && *p_ != '>') p_++;
+					if (!more()) { fail("unterminated group name"); return nullptr; }
+					p_++;
+				} else if ((*p_ == '<' || *p_ == '\'') && p_ + 1 < end_ && p_[1] != '=' && p_[1] != '!') {
+					unsigned close = *p_ == '<' ? '>' : '\'';
+					p_++;
+					while (more() && *p_ != close) p_++;
+					if (!more()) { fail("unterminated group name"); return nullptr; }
+					p_++;
+				} else if (strchr("=!<>|#R(&C+0123456789", (int)*p_)) {
+					fail("lookaround / atomic / recursive / conditional groups are not supported by the device engines");
+					return nullptr;
+				} else {
+					bool on = true;
+					Flags nf = f;
+					for (;;) {
+						if (!more()) { fail("unterminated inline option"); return nullptr; }
+						unsigned o = *p_++;
+						if (o == '-') { on = false; continue; }
+						if (o == 'i') { nf.icase = on; continue; }
+						if (o == 's') { nf.dotall = on; continue; }
+						if (o == 'm') { nf.multiline = on; continue; }
+						if (o == ')') { f = nf; flag_only = true; return nullptr; }
+						if (o == ':') { inner = nf; capturing = false; break; }
+						fail("unsupported inline option");
+						return nullptr;
+					}
+				}
+			}
+			if (capturing) captures_++;
+			if (++depth_ > 200) { fail("parentheses nested too deeply"); return nullptr; }
+			NodeP body = alternation(inner);
+			depth_--;
+			if (!ok_) return nullptr;
+			if (!more() || *p_ != ')') { fail("missing )"); return nullptr; }
+			p_++;
+			NodeP g(new Node(Node::GROUP));
+			g->capturing = capturing;
+			g->kids.push_back(std::move(body));
+			return g;
+		}
+		case '[': return char_class(f);
+		case '.': {
+			NodeP n(new Node(Node::SET));
+			n->set.invert();
+			if (!f.dotall) n->set.w[0] &= ~(1u << 10);
+			return n;
+		}
+		case '^': case '$': return NodeP(new Node(Node::ASSERT));
+		case '\\': {
+			if (more() && *p_ == 'Q') {
+				p_++;
+				NodeP cat(new Node(Node::CAT));
+				while (more()) {
+					if (p_ + 1 < end_ && p_[0] == '\\' && p_[1] == 'E') { p_ += 2; break; }
+					cat->kids.push_back(make_char(*p_++, f));
+				}
+				return cat;
+			}
+			if (more() && *p_ == 'E') { p_++; return NodeP(new Node(Node::EMPTY)); }
+			ByteSet t;
+			unsigned ch = 0;
+			int k = escape(false, ch, t);
+			if (k == 0) return nullptr;
+			if (k == 1) return make_char(ch, f);
+			if (k == 2) { NodeP n(new Node(Node::SET)); n->set = t; return n; }
+			return NodeP(new Node(Node::ASSERT));
+		}
+		case '*': case '+': case '?':
+			fail("quantifier does not follow a repeatable item");
+			return nullptr;
+		default: return make_char(c, f);
+		}
+	}
+
+	NodeP concatenation(Flags &f)
+	{
+		NodeP cat(new Node(Node::CAT));
+		while (ok_ && more() && *p_ != '|' && *p_ != ')') {
+			bool flag_only = false;
+			NodeP a = atom(f, flag_only);
+			if (!ok_) break;
+			if (flag_only) continue;
+			if (!a) break;
+			if (more()) {
+				uint32_t mn = 0, mx = 0;
+				bool q = false;
+				if (*p_ == '*') { mn = 0; mx = kInf; p_++; q = true; }
+				else if (*p_ == '+') { mn = 1; mx = kInf; p_++; q = true; }
+				else if (*p_ == '?') { mn = 0; mx = 1; p_++; q = true; }
+				else if (*p_ == '{') {
+					int r = braces(mn, mx);
+					if (r < 0) { fail("bad {n,m} quantifier"); break; }
+					q = r == 1;
+				}
+				if (q) {
+					NodeP r(new Node(Node::REP));
+					r->rmin = mn;
+					r->rmax = mx;
+					if (more() && *p_ == '?') { r->lazy = true; p_++; }
+					else if (more() && *p_ == '+') { r->possessive = true; p_++; }
+					if (a->kind == Node::ASSERT) { fail("quantified assertion"); break; }
+					r->kids.push_back(std::move(a));
+					a = std::move(r);
+				}
+			}
+			cat->kids.push_back(std::move(a));
+		}
+		return cat;
+	}
+
+	NodeP alternation(Flags f)
+	{
+		NodeP alt(new Node(Node::ALT));
+		Flags cur = f;
+		for (;;) {
+			alt->kids.push_back(concatenation(cur));
+			if (!ok_) break;
+			if (more() && *p_ == '|') { p_++; continue; }
+			break;
+		}
+		if (alt->kids.size() == 1) return std::move(alt->kids[0]);
+		return alt;
+	}
+};
+
+// ------------------------------------------------------------------------------------------
+// analysis
+// ------------------------------------------------------------------------------------------
+
+uint64_t min_length(const Node *n)
+{
+	uint64_t m = 0;
+	switch (n->kind) {
+	case Node::EMPTY: case Node::ASSERT: return 0;
+	case Node::SET: return 1;
+	case Node::CAT: for (auto &k : n->kids) m += min_length(k.get()); return m;
+	case Node::ALT:
+		m = UINT64_MAX;
+		for (auto &k : n->kids) m = std::min(m, min_length(k.get()));
+		return m;
+	case Node::REP: return (uint64_t)n->rmin * min_length(n->kids[0].get());
+	case Node::GROUP: return min_length(n->kids[0].get());
+	}
+	return 0;
+}
+
+bool has_assert(const Node *n)
+{
+	if (n->kind == Node::ASSERT) return true;
+	for (auto &k : n->kids) if (has_assert(k.get())) return true;
+	return false;
+}
+
+// strips groups and single-child CAT/ALT wrappers
+const Node *peel(const Node *n)
+{
+	for (;;) {
+		if (n->kind == Node::GROUP) { n = n->kids[0].get(); continue; }
+		if ((n->kind == Node::CAT || n->kind == Node::ALT) && n->kids.size() == 1) { n = n->kids[0].get(); continue; }
+		return n;
+	}
+}
+
+struct Expander {
+	size_t budget_seqs = kMaxSequences;
+	size_t budget_bytes = 1u << 20;
+	bool overflow = false;
+	std::string why;
+
+	typedef std::vector<Sequence> List;
+
+	bool charge(const List &l)
+	{
+		if (l.size() > budget_seqs) { overflow = true; why = "pattern expands to too many alternatives"; return false; }
+		size_t b = 0;
+		for (auto &s : l) {
+			b += s.size();
+			if (s.size() > (size_t)kMaxPatternLen) { overflow = true; why = "alternative longer than 1024 bytes"; return false; }
+		}
+		if (b > budget_bytes) { overflow = true; why = "pattern expands to too many bytes"; return false; }
+		return true;
+	}
+
+	// ordered product a x b (a-major: PCRE backtracks the right-hand side first)
+	List product(const List &a, const List &b)
+	{
+		List out;
+		if (overflow) return out;
+		if (a.size() * b.size() > budget_seqs) { overflow = true; why = "pattern expands to too many alternatives"; return out; }
+		out.reserve(a.size() * b.size());
+		for (auto &x : a)
+			for (auto &y : b) {
+				Sequence s = x;
+				s.insert(s.end(), y.begin(), y.end());
+				out.push_back(std::move(s));
+			}
+		charge(out);
+		return out;
+	}
+
+	// alternatives of `count` more iterations of `body` having done `done`, in backtracking order
+	List rest(const List &body, uint32_t done, uint32_t mn, uint32_t mx, bool lazy)
+	{
+		List out;
+		if (overflow) return out;
+		List more;
+		if (done < mx) more = product(body, rest(body, done + 1, mn, mx, lazy));
+		List stop;
+		if (done >= mn) stop.push_back(Sequence());
+		if (lazy) { out = stop; out.insert(out.end(), more.begin(), more.end()); }
+		else { out = more; out.insert(out.end(), stop.begin(), stop.end()); }
+		charge(out);
+		return out;
+	}
+
+	List expand(const Node *n)
+	{
+		List out;
+		if (overflow) return out;
+		switch (n->kind) {
+		case Node::EMPTY: out.push_back(Sequence()); return out;
+		case Node::ASSERT: overflow = true; why = "assertions (^ $ \\b ...) are not supported by the device engines"; return out;
+		case Node::SET:
+			if (n->set.empty()) return out; // can never match: contributes no alternative
+			out.push_back(Sequence(1, n->set));
+			return out;
+		case Node::GROUP: return expand(n->kids[0].get());
+		case Node::CAT: {
+			out.push_back(Sequence());
+			for (auto &k : n->kids) {
+				out = product(out, expand(k.get()));
+				if (overflow) break;
+			}
+			return out;
+		}
+		case Node::ALT:
+			for (auto &k : n->kids) {
+				List l = expand(k.get());
+				out.insert(out.end(), l.begin(), l.end());
+				if (!charge(out)) break;
+			}
+			return out;
+		case Node::REP: {
+			if (n->rmax == kInf) {
+				overflow = true;
+				why = "unbounded repeat (* + {n,}) is only supported as a whole-pattern byte-class run like [a-z]{4,}";
+				return out;
+			}
+			List body = expand(n->kids[0].get());
+			if (overflow) return out;
+			// a possessive bounded repeat of single-byte bodies behaves like greedy without give-back;
+			// expanding it as greedy could add matches PCRE would not find, so refuse
+			if (n->possessive) { overflow = true; why = "possessive quantifier on a bounded repeat is not supported"; return out; }
+			return rest(body, 0, n->rmin, n->rmax, n->lazy);
+		}
+		}
+		return out;
+	}
+};
+
+// crude byte-frequency prior (text / source code) used only to pick the rarest filter bytes
+double byte_prior(unsigned c)
+{
+	static const char *common = " etaoinsrhldcumfpgwybvkxjqz";
+	if (c == ' ') return 0.15;
+	if (c == '\n') return 0.02;
+	if (is_lower(c)) {
+		const char *p = strchr(common, (int)c);
+		int rank = p ? (int)(p - common) : 26;
+		return 0.09 * (1.0 - rank / 30.0) + 0.002;
+	}
+	if (is_upper(c)) return 0.004;
+	if (is_digit(c)) return 0.006;
+	if (c > 32 && c < 127) return 0.004;
+	if (c == '\t') return 0.005;
+	if (c == 0) return 0.002;
+	return 0.0005;
+}
+
+double test_prior(const MaskedEq &m)
+{
+	double p = 0;
+	for (unsigned c = 0; c < 256; c++)
+		if ((c & m.mask) == m.val) p += byte_prior(c);
+	return p;
+}
+
+// can sequence b match `shift` bytes after sequence a started, with both matches overlapping?
+bool can_overlap(const Sequence &a, const Sequence &b, size_t shift)
+{
+	for (size_t i = 0; shift + i < a.size() && i < b.size(); i++)
+		if (!a[shift + i].intersects(b[i])) return false;
+	return true;
+}
+
+std::atomic<uint64_t> g_next_id{1};
+
+} // namespace
+
+bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, std::string &err)
+{
+	out = Program();
+	out.id = g_next_id.fetch_add(1);
+	out.strict_q2 = (flags & GSCAN_STRICT_REF) != 0;
+	if (memchr(pat, 0, len)) { err = "pattern contains a NUL byte (the reference passes a C string, grab.cc:106)"; return false; }
+
+	NodeP root;
+	int captures = 0;
+	if (flags & GSCAN_LITERAL) {
+		root.reset(new Node(Node::CAT));
+		for (size_t i = 0; i < len; i++) {
+			NodeP n(new Node(Node::SET));
+			n->set.add((uint8_t)pat[i]);
+			root->kids.push_back(std::move(n));
+		}
+	} else {
+		Parser ps((const uint8_t *)pat, len);
+		root = ps.parse(err);
+		if (!root) return false;
+		captures = ps.captures();
+	}
+	out.captures = captures;
+
+	uint64_t ml = min_length(root.get());
+	if (ml == 0) {
+		err = "pattern can match the empty string: the reference never terminates on it (grab.cc:209); rejected";
+		return false;
+	}
+	out.minlen = ml > 65535 ? 65535 : (int)ml; // PCRE2's study caps MINLENGTH at 65535
+
+	if (out.strict_q2 && captures > 0) {
+		// Q2: pcre_exec returns 0 for every match => the loop breaks before printing (grab.cc:179)
+		out.kind = ENGINE_NONE;
+		out.maxlen = -1;
+		return true;
+	}
+	if (has_assert(root.get())) {
+		err = "assertions (^ $ \\b \\B \\A \\z \\Z) are not supported by the device engines";
+		return false;
+	}
+
+	// RUN: the whole pattern is one byte class repeated {n,}
+	const Node *core = peel(root.get());
+	if (core->kind == Node::REP && core->rmax == kInf && !core->lazy) {
+		const Node *body = peel(core->kids[0].get());
+		if (body->kind == Node::SET && core->rmin >= 1) {
+			if (core->rmin > (uint32_t)kMaxPatternLen) { err = "run minimum above 1024"; return false; }
+			out.kind = ENGINE_RUN;
+			out.run_class = body->set;
+			out.run_min = (int)core->rmin;
+			out.maxlen = -1;
+			out.disjoint = true;
+			for (auto r : to_ranges(body->set)) {
+				if (r.lo < 0x80) out.ranges_low.push_back(ByteRange{r.lo, (uint8_t)std::min<int>(r.hi, 0x7f)});
+				if (r.hi >= 0x80) out.ranges_high.push_back(ByteRange{(uint8_t)std::max<int>(r.lo, 0x80), r.hi});
+			}
+			if ((int)out.ranges_low.size() > kMaxRunRangesLow || (int)out.ranges_high.size() > kMaxRunRangesHigh) {
+				err = "byte class of the run needs too many ranges for the SWAR class test";
+				return false;
+			}
+			if (body->set.empty()) { err = "empty byte class"; return false; }
+			return true;
+		}
+	}
+
+	// FIXED: expand into fixed-length sequences in backtracking (preference) order
+	Expander ex;
+	std::vector<Sequence> seqs = ex.expand(root.get());
+	if (ex.overflow) { err = ex.why; return false; }
+	// drop exact duplicates (a later identical alternative can never win) and never-matching ones
+	std::vector<Sequence> uniq;
+	for (auto &s : seqs) {
+		if (s.empty()) { err = "internal: empty alternative"; return false; }
+		bool dup = false;
+		for (auto &u : uniq)
+			if (u.size() <= s.size()) {
+				// u shadows s if u is a prefix-wise superset: whenever s matches at q, u (earlier) does too
+				bool shadow = true;
+				for (size_t i = 0; i < u.size() && shadow; i++) shadow = s[i].subset_of(u[i]);
+				if (shadow) { dup = true; break; }
+			}
+		if (!dup) uniq.push_back(s);
+	}
+	if (uniq.empty()) { err = "pattern can never match"; return false; }
+	out.kind = ENGINE_FIXED;
+	out.seqs = uniq;
+	size_t mn = SIZE_MAX, mx = 0;
+	for (auto &s : out.seqs) { mn = std::min(mn, s.size()); mx = std::max(mx, s.size()); }
+	out.maxlen = (int)mx;
+	// (minlen from the tree equals mn unless shadowing removed the shortest: keep PCRE's figure)
+
+	// ---- choose the SWAR filter: anchor byte + second byte `delta` further on ----
+	double best_score = 1e300;
+	int best_a = 0, best_d = 0;
+	std::vector<FilterTest> best_tests;
+	for (int d = (mn >= 2 ? 1 : 0); d <= 3; d++) {
+		for (int a = 0; a + d < (int)mn && a <= 224; a++) {
+			std::vector<FilterTest> tests;
+			double p = 0;
+			for (auto &s : out.seqs) {
+				MaskedEq e0 = masked_superset(s[a]);
+				MaskedEq e1 = d ? masked_superset(s[a + d]) : MaskedEq{0, 0, false, 256};
+				FilterTest t{e0.mask, e0.val, e1.mask, e1.val};
+				if (std::find(tests.begin(), tests.end(), t) == tests.end()) {
+					tests.push_back(t);
+					p += test_prior(e0) * (d ? test_prior(e1) : 1.0);
+				}
+			}
+			if ((int)tests.size() > kMaxFilterTests) continue;
+			// each test costs ~4 ALU ops per 4 bytes; each flagged position costs a slow-path visit
+			double score = p * 4000.0 + (double)tests.size();
+			if (score < best_score) { best_score = score; best_a = a; best_d = d; best_tests = tests; }
+		}
+		if (mn < 2) break;
+	}
+	if (best_tests.empty()) {
+		err = "alternation needs more than 8 distinct byte-pair filter tests (large literal sets: hashed engine not built yet)";
+		return false;
+	}
+	out.anchor = best_a;
+	out.delta = best_d;
+	out.tests = best_tests;
+
+	// ---- can two matches overlap?  If not, the greedy resolve keeps every candidate ----
+	bool disjoint = true;
+	for (auto &a : out.seqs) {
+		for (auto &b : out.seqs) {
+			for (size_t sh = 1; sh < a.size() && disjoint; sh++)
+				if (can_overlap(a, b, sh)) disjoint = false;
+			if (!disjoint) break;
+		}
+		if (!disjoint) break;
+	}
+	out.disjoint = disjoint;
+	return true;
+}
+
+} // namespace gscan

@@ -1,0 +1,84 @@
+// pattern.h -- host-side pattern compiler: PCRE subset -> device automaton tables.
+//
+// Replaces what FileGrep::prepare gets from libpcre (/root/reference/src/grab.cc:101-123):
+// pcre_compile(regex, options = 0, ...), pcre_study and PCRE_INFO_MINLENGTH.  Semantics are
+// PCRE's with options 0: bytes (no UTF), case-sensitive unless (?i), '.' excludes '\n',
+// "C"-locale classes (pcre_maketables() without setlocale, grab.cc:106), leftmost-first
+// alternation.  Instead of byte code for a backtracking interpreter the output is one of two
+// data-parallel programs:
+//   FIXED : ordered list of fixed-length byte-class sequences (literals, alternations, classes,
+//           bounded repeats expanded in backtracking order) + a SWAR byte-pair filter
+//   RUN   : one byte class repeated {n,} greedily, as SWAR range tests
+// Anything else is rejected loudly: there is no CPU fallback for the scan.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace gscan {
+
+struct ByteSet {
+	uint32_t w[8];
+	ByteSet() { for (auto &x : w) x = 0; }
+	void add(unsigned c) { w[(c & 255) >> 5] |= 1u << (c & 31); }
+	bool has(unsigned c) const { return (w[(c & 255) >> 5] >> (c & 31)) & 1u; }
+	void add_range(unsigned lo, unsigned hi) { for (unsigned c = lo; c <= hi; c++) add(c); }
+	void invert() { for (auto &x : w) x = ~x; }
+	void unite(const ByteSet &o) { for (int i = 0; i < 8; i++) w[i] |= o.w[i]; }
+	bool intersects(const ByteSet &o) const { for (int i = 0; i < 8; i++) if (w[i] & o.w[i]) return true; return false; }
+	bool subset_of(const ByteSet &o) const { for (int i = 0; i < 8; i++) if (w[i] & ~o.w[i]) return false; return true; }
+	bool operator==(const ByteSet &o) const { for (int i = 0; i < 8; i++) if (w[i] != o.w[i]) return false; return true; }
+	int count() const { int n = 0; for (auto x : w) n += __builtin_popcount(x); return n; }
+	bool empty() const { return count() == 0; }
+};
+
+// {x : (x & mask) == val}; exact == true when that set equals the class itself
+struct MaskedEq {
+	uint8_t mask, val;
+	bool exact;
+	int size; // number of bytes passing the test
+};
+MaskedEq masked_superset(const ByteSet &s);
+
+struct ByteRange { uint8_t lo, hi; };
+std::vector<ByteRange> to_ranges(const ByteSet &s);
+
+typedef std::vector<ByteSet> Sequence;
+
+struct FilterTest {
+	uint8_t m0, v0, m1, v1; // (byte[p] & m0) == v0 && (byte[p+d] & m1) == v1
+	bool operator==(const FilterTest &o) const { return m0 == o.m0 && v0 == o.v0 && m1 == o.m1 && v1 == o.v1; }
+};
+
+enum EngineKind { ENGINE_FIXED = 1, ENGINE_RUN = 2, ENGINE_NONE = 3 };
+
+constexpr int kMaxFilterTests = 8;
+constexpr int kMaxPatternLen = 1024;   // longest sequence the smem halo can verify
+constexpr int kMaxSequences = 4096;
+constexpr int kMaxRunRangesLow = 8, kMaxRunRangesHigh = 2;
+
+struct Program {
+	EngineKind kind = ENGINE_FIXED;
+	int minlen = 0, maxlen = 0; // maxlen -1: unbounded
+	int captures = 0;
+	bool strict_q2 = false;
+
+	// FIXED
+	std::vector<Sequence> seqs;       // in PCRE preference order
+	std::vector<FilterTest> tests;    // deduplicated
+	int anchor = 0, delta = 0;        // filter bytes are pattern[anchor], pattern[anchor+delta]
+	bool disjoint = false;            // no two matches can ever overlap => resolve is a pure copy
+
+	// RUN
+	ByteSet run_class;
+	int run_min = 0;
+	std::vector<ByteRange> ranges_low, ranges_high; // within 0x00-0x7F / 0x80-0xFF
+
+	uint64_t id = 0; // unique per compiled pattern (device-table cache key)
+};
+
+// Returns true and fills `out`; false and `err` otherwise.
+bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, std::string &err);
+
+} // namespace gscan

@@ -1,0 +1,94 @@
+"""CPU-only checks of the product library: it loads, exports every symbol include/gscan.h declares,
+compiles patterns to the same minimum length as PCRE2 (fixtures from the reference's library),
+rejects what the device engines do not serve, and FAILS LOUDLY without a GPU (no CPU fallback)."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+
+import grab_b200 as G
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+MINLEN = json.load(open(os.path.join(HERE, "golden", "minlen.json")))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "gscan.h")).read()
+    declared = set(re.findall(r"\b(gscan_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = ctypes.CDLL(G.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), "libgscan.so does not export %s" % name
+    assert declared == set(G._PROTOS), "python prototypes out of sync with include/gscan.h"
+    assert G.lib().gscan_abi_version() == 1
+
+
+def test_struct_layouts():
+    assert ctypes.sizeof(G.Unit) == 32 and G.UNIT_DTYPE.itemsize == 32
+    assert ctypes.sizeof(G.Match) == 16 and G.MATCH_DTYPE.itemsize == 16
+
+
+UNSUPPORTED_OK = ("not supported", "only supported", "empty string", "too many", "not built yet", "needs more than")
+
+
+@pytest.mark.parametrize("ent", MINLEN, ids=lambda e: e["pattern"][:24])
+def test_minlen_equals_pcre2(ent):
+    if not ent["compiles"]:
+        with pytest.raises(G.GscanError):
+            G.Pattern(ent["pattern"])
+        return
+    try:
+        p = G.Pattern(ent["pattern"])
+    except G.GscanError as e:
+        # loud, explained rejection is the contract for constructs outside the device engines
+        assert any(s in str(e) for s in UNSUPPORTED_OK), str(e)
+        if ent["minlen"] == 0:
+            assert "empty string" in str(e)
+        return
+    assert p.minlen == ent["minlen"]
+    assert p.info["captures"] == ent["captures"]
+
+
+def test_engine_selection_and_filter():
+    i = G.Pattern("foobardoesnotexist").info
+    assert i["engine"] == G.ENGINE_FIXED and i["n_sequences"] == 1 and i["n_filter_tests"] == 1
+    assert i["minlen"] == 18 and i["maxlen"] == 18 and i["filter_delta"] in (1, 2, 3)
+    i = G.Pattern("foo|bar|baz|quux").info
+    assert i["engine"] == G.ENGINE_FIXED and i["n_sequences"] == 4 and i["minlen"] == 3 and i["maxlen"] == 4
+    assert 1 <= i["n_filter_tests"] <= 4
+    i = G.Pattern("[A-Za-z0-9_]{16,}").info
+    assert i["engine"] == G.ENGINE_RUN and i["minlen"] == 16 and i["maxlen"] == -1
+    assert G.Pattern("(?i)linus").info["minlen"] == 5
+    assert G.Pattern("a.c", literal=True).info["n_sequences"] == 1
+    # Q2: strict mode + capturing group => nothing can ever be printed
+    assert G.Pattern("(foo|bar)", strict_ref=True).info["engine"] == G.ENGINE_NONE
+    assert G.Pattern("(foo|bar)").info["engine"] == G.ENGINE_FIXED
+    # bounded repeats expand in backtracking order
+    assert G.Pattern("a{2,4}").info["n_sequences"] == 3  # aaaa, aaa, aa (greedy order)
+    assert G.Pattern("fo|foo|foobar").info["n_sequences"] == 1  # later alternatives are shadowed by fo
+    assert G.Pattern("colou?r").info["n_sequences"] == 2
+
+
+@pytest.mark.parametrize("pat,frag", [
+    ("x*", "empty string"), ("", "empty string"), ("a|", "empty string"),
+    ("^foo", "not supported"), (r"\bfoo", "not supported"), ("foo$", "not supported"),
+    ("ab*c", "only supported"), ("<.+>", "only supported"), (r"foo\d+bar", "only supported"),
+    ("(", "missing )"), ("[a-", "missing terminating ]"), (r"\1", "back references"), ("(?=a)b", "not supported"),
+    ("a{3,2}", "quantifier"),
+])
+def test_rejections_are_loud(pat, frag):
+    with pytest.raises(G.GscanError) as ei:
+        G.Pattern(pat)
+    assert frag in str(ei.value)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(G.GscanError) as ei:
+        G.Context(0)
+    assert "no CPU fallback" in str(ei.value)

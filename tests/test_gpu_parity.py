@@ -1,0 +1,216 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle port and the fixtures produced
+by the unmodified reference.  Bit-exact: offsets and lengths are integers."""
+import base64
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import corpus
+import grab_b200 as G
+import oracle_py as O
+from chunker import windows
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KAT = json.load(open(os.path.join(HERE, "golden", "kat.json")))
+BIG = json.load(open(os.path.join(HERE, "golden", "big.json")))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = G.Context(0)
+    yield c
+    c.close()
+
+
+def gpu_scan(ctx, pat, data, mode=G.MODE_ALL, strict=True, base_off=0):
+    p = G.Pattern(pat, strict_ref=strict)
+    r = ctx.scan(p, [data], mode=mode, base_offs=[base_off])
+    return [(int(s), int(l)) for s, l in zip(r["start"], r["match_len"])]
+
+
+def oracle_scan(pat, data, mode=O.MODE_ALL, strict=True, base_off=0):
+    return O.Regex(pat).scan_window(bytes(data), base_off=base_off, mode=mode, strict_q2=strict)
+
+
+def supported(pat):
+    try:
+        G.Pattern(pat)
+        return True
+    except G.GscanError:
+        return False
+
+
+def offsets_of(stdout):
+    return [int(l[len(b"Match at offset "):]) for l in stdout.split(b"\n") if l.startswith(b"Match at offset ")]
+
+
+# ---- golden vectors produced by the reference binary -------------------------------------
+OL_CASES = [c for c in KAT["cases"] if c["flags"] == ["-O", "-l"]]
+
+
+@pytest.mark.parametrize("case", OL_CASES, ids=lambda c: c["name"])
+def test_kat_offsets(ctx, case):
+    if not supported(case["pattern"]):
+        pytest.skip("pattern outside the device engines (rejected loudly at compile)")
+    data = base64.b64decode(case["input"])
+    want = offsets_of(base64.b64decode(case["stdout"]))
+    p = G.Pattern(case["pattern"], strict_ref=True)
+    if p.minlen > len(data):  # small-file skip (grab.cc:133-135) is host logic
+        got = []
+    else:
+        got = [s for s, _ in gpu_scan(ctx, case["pattern"], data)]
+    assert got == want
+
+
+@pytest.mark.parametrize("case", OL_CASES, ids=lambda c: c["name"])
+def test_kat_all_modes_vs_oracle(ctx, case):
+    if not supported(case["pattern"]):
+        pytest.skip("pattern outside the device engines")
+    data = base64.b64decode(case["input"])
+    if not data:
+        return
+    for mode in (G.MODE_ALL, G.MODE_FIRST, G.MODE_LINE):
+        for strict in (True, False):
+            assert gpu_scan(ctx, case["pattern"], data, mode, strict) == oracle_scan(case["pattern"], data, mode, strict), (mode, strict)
+
+
+# ---- seeded differential: random small-alphabet inputs ------------------------------------
+DIFF_PATTERNS = ["ab", "aa", "aba", "abab", "a", "abc|bc|c", "ab|abc", "abc|ab", "a|b", "aab|ab|b", "[ab]{3,}", "[ab]{2}",
+                 "a{2,}", "b+", "[^a\\n]{2,}", "a.b", "a..", "(?i)AB", "(?:ab|ba)a", "a[ab]b", "ab{2}", "[a-c]{4,}", "b[^b]b",
+                 "abcabc", "cab|abc|bca", "a{2,3}", "(?:ab){1,2}c", "b?ac", "[ab]c{0,2}a"]
+
+
+@pytest.mark.parametrize("pat", DIFF_PATTERNS)
+def test_differential_small_alphabet(ctx, pat):
+    rnd = random.Random(hash(pat) & 0xffff)
+    p = G.Pattern(pat)
+    o = O.Regex(pat)
+    bufs = []
+    for k in range(60):
+        alpha = [b"ab", b"abc", b"ab\n", b"abc \n"][k % 4]
+        ln = rnd.choice([1, 2, 3, 5, 8, 15, 16, 17, 31, 33, 64, 100, 257, 511, 513, 600, 2047, 2049, 5000])
+        bufs.append(bytes(rnd.choice(alpha) for _ in range(ln)))
+    for mode in (G.MODE_ALL, G.MODE_FIRST, G.MODE_LINE):
+        r = ctx.scan(p, bufs, mode=mode)
+        got = {}
+        for fid, s, l in zip(r["file_id"], r["start"], r["match_len"]):
+            got.setdefault(int(fid), []).append((int(s), int(l)))
+        for i, b in enumerate(bufs):
+            assert got.get(i, []) == o.scan_window(b, mode=mode), (pat, mode, i, len(b))
+    # output is sorted by (unit, start)
+    r = ctx.scan(p, bufs)
+    keys = list(zip(r["file_id"].tolist(), r["start"].tolist()))
+    assert keys == sorted(keys)
+
+
+# ---- boundaries: lane (16 B), warp row (512 B), warp slice (2 KiB), tile (32 KiB), unit end ----
+@pytest.mark.parametrize("pat,needle", [("NEEDLE", b"NEEDLE"), ("foo|quux|NEEDLES", b"NEEDLES"), ("[A-Z]{6,}", b"NEEDLE"),
+                                         ("(?i)needle", b"nEeDlE"), ("N.{4}E", b"NEEDLE"), ("Q{20,}", b"Q" * 23)])
+def test_boundary_straddles(ctx, pat, needle):
+    size = 3 * 32768 + 777
+    base = np.full(size, ord("."), dtype=np.uint8)
+    base[97::101] = 10
+    p = G.Pattern(pat)
+    o = O.Regex(pat)
+    bufs = []
+    for edge in (16, 512, 2048, 32768, 65536, size):
+        for d in range(-len(needle) - 1, 2):
+            pos = edge + d
+            if pos < 0 or pos + len(needle) > size:
+                continue
+            a = base.copy()
+            a[pos:pos + len(needle)] = np.frombuffer(needle, dtype=np.uint8)
+            bufs.append(a)
+    r = ctx.scan(p, bufs)
+    got = {}
+    for fid, s, l in zip(r["file_id"], r["start"], r["match_len"]):
+        got.setdefault(int(fid), []).append((int(s), int(l)))
+    for i, b in enumerate(bufs):
+        assert got.get(i, []) == o.scan_window(b.tobytes()), (pat, i)
+
+
+def test_ragged_units_and_empty(ctx):
+    pat = "foo|ba"
+    p, o = G.Pattern(pat), O.Regex(pat)
+    rnd = random.Random(5)
+    bufs = [b"", b"f", b"fo", b"foo", b"ba", b"bax", b"xfoo", b"foofoo", b"foofoox"]
+    bufs += [bytes(rnd.choice(b"fobax\n") for _ in range(rnd.randrange(0, 70000))) for _ in range(40)]
+    r = ctx.scan(p, bufs, file_ids=[100 + i for i in range(len(bufs))], base_offs=[7 * i for i in range(len(bufs))])
+    got = {}
+    for fid, s, l in zip(r["file_id"], r["start"], r["match_len"]):
+        got.setdefault(int(fid) - 100, []).append((int(s), int(l)))
+    for i, b in enumerate(bufs):
+        assert got.get(i, []) == o.scan_window(b, base_off=7 * i), i
+
+
+def test_dense_matches_grow_candidate_buffer(ctx):
+    # pattern 'e' on a buffer of e's: one candidate per byte; nothing may be truncated
+    data = b"e" * (1 << 20) + b"x"
+    got = gpu_scan(ctx, "e", data)
+    assert len(got) == 1 << 20 and got[0] == (0, 1) and got[-1] == ((1 << 20) - 1, 1)
+    got = gpu_scan(ctx, "ee", data)
+    assert [s for s, _ in got] == list(range(0, 1 << 20, 2))
+
+
+# ---- chunk windows (Q3): duplicates and phantoms reproduced by construction ------------------
+@pytest.mark.parametrize("ent", BIG["overlap"], ids=lambda e: e["gen"] + str(len(e["flags"])))
+def test_chunk_overlap(ctx, ent):
+    data = getattr(corpus, ent["gen"])()
+    chunk = 1 << 30
+    for f in ent["flags"]:
+        if f == "-L":
+            chunk = max(chunk >> 1, 1 << 25)
+    wins = windows(len(data), chunk)
+    p = G.Pattern(ent["pattern"])
+    r = ctx.scan(p, [data[o:o + n] for o, n in wins], file_ids=[0] * len(wins), base_offs=[o for o, _ in wins])
+    assert r["start"].tolist() == ent["offsets"]
+
+
+# ---- mid-size corpora pinned by the reference ------------------------------------------------
+@pytest.mark.parametrize("ent", BIG["synth"], ids=lambda e: e["pattern"][:16])
+def test_synth_files_host_and_device_generator(ctx, ent):
+    if not supported(ent["pattern"]):
+        pytest.skip("pattern outside the device engines")
+    p = G.Pattern(ent["pattern"])
+    n, flen = len(ent["offsets"]), ent["file_len"]
+    # (a) host twin through host units
+    bufs = [corpus.synth_file(ent["seed"], fid, flen, ent["needle"].encode(), ent["needle_every"]) for fid in range(n)]
+    r = ctx.scan(p, bufs)
+    for fid in range(n):
+        assert r["start"][r["file_id"] == fid].tolist() == ent["offsets"][str(fid)]
+    # (b) device generator, device-resident units: same bytes, same matches
+    d = ctx.device_alloc(n * flen)
+    try:
+        ctx.synth_corpus(d, ent["seed"], 0, n, flen, needle=ent["needle"].encode(), needle_every=ent["needle_every"])
+        back = ctx.d2h(d, n * flen)
+        assert bytes(back) == b"".join(b.tobytes() for b in bufs)
+        r2 = ctx.scan_units(p, G.Context.device_units(d, n, flen))
+        assert r2.tobytes() == r.tobytes()
+    finally:
+        ctx.device_free(d)
+
+
+def test_b3_256mib_md5(ctx):
+    a = corpus.b3_corpus()
+    assert hashlib.md5(a.tobytes()).hexdigest() == BIG["b3_file_md5"]
+    d = ctx.device_alloc(a.size)
+    try:
+        ctx.h2d(d, a)
+        units = G.Context.device_units(d, 1, a.size)
+        batch = ctx.batch_create(units)
+        for ent in BIG["b3"]:
+            if not supported(ent["pattern"]):
+                continue
+            r = ctx.batch_scan(G.Pattern(ent["pattern"]), batch)
+            txt = "".join("%d\n" % o for o in r["start"].tolist()).encode()
+            assert len(r) == ent["n"], ent["pattern"][:20]
+            assert hashlib.md5(txt).hexdigest() == ent["md5"], ent["pattern"][:20]
+        batch.free()
+    finally:
+        ctx.device_free(d)
