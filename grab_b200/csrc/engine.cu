@@ -93,7 +93,7 @@ struct gscan_ctx {
 	DevBuf<Cand> cand;
 	DevBuf<Cand> scratch;
 	DevBuf<OutRec> ord, out;
-	DevBuf<uint32_t> unit_start, blk;
+	DevBuf<uint32_t> unit_start, unit_out, blk;
 	DevBuf<unsigned long long> cursor; // [0] cursor, then 2 x u32 totals behind it
 	DevBuf<uint8_t> pat_tables;
 	uint64_t pat_id = 0;
@@ -262,7 +262,7 @@ extern "C" void gscan_close(gscan_ctx *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->segs.release(); c->cand.release(); c->scratch.release(); c->ord.release(); c->out.release();
-	c->unit_start.release(); c->blk.release(); c->cursor.release(); c->pat_tables.release();
+	c->unit_start.release(); c->unit_out.release(); c->blk.release(); c->cursor.release(); c->pat_tables.release();
 	c->probe_sum.release(); c->needle.release();
 	c->readback.release(); c->out_host.release(); c->stage[0].release(); c->stage[1].release();
 	for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -484,12 +484,11 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	size_t n = 0;
 	const OutRec *h_recs = nullptr;
 	if (total_cand) {
-		const uint32_t nb_seg = (n_segs + 2047) / 2048, nb_ord = (uint32_t)((total_cand + 2047) / 2048);
+		const uint32_t nb_seg = (n_segs + 2047) / 2048, nb_u = (uint32_t)((b->units.size() + 2047) / 2048);
 		CK(ctx, ctx->ord.ensure((size_t)total_cand));
-		CK(ctx, ctx->out.ensure((size_t)total_cand));
 		CK(ctx, ctx->unit_start.ensure(b->units.size() + 1));
-		CK(ctx, ctx->blk.ensure((size_t)nb_seg + nb_ord + 4));
-		CK(ctx, ctx->out_host.ensure((size_t)total_cand * sizeof(OutRec)));
+		CK(ctx, ctx->unit_out.ensure(b->units.size() + 1));
+		CK(ctx, ctx->blk.ensure((size_t)nb_seg + nb_u + 4));
 		ResolveArgs R;
 		R.tiles = b->d_tiles;
 		R.segs = ctx->segs.p;
@@ -498,8 +497,9 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		R.units = b->d_units;
 		R.n_units = (uint32_t)b->units.size();
 		R.ord = ctx->ord.p;
-		R.out = ctx->out.p;
+		R.out = nullptr;
 		R.unit_start = ctx->unit_start.p;
+		R.unit_out = ctx->unit_out.p;
 		R.blk = ctx->blk.p;
 		R.totals = reinterpret_cast<uint32_t *>(ctx->cursor.p + 1);
 		R.mode = mode;
@@ -509,18 +509,28 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		for (int i = 0; i < 8; i++) R.bitmap[i] = pat->prog.run_class.w[i];
 		R.total_cand = (uint32_t)total_cand;
 		uint32_t nl = 0;
-		CK(ctx, launch_resolve(R, ctx->stream, &nl));
+		CK(ctx, launch_resolve_count(R, ctx->stream, &nl));
 		S.total_launches += nl;
-		CK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
 		uint32_t *h_tot = reinterpret_cast<uint32_t *>((uint8_t *)ctx->readback.p + 16);
 		CK(ctx, cudaMemcpyAsync(h_tot, R.totals, 8, cudaMemcpyDeviceToHost, ctx->stream));
-		CK(ctx, cudaMemcpyAsync(ctx->out_host.p, ctx->out.p, (size_t)total_cand * sizeof(OutRec), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		if (h_tot[0] != (uint32_t)total_cand) return fail(ctx, "gscan_batch_scan: internal: segment counts disagree with the cursor");
+		n = h_tot[1];
+		if (n) {
+			CK(ctx, ctx->out.ensure(n));
+			CK(ctx, ctx->out_host.ensure(n * sizeof(OutRec)));
+			R.out = ctx->out.p;
+			CK(ctx, launch_resolve_write(R, ctx->stream, &nl));
+			S.total_launches += nl;
+			CK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+			CK(ctx, cudaMemcpyAsync(ctx->out_host.p, ctx->out.p, n * sizeof(OutRec), cudaMemcpyDeviceToHost, ctx->stream));
+		} else {
+			CK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+		}
 		CK(ctx, cudaStreamSynchronize(ctx->stream));
 		float ms = 0;
 		cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
 		S.resolve_ms = ms;
-		n = h_tot[1];
-		if (h_tot[0] != (uint32_t)total_cand) return fail(ctx, "gscan_batch_scan: internal: segment counts disagree with the cursor");
 		h_recs = reinterpret_cast<const OutRec *>(ctx->out_host.p);
 	}
 	gscan_match *m = nullptr;

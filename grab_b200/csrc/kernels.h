@@ -25,17 +25,20 @@ struct ResolveArgs {
 	const Cand *cand;
 	const DevUnit *units;
 	uint32_t n_units;
-	OutRec *ord;          // candidates in (unit, pos) order; pad = keep flag after selection
-	OutRec *out;          // selected matches, same order
-	uint32_t *unit_start; // [n_units + 1]
+	OutRec *ord;          // candidates in (unit, pos) order
+	OutRec *out;          // selected matches, same order (capacity known after the count pass)
+	uint32_t *unit_start; // [n_units + 1] first candidate of each unit in ord
+	uint32_t *unit_out;   // [n_units] matches per unit, then (exclusive scan) first output slot
 	uint32_t *blk;        // block-sum scratch
 	uint32_t *totals;     // [0] candidates, [1] matches
 	uint32_t mode, minlen, engine, run_min;
 	uint32_t bitmap[8];   // RUN class, for match-length extension
 	uint32_t total_cand;  // known on the host after the scan kernel
 };
-// returns the number of kernels launched through *launches
-cudaError_t launch_resolve(const ResolveArgs &R, cudaStream_t st, uint32_t *launches);
+// count pass: segment scan, gather, per-unit replay that counts, slot scan; totals[1] = number of matches
+cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t *launches);
+// write pass: per-unit replay that writes R.out
+cudaError_t launch_resolve_write(const ResolveArgs &R, cudaStream_t st, uint32_t *launches);
 
 cudaError_t launch_synth_corpus(uint8_t *dptr, uint64_t seed, uint64_t first_file_id, uint64_t n_files, uint64_t file_len,
                                 uint64_t stride, const uint8_t *d_needle, uint32_t needle_len, uint32_t needle_every,

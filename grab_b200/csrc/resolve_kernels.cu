@@ -122,91 +122,110 @@ __global__ void k_gather(const ResolveArgs R)
 }
 
 // ---- 3. per-unit replay of the reference loop ----
-__global__ void k_select(const ResolveArgs R)
+// Pass 1 (WRITE=false) counts the matches of every unit, pass 2 writes them at the unit's slot of
+// the output (exclusive scan of the counts in between): the output can hold matches that are not
+// candidates -- in LINE mode the RUN engine restarts up to 511 bytes after a match, possibly in
+// the middle of a run, and PCRE then reports a match at that very byte.
+__device__ __forceinline__ bool in_class(const ResolveArgs &R, uint32_t b) { return (R.bitmap[b >> 5] >> (b & 31)) & 1u; }
+
+template <bool WRITE>
+__global__ void k_walk(const ResolveArgs R)
 {
 	const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
 	if (u >= R.n_units) return;
 	uint32_t i = R.unit_start[u];
 	const uint32_t end = R.unit_start[u + 1];
-	if (i == end) return;
-	const DevUnit du = R.units[u];
-	const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
-	const uint64_t ulen = du.len;
-	uint64_t start = 0;
-	while (i < end) {
-		if (!(start + R.minlen < ulen)) break;                 // grab.cc:175 (strict '<': Q1)
-		while (i < end && R.ord[i].pos < start) i++;           // candidates inside the previous match
-		if (i == end) break;
-		const uint32_t pos = R.ord[i].pos;
-		uint32_t len = R.ord[i].len;
-		if (R.engine == GSCAN_ENGINE_RUN) {                    // greedy: extend to the end of the run
-			uint64_t e = (uint64_t)pos + R.run_min;
-			while (e < ulen) {
-				const uint32_t b = data[e];
-				if (!((R.bitmap[b >> 5] >> (b & 31)) & 1u)) break;
-				e++;
+	uint32_t n = 0;
+	OutRec *o = WRITE ? R.out + R.unit_out[u] : nullptr;
+	if (i != end) {
+		const DevUnit du = R.units[u];
+		const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
+		const uint64_t ulen = du.len;
+		const bool run = R.engine == GSCAN_ENGINE_RUN;
+		uint64_t start = 0;
+		for (;;) {
+			if (!(start + R.minlen < ulen)) break;                 // grab.cc:175 (strict '<': Q1)
+			uint64_t pos = 0, e = 0;
+			bool found = false;
+			if (run && R.mode == GSCAN_MODE_LINE && start > 0 && in_class(R, data[start - 1]) && in_class(R, data[start])) {
+				// `start` lies inside a run: the leftmost match, if the rest of the run is long enough, is AT start
+				e = start;
+				while (e < ulen && in_class(R, data[e])) e++;
+				if (e - start >= R.run_min) { pos = start; found = true; }
 			}
-			len = (uint32_t)(e - pos);
-			R.ord[i].len = len;
+			if (!found) {
+				while (i < end && R.ord[i].pos < start) i++;       // candidates swallowed by the previous match / skip
+				if (i == end) break;
+				pos = R.ord[i].pos;
+				e = pos + R.ord[i].len;
+				if (run) {                                         // greedy: extend to the end of the run
+					e = pos + R.run_min;
+					while (e < ulen && in_class(R, data[e])) e++;
+				}
+				i++;
+			}
+			if (WRITE) { OutRec r; r.unit = u; r.pos = (uint32_t)pos; r.len = (uint32_t)(e - pos); r.pad = 0; o[n] = r; }
+			n++;
+			if (R.mode == GSCAN_MODE_FIRST) break;                 // grab.cc:206 / :211
+			if (R.mode == GSCAN_MODE_LINE) {                       // grab.cc:194-196: a = bytes to '\n', <= 511
+				uint32_t a = 0;
+				while (e + a < ulen && a < 511 && data[e + a] != '\n') a++;
+				e += a;
+			}
+			start = e;                                             // grab.cc:209
 		}
-		R.ord[i].pad = 1;
-		uint64_t e = (uint64_t)pos + len;
-		if (R.mode == GSCAN_MODE_FIRST) break;                 // grab.cc:206 / :211
-		if (R.mode == GSCAN_MODE_LINE) {                       // grab.cc:194-196: a = bytes to '\n', <= 511
-			uint32_t a = 0;
-			while (e + a < ulen && a < 511 && data[e + a] != '\n') a++;
-			e += a;
-		}
-		start = e;                                             // grab.cc:209
-		i++;
 	}
+	if (!WRITE) R.unit_out[u] = n;
 }
 
-// ---- 4. compact kept records ----
-__global__ void k_keep_sums(const OutRec *ord, uint32_t n, uint32_t *blk)
+// ---- 4. generic u32 block sums / exclusive scan (per-unit match counts -> output slots) ----
+__global__ void k_u32_sums(const uint32_t *v, uint32_t n, uint32_t *blk)
 {
 	const uint32_t base = blockIdx.x * kPerBlock + threadIdx.x * kPerThread;
 	uint32_t s = 0;
 #pragma unroll
 	for (int i = 0; i < kPerThread; i++)
-		if (base + i < n) s += ord[base + i].pad;
+		if (base + i < n) s += v[base + i];
 	uint32_t total;
 	block_exclusive_scan(s, &total);
 	if (threadIdx.x == 0) blk[blockIdx.x] = total;
 }
 
-__global__ void k_compact(const OutRec *ord, uint32_t n, const uint32_t *blk, OutRec *out)
+__global__ void k_u32_exclusive(uint32_t *v, uint32_t n, const uint32_t *blk)
 {
 	const uint32_t base = blockIdx.x * kPerBlock + threadIdx.x * kPerThread;
+	uint32_t x[kPerThread];
 	uint32_t s = 0;
 #pragma unroll
-	for (int i = 0; i < kPerThread; i++)
-		if (base + i < n) s += ord[base + i].pad;
+	for (int i = 0; i < kPerThread; i++) { x[i] = base + i < n ? v[base + i] : 0u; s += x[i]; }
 	uint32_t total;
 	uint32_t p = block_exclusive_scan(s, &total) + blk[blockIdx.x];
 #pragma unroll
 	for (int i = 0; i < kPerThread; i++)
-		if (base + i < n && ord[base + i].pad) out[p++] = ord[base + i];
+		if (base + i < n) { v[base + i] = p; p += x[i]; }
 }
 
-cudaError_t launch_resolve(const ResolveArgs &R, cudaStream_t st, uint32_t *launches)
+cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t *launches)
 {
 	uint32_t nl = 0;
 	const uint32_t nb_seg = (R.n_segs + kPerBlock - 1) / kPerBlock;
 	k_seg_sums<<<nb_seg, kScanBlock, 0, st>>>(R.segs, R.n_segs, R.blk); nl++;
 	k_scan_blk<<<1, kScanBlock, 0, st>>>(R.blk, nb_seg, R.totals, R.unit_start + R.n_units); nl++;
 	k_gather<<<nb_seg, kScanBlock, 0, st>>>(R); nl++;
-	k_select<<<(R.n_units + 127) / 128, 128, 0, st>>>(R); nl++;
-	const uint32_t n = R.total_cand;
-	const uint32_t nb_ord = (n + kPerBlock - 1) / kPerBlock;
-	if (nb_ord) {
-		// block sums of the keep flags live behind the segment block sums
-		uint32_t *blk2 = R.blk + nb_seg + 1;
-		k_keep_sums<<<nb_ord, kScanBlock, 0, st>>>(R.ord, n, blk2); nl++;
-		k_scan_blk<<<1, kScanBlock, 0, st>>>(blk2, nb_ord, R.totals + 1, nullptr); nl++;
-		k_compact<<<nb_ord, kScanBlock, 0, st>>>(R.ord, n, blk2, R.out); nl++;
-	}
+	k_walk<false><<<(R.n_units + 127) / 128, 128, 0, st>>>(R); nl++;
+	const uint32_t nb_u = (R.n_units + kPerBlock - 1) / kPerBlock;
+	uint32_t *blk2 = R.blk + nb_seg + 1; // block sums of the per-unit counts live behind the segment block sums
+	k_u32_sums<<<nb_u, kScanBlock, 0, st>>>(R.unit_out, R.n_units, blk2); nl++;
+	k_scan_blk<<<1, kScanBlock, 0, st>>>(blk2, nb_u, R.totals + 1, nullptr); nl++;
+	k_u32_exclusive<<<nb_u, kScanBlock, 0, st>>>(R.unit_out, R.n_units, blk2); nl++;
 	if (launches) *launches = nl;
+	return cudaGetLastError();
+}
+
+cudaError_t launch_resolve_write(const ResolveArgs &R, cudaStream_t st, uint32_t *launches)
+{
+	k_walk<true><<<(R.n_units + 127) / 128, 128, 0, st>>>(R);
+	if (launches) *launches = 1;
 	return cudaGetLastError();
 }
 
