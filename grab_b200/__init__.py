@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgscan.so")
+LIB_PATH = os.environ.get("GSCAN_LIB") or os.path.join(_HERE, "libgscan.so")  # GSCAN_LIB: tuning variants
 
 MODE_ALL, MODE_FIRST, MODE_LINE = 0, 1, 2
 LITERAL, STRICT_REF = 1, 2

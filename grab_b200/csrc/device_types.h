@@ -4,16 +4,29 @@
 
 namespace gscan {
 
-// Geometry of the persistent scan kernel.
-constexpr int kTileBytes = 32768;   // bytes of one tile: the unit of the TMA pipeline
-constexpr int kConsumerWarps = 16;  // warps that scan; +1 producer warp issues the bulk copies
-constexpr int kStages = 4;          // smem ring depth
-constexpr int kPreMax = 256;        // bytes kept in front of a tile (filter anchor look-behind)
-constexpr int kPostMax = 1056;      // bytes kept behind a tile (verification look-ahead)
-constexpr int kStageBytes = kPreMax + kTileBytes + kPostMax; // 34080, multiple of 16
-constexpr int kStageStride = ((kStageBytes + 127) / 128) * 128;
-constexpr int kSubTileMax = ((kTileBytes / kConsumerWarps + 511) / 512) * 512; // bytes one warp owns per tile
-constexpr int kScanThreads = (kConsumerWarps + 1) * 32;
+// Geometry.  A tile (the planning unit, one 32-byte descriptor) is always 64 KiB of one unit; the
+// scan kernel cuts it into slices, the amount one warp scans per step.  Geometry is a template
+// parameter of the kernel, chosen per engine (memory-bound filters want big slices and a deep
+// ring, instruction-bound ones want as many warps as fit).
+constexpr int kTileBytes = 65536;
+constexpr int kPreMax = 256;              // most bytes kept in front of a slice (filter anchor look-behind)
+constexpr int kPostMax = 1056;            // most bytes kept behind a slice (verification look-ahead)
+constexpr int kSmemBudget = 227 * 1024;
+
+template <int W, int R, int S>
+struct Geom {
+	static constexpr int kWarps = W;          // warps per CTA, every one an independent scanner
+	static constexpr int kRing = R;           // slices in flight per warp
+	static constexpr int kSlice = S;          // bytes one warp scans per step (rows of 512)
+	static constexpr int kSlicesPerTile = kTileBytes / S;
+	static constexpr int kThreads = W * 32;
+};
+typedef Geom<16, 3, 4096> GeomStream;  // memory-bound: single-test literal filter
+typedef Geom<24, 4, 2048> GeomBalanced;
+typedef Geom<32, 3, 2048> GeomDense;   // instruction-bound: many filter tests / class runs
+typedef Geom<8, 3, 4096> GeomLong;     // patterns whose halo (up to 256 + 1056 bytes per slice) leaves room for few slots
+
+struct ScanGeom { int warps, ring, slice; }; // host-side mirror of the chosen Geom
 
 // One tile of one unit.  Built on the host when a batch is planned, 32 bytes.
 struct TileDesc {
@@ -26,8 +39,8 @@ struct TileDesc {
 };
 static_assert(sizeof(TileDesc) == 32, "TileDesc layout");
 
-// One segment == the part of one tile one consumer warp owns; candidates of a segment are
-// contiguous and ordered in the candidate buffer.  seg id = tile * kConsumerWarps + warp.
+// One segment == one slice; candidates of a segment are contiguous and ordered in the candidate
+// buffer.  seg id = tile * slices_per_tile + slice.
 struct SegEntry { uint32_t base, n; };
 
 // A candidate / match inside a unit.
@@ -66,7 +79,7 @@ struct ScanArgs {
 	uint32_t cand_cap;
 	unsigned long long *cursor; // [0]: candidates reserved so far
 	SegEntry *segs;
-	Cand *scratch;  // [gridDim.x * kConsumerWarps][kSubTileMax]
+	Cand *scratch;  // [gridDim.x * warps][slice bytes]: one private list per warp
 };
 
 } // namespace gscan

@@ -192,7 +192,7 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 		p->pre = 16;
 		p->post = round16((uint32_t)pr.run_min + 32u);
 	}
-	if (p->pre > (uint32_t)kPreMax || p->post > (uint32_t)kPostMax) {
+	if (p->pre > (uint32_t)kPreMax || p->post > (uint32_t)kPostMax || scan_smem_bytes(ScanGeom{8, 3, 4096}, p->pre, p->post) > (size_t)kSmemBudget) {
 		g_last_error = "gscan_compile: pattern too long for the shared-memory halo";
 		delete p;
 		return -1;
@@ -435,10 +435,12 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	}
 	if (ensure_pattern(ctx, pat) < 0) return -1;
 
-	const uint32_t n_segs = b->n_tiles * kConsumerWarps;
+	const ScanGeom geom = scan_geom((int)pat->prog.kind, pat->prog.kind == ENGINE_FIXED ? (uint32_t)pat->prog.tests.size() : 99u, pat->pre, pat->post);
+	const uint32_t spt = (uint32_t)(kTileBytes / geom.slice);
+	const uint32_t n_segs = b->n_tiles * spt;
 	const int grid = (int)std::min<uint32_t>((uint32_t)ctx->num_sms, b->n_tiles);
 	CK(ctx, ctx->segs.ensure(n_segs));
-	CK(ctx, ctx->scratch.ensure((size_t)ctx->num_sms * kConsumerWarps * kSubTileMax));
+	CK(ctx, ctx->scratch.ensure((size_t)ctx->num_sms * geom.warps * geom.slice));
 	CK(ctx, ctx->cursor.ensure(2));
 	CK(ctx, ctx->readback.ensure(64));
 	if (ctx->cand.cap == 0) {
@@ -462,8 +464,8 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		A.cand_cap = (uint32_t)std::min<size_t>(ctx->cand.cap, 0xffffffffu);
 		CK(ctx, cudaMemsetAsync(ctx->cursor.p, 0, 16, ctx->stream));
 		CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-		if (pat->prog.kind == ENGINE_FIXED) CK(ctx, launch_scan_fixed(A, ctx->pat_fixed, pat->prog.delta, grid, ctx->stream));
-		else CK(ctx, launch_scan_run(A, pat->run, grid, ctx->stream));
+		if (pat->prog.kind == ENGINE_FIXED) CK(ctx, launch_scan_fixed(A, ctx->pat_fixed, pat->prog.delta, geom, grid, ctx->stream));
+		else CK(ctx, launch_scan_run(A, pat->run, geom, grid, ctx->stream));
 		CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 		CK(ctx, cudaMemcpyAsync(h_cursor, ctx->cursor.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
 		CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -493,6 +495,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		R.tiles = b->d_tiles;
 		R.segs = ctx->segs.p;
 		R.n_segs = n_segs;
+		R.slices_per_tile = spt;
 		R.cand = ctx->cand.p;
 		R.units = b->d_units;
 		R.n_units = (uint32_t)b->units.size();

@@ -8,9 +8,10 @@
 
 namespace gscan {
 
-size_t scan_smem_bytes();
-cudaError_t launch_scan_fixed(const ScanArgs &A, const FixedParams &P, int delta, int grid, cudaStream_t st);
-cudaError_t launch_scan_run(const ScanArgs &A, const RunParams &P, int grid, cudaStream_t st);
+size_t scan_smem_bytes(const ScanGeom &g, uint32_t pre, uint32_t post);
+ScanGeom scan_geom(int engine, uint32_t n_tests_or_ranges, uint32_t pre, uint32_t post);
+cudaError_t launch_scan_fixed(const ScanArgs &A, const FixedParams &P, int delta, const ScanGeom &g, int grid, cudaStream_t st);
+cudaError_t launch_scan_run(const ScanArgs &A, const RunParams &P, const ScanGeom &g, int grid, cudaStream_t st);
 
 struct DevUnit {
 	uint64_t ptr;        // device address of the unit's bytes
@@ -22,6 +23,7 @@ struct ResolveArgs {
 	const TileDesc *tiles;
 	const SegEntry *segs;
 	uint32_t n_segs;
+	uint32_t slices_per_tile;
 	const Cand *cand;
 	const DevUnit *units;
 	uint32_t n_units;

@@ -2,24 +2,24 @@
 // /root/reference/src/grab.cc:175-213 (one pcre_exec per match) with one persistent streaming
 // pass over every byte of a batch of scan units.
 //
-// Structure (one CTA per SM, persistent):
-//   warp kConsumerWarps   producer: one lane walks this CTA's tiles and issues ONE 1-D TMA bulk
-//                         copy (cp.async.bulk, SASS UBLKCP) per tile into a kStages-deep shared-memory
-//                         ring, completion signalled through an mbarrier (complete_tx::bytes)
-//   warps 0..15           consumers: each owns a contiguous slice of the tile, reads it with
-//                         conflict-free 16-byte LDS (lane l <- bytes [16l,16l+16) of a 512-byte row),
-//                         runs the SWAR filter (4 bytes per 32-bit op) and, on the rare flagged
-//                         lane, verifies from shared memory.  Matches cross lane / warp / tile
-//                         borders through the halo kept in front of and behind every tile.
+// Structure (one CTA per SM, persistent, every warp independent):
+//   each warp owns a ring of kRing shared-memory slots.  Lane 0 issues one 1-D TMA bulk copy
+//   (cp.async.bulk, SASS UBLKCP) per slice of <= kSliceBytes (+ halo) into a slot, completion
+//   signalled through the slot's mbarrier (complete_tx::bytes); the warp waits on the barrier, reads
+//   the slice with conflict-free 16-byte LDS (lane l <- bytes [16l,16l+16) of a 512-byte row), runs
+//   the SWAR filter (4 bytes per 32-bit op) over the whole slice and, on the rare flagged lane,
+//   verifies from shared memory, then re-arms the slot for the slice kRing steps ahead.  Matches
+//   cross lane / row / slice / tile borders through the halo loaded in front of and behind a slice.
 // Output order: each warp appends its candidates in position order to a private scratch list and,
 // at the end of its slice, reserves a contiguous range of the global candidate buffer with one
 // atomicAdd and records (base, n) in the segment table.  Segment ids are position ordered, so the
 // resolve pass needs no sort.
 //
-// HBM traffic per tile: len + pre + post bytes read once (pre+post <= 3% at the default geometry),
-// 8 bytes of segment table written per 2 KiB scanned, candidates only where they exist.
+// HBM traffic: every byte once (the halos of neighbouring slices are fetched within microseconds of
+// each other and hit L2), 8 bytes of segment table written per slice, candidates only where they exist.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 
 #include "device_types.h"
 #include "swar.h"
@@ -70,18 +70,21 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
 }
 
 // ------------------------------------------------------------------------------------------
-// shared-memory layout
+// shared-memory layout: every warp owns kRing slots of (pre + kSliceBytes + post) bytes, one
+// mbarrier and one 32-byte slice descriptor per slot.  Nothing is shared between warps.
 // ------------------------------------------------------------------------------------------
-struct __align__(16) StageCtl {
-	uint64_t full[kStages];
-	uint64_t empty[kStages];
-	TileDesc desc[kStages];
+struct __align__(16) SlotCtl {
+	uint64_t full;
+	uint32_t off, ulen, tile_len, begin, niter, pad;
 };
 
-constexpr size_t kSmemBytes = (size_t)kStages * kStageStride + sizeof(StageCtl) + 128;
-size_t scan_smem_bytes() { return kSmemBytes; }
+size_t scan_smem_bytes(const ScanGeom &g, uint32_t pre, uint32_t post)
+{
+	const size_t slot = (size_t)pre + g.slice + post;
+	return (size_t)g.warps * g.ring * (slot + sizeof(SlotCtl));
+}
 
-// what a consumer warp knows about its slice of the current tile
+// what a warp knows about the slice it is scanning
 struct Slice {
 	const uint8_t *tile; // shared-memory address of the tile's byte 0
 	uint32_t off;        // offset of the tile in its unit
@@ -94,9 +97,10 @@ struct Emitter {
 	Cand *scratch; // this warp's private list (global memory, L2 resident)
 	uint32_t n;    // warp-uniform
 
-	// mm: per-lane 16-bit mask of matched bytes of the lane's chunk; lens via callback
+	// mm: per-lane 16-bit mask of matched bytes of the lane's chunk; lens via callback.
+	// Appends in (lane, bit) order == position order at dst; returns how many the warp wrote.
 	template <class LenFn>
-	__device__ __forceinline__ void emit(uint32_t mm, uint32_t pos0, LenFn len_of, uint32_t lane)
+	static __device__ __forceinline__ uint32_t emit_at(Cand *dst, uint32_t mm, uint32_t pos0, LenFn len_of, uint32_t lane)
 	{
 		uint32_t cnt = __popc(mm), incl = cnt;
 #pragma unroll
@@ -105,16 +109,16 @@ struct Emitter {
 			if ((int)lane >= d) incl += v;
 		}
 		uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-		uint32_t idx = n + incl - cnt;
+		uint32_t idx = incl - cnt;
 		while (mm) {
 			uint32_t b = __ffs(mm) - 1;
 			mm &= mm - 1;
 			Cand c;
 			c.pos = pos0 + b;
 			c.len = len_of(b);
-			scratch[idx++] = c;
+			dst[idx++] = c;
 		}
-		n += total;
+		return total;
 	}
 
 	__device__ __forceinline__ void flush(const ScanArgs &A, uint32_t seg, uint32_t lane)
@@ -144,19 +148,19 @@ struct FixedEngine {
 	typedef FixedParams Params;
 
 	// first sequence (in preference order) matching with its anchor byte at tile position p; 0: none
-	static __device__ uint32_t verify(const FixedParams &P, const Slice &S, int p)
+	static __device__ uint32_t verify(const FixedParams &P, const uint8_t *tile, uint32_t off, uint32_t ulen, int p)
 	{
 		const int q = p - (int)P.anchor;              // match start in tile coordinates (may be < 0: pre-halo)
-		const long long qu = (long long)S.off + q;    // ... in unit coordinates
+		const long long qu = (long long)off + q;      // ... in unit coordinates
 		if (qu < 0) return 0;
 		for (uint32_t s = 0; s < P.nseq; s++) {
 			const uint32_t len = P.seq_len[s];
-			if ((unsigned long long)qu + len > S.ulen) continue;
+			if ((unsigned long long)qu + len > ulen) continue;
 			const uint32_t *pp = P.seq_pos + P.seq_off[s];
 			uint32_t i = 0;
 			for (; i < len; i++) {
 				const uint32_t e = pp[i];
-				const uint32_t b = S.tile[q + (int)i];
+				const uint32_t b = tile[q + (int)i];
 				const uint32_t cls = e >> 16;
 				bool ok;
 				if (cls == 0xffffu) ok = (b & (e & 0xffu)) == ((e >> 8) & 0xffu);
@@ -168,46 +172,81 @@ struct FixedEngine {
 		return 0;
 	}
 
+	// SWAR filter over the lane's 16 bytes (+ D bytes of the next chunk); bit 7 of a byte set => candidate
+	static __device__ __forceinline__ uint32_t filter(const FixedParams &P, const uint32_t (&w)[5], uint32_t (&f)[4])
+	{
+		uint32_t acc = 0;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const uint32_t s = D ? __funnelshift_r(w[j], w[j + 1], 8 * D) : w[j];
+			uint32_t t = 0;
+#pragma unroll
+			for (int k = 0; k < K; k++) t |= pair_test(w[j], s, P.m0[k], P.v0[k], P.m1[k], P.v1[k]);
+			f[j] = t;
+			acc |= t;
+		}
+		return acc & kHigh;
+	}
+
+	// rare path for one 512-byte row: exact verification of every flagged byte, ordered emission
+	static __device__ __noinline__ uint32_t slow_row(const FixedParams &P, const uint8_t *tile, uint32_t off, uint32_t ulen,
+	                                                 uint32_t tile_len, Cand *dst, uint32_t lane, uint32_t c0,
+	                                                 uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3)
+	{
+		uint32_t mm = 0;
+		const uint32_t f[4] = {f0 & kHigh, f1 & kHigh, f2 & kHigh, f3 & kHigh};
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			uint32_t t = f[j];
+			while (t) {
+				const int byte = (__ffs(t) - 1) >> 3;
+				t &= t - 1;
+				const int p = (int)c0 + j * 4 + byte;
+				if (p < (int)tile_len && verify(P, tile, off, ulen, p)) mm |= 1u << (j * 4 + byte);
+			}
+		}
+		const uint32_t pos0 = off + c0 - P.anchor; // unit offset of a match anchored at chunk byte 0
+		return Emitter::emit_at(dst, mm, pos0, [&](uint32_t b) -> uint32_t {
+			return P.uniform_len ? P.uniform_len : verify(P, tile, off, ulen, (int)(c0 + b));
+		}, lane);
+	}
+
+	static __device__ __forceinline__ void load_row(const Slice &S, uint32_t c0, uint32_t (&w)[5])
+	{
+		const uint4 a = *reinterpret_cast<const uint4 *>(S.tile + c0);
+		w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+		w[4] = D ? *reinterpret_cast<const uint32_t *>(S.tile + c0 + 16) : 0u;
+	}
+
+	template <class G>
 	static __device__ __forceinline__ void run(const FixedParams &P, const Slice &S, Emitter &E, uint32_t lane)
 	{
-		for (uint32_t it = 0; it < S.niter; it++) {
-			const uint32_t c0 = S.begin + it * 512 + lane * 16;
-			const uint4 a = *reinterpret_cast<const uint4 *>(S.tile + c0);
-			uint32_t w[5];
-			w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-			w[4] = D ? *reinterpret_cast<const uint32_t *>(S.tile + c0 + 16) : 0u;
+		constexpr int kRows = G::kSlice / 512;
+		const uint32_t base = S.begin + lane * 16;
+		if (S.niter == (uint32_t)kRows) {
+			// whole slice at once: all loads first, one vote for the slice
+			uint32_t w[kRows][5], f[kRows][4];
+#pragma unroll
+			for (int r = 0; r < kRows; r++) load_row(S, base + r * 512, w[r]);
 			uint32_t acc = 0;
 #pragma unroll
-			for (int j = 0; j < 4; j++) {
-				const uint32_t s = D ? __funnelshift_r(w[j], w[j + 1], 8 * D) : w[j];
-#pragma unroll
-				for (int k = 0; k < K; k++) acc |= pair_test(w[j], s, P.m0[k], P.v0[k], P.m1[k], P.v1[k]);
-			}
-			acc &= kHigh;
+			for (int r = 0; r < kRows; r++) acc |= filter(P, w[r], f[r]);
 			if (__any_sync(0xffffffffu, acc != 0)) {
-				// rare path: exact verification of every flagged byte of this lane's chunk
-				uint32_t mm = 0;
-				if (acc) {
 #pragma unroll
-					for (int j = 0; j < 4; j++) {
-						const uint32_t s = D ? __funnelshift_r(w[j], w[j + 1], 8 * D) : w[j];
-						uint32_t f = 0;
-#pragma unroll
-						for (int k = 0; k < K; k++) f |= pair_test(w[j], s, P.m0[k], P.v0[k], P.m1[k], P.v1[k]);
-						f &= kHigh;
-						while (f) {
-							const int byte = (__ffs(f) - 1) >> 3;
-							f &= f - 1;
-							const int p = (int)c0 + j * 4 + byte;
-							if (p < (int)S.tile_len && verify(P, S, p)) mm |= 1u << (j * 4 + byte);
-						}
-					}
+				for (int r = 0; r < kRows; r++) {
+					const uint32_t a = (f[r][0] | f[r][1] | f[r][2] | f[r][3]) & kHigh;
+					if (__any_sync(0xffffffffu, a != 0))
+						E.n += slow_row(P, S.tile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, base + r * 512, f[r][0], f[r][1], f[r][2], f[r][3]);
 				}
-				const uint32_t pos0 = S.off + c0 - P.anchor; // unit offset of a match anchored at chunk byte 0
-				E.emit(mm, pos0, [&](uint32_t b) -> uint32_t {
-					return P.uniform_len ? P.uniform_len : verify(P, S, (int)(c0 + b));
-				}, lane);
 			}
+			return;
+		}
+		for (uint32_t it = 0; it < S.niter; it++) {
+			uint32_t w[5], f[4];
+			load_row(S, base + it * 512, w);
+			const uint32_t acc = filter(P, w, f);
+			if (__any_sync(0xffffffffu, acc != 0))
+				E.n += slow_row(P, S.tile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, base + it * 512, f[0], f[1], f[2], f[3]);
 		}
 	}
 };
@@ -247,6 +286,7 @@ struct RunEngine {
 		return r & valid;
 	}
 
+	template <class G>
 	static __device__ __forceinline__ void run(const RunParams &P, const Slice &S, Emitter &E, uint32_t lane)
 	{
 		if (S.niter == 0) return;
@@ -295,139 +335,189 @@ struct RunEngine {
 					}
 					cand = keep;
 				}
-				E.emit(cand, S.off + c0, [](uint32_t) -> uint32_t { return 0u; }, lane);
+				E.n += Emitter::emit_at(E.scratch + E.n, cand, S.off + c0, [](uint32_t) -> uint32_t { return 0u; }, lane);
 			}
 		}
 	}
 };
 
 // ------------------------------------------------------------------------------------------
-// the persistent kernel
+// the persistent kernel: warp-private TMA rings
 // ------------------------------------------------------------------------------------------
-template <class Eng>
-__global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename Eng::Params P)
+// Slice s = 16 * tile + j is the j-th of the (up to) 16 contiguous 512-byte-row-aligned parts of a
+// tile.  Warp g (of all warps of the grid) scans slices g, g + G, g + 2G, ...  Each warp keeps kRing
+// slices in flight: after finishing a slice its lane 0 re-arms the slot's mbarrier and issues the
+// bulk copy for the slice kRing steps ahead.  No producer warp, no "empty" barriers, no __syncthreads.
+template <class G>
+__device__ __forceinline__ void slice_geometry(const TileDesc &d, uint32_t j, uint32_t &begin, uint32_t &niter)
+{
+	const uint32_t sub = ((d.len + G::kSlicesPerTile - 1) / G::kSlicesPerTile + 511u) & ~511u;
+	begin = j * sub;
+	niter = 0;
+	if (begin < d.len) {
+		const uint32_t end = begin + sub < d.len ? begin + sub : d.len;
+		niter = (end - begin + 511u) >> 9;
+	}
+}
+
+template <class Eng, class G>
+__global__ void __launch_bounds__(G::kThreads, 1)
+scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename Eng::Params P)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
-	StageCtl *ctl = reinterpret_cast<StageCtl *>(smem + (size_t)kStages * kStageStride);
-
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	if (threadIdx.x == 0) {
-		for (int s = 0; s < kStages; s++) {
-			mbar_init(&ctl->full[s], 1);
-			mbar_init(&ctl->empty[s], kConsumerWarps);
-		}
+	const uint32_t slot_bytes = A.pre + G::kSlice + A.post;
+	uint8_t *my = smem + (size_t)warp * G::kRing * slot_bytes;
+	SlotCtl *ctl = reinterpret_cast<SlotCtl *>(smem + (size_t)G::kWarps * G::kRing * slot_bytes) + warp * G::kRing;
+
+	const uint32_t total = A.n_tiles * G::kSlicesPerTile;
+	const uint32_t stride = gridDim.x * G::kWarps;
+	const uint32_t first = blockIdx.x * G::kWarps + warp;
+
+	if (lane == 0) {
+		for (int s = 0; s < G::kRing; s++) mbar_init(&ctl[s].full, 1);
 		mbar_fence_init();
 	}
-	__syncthreads();
+	__syncwarp();
 
-	if (warp == kConsumerWarps) {
-		// ---------------- producer ----------------
-		if (lane == 0) {
-			uint32_t stage = 0, phase = 0;
-			for (uint32_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
-				mbar_wait(&ctl->empty[stage], phase ^ 1u);
-				const TileDesc d = A.tiles[t];
-				ctl->desc[stage] = d;
-				const uint32_t pre = d.off ? A.pre : 0u;
-				uint32_t body = (d.ulen - d.off + 15u) & ~15u; // bytes of the unit from the tile start, padded to 16
-				const uint32_t want = (uint32_t)kTileBytes + A.post;
-				if (body > want) body = want;
-				const uint32_t bytes = pre + body;
-				uint8_t *dst = smem + (size_t)stage * kStageStride + kPreMax - pre;
-				mbar_arrive_expect_tx(&ctl->full[stage], bytes);
-				tma_load_1d(dst, reinterpret_cast<const void *>(d.src - pre), bytes, &ctl->full[stage]);
-				if (++stage == kStages) { stage = 0; phase ^= 1u; }
-			}
+	// lane 0: describe slice `s` in slot `slot` and start its copy
+	auto issue = [&](uint32_t slot, uint32_t s, const TileDesc &d) {
+		uint32_t begin, niter;
+		slice_geometry<G>(d, s % G::kSlicesPerTile, begin, niter);
+		SlotCtl *c = &ctl[slot];
+		c->off = d.off; c->ulen = d.ulen; c->tile_len = d.len; c->begin = begin; c->niter = niter;
+		if (niter == 0) { mbar_arrive(&c->full); return; }
+		const uint32_t pre = (d.off + begin) ? A.pre : 0u;
+		uint32_t body = (d.ulen - d.off - begin + 15u) & ~15u; // rest of the unit from the slice start, padded to 16
+		const uint32_t want = niter * 512u + A.post;
+		if (body > want) body = want;
+		const uint32_t bytes = pre + body;
+		uint8_t *dst = my + (size_t)slot * slot_bytes + A.pre - pre;
+		mbar_arrive_expect_tx(&c->full, bytes);
+		tma_load_1d(dst, reinterpret_cast<const void *>(d.src + begin - pre), bytes, &c->full);
+	};
+
+	if (lane == 0) {
+		for (uint32_t k = 0; k < (uint32_t)G::kRing; k++) {
+			const uint32_t s = first + k * stride;
+			if (s < total) issue(k, s, A.tiles[s / G::kSlicesPerTile]);
 		}
-		return;
 	}
+	__syncwarp();
 
-	// ---------------- consumers ----------------
 	Emitter E;
-	E.scratch = A.scratch + ((size_t)blockIdx.x * kConsumerWarps + warp) * kSubTileMax;
+	E.scratch = A.scratch + ((size_t)blockIdx.x * G::kWarps + warp) * G::kSlice;
 	E.n = 0;
-	uint32_t stage = 0, phase = 0;
-	for (uint32_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
-		mbar_wait(&ctl->full[stage], phase);
-		const TileDesc d = ctl->desc[stage];
+	uint32_t slot = 0, phase = 0;
+	for (uint32_t s = first; s < total; s += stride) {
+		// descriptor of the slice that will reuse this slot: fetched now, needed after the scan
+		const uint32_t nxt = s + G::kRing * stride;
+		TileDesc dn;
+		if (lane == 0 && nxt < total) dn = A.tiles[nxt / G::kSlicesPerTile];
+
+		mbar_wait(&ctl[slot].full, phase);
 		Slice S;
-		S.tile = smem + (size_t)stage * kStageStride + kPreMax;
-		S.off = d.off;
-		S.ulen = d.ulen;
-		S.tile_len = d.len;
-		// slice length: a multiple of 512 so that every warp row is 32 x 16 contiguous bytes
-		const uint32_t sub = ((d.len + kConsumerWarps - 1) / kConsumerWarps + 511u) & ~511u;
-		S.begin = warp * sub;
-		S.niter = 0;
-		if (S.begin < d.len) {
-			const uint32_t end = S.begin + sub < d.len ? S.begin + sub : d.len;
-			S.niter = (end - S.begin + 511u) >> 9;
-		}
-		Eng::run(P, S, E, lane);
-		E.flush(A, t * kConsumerWarps + warp, lane);
-		__syncwarp();
-		if (lane == 0) mbar_arrive(&ctl->empty[stage]);
-		if (++stage == kStages) { stage = 0; phase ^= 1u; }
+		S.off = ctl[slot].off;
+		S.ulen = ctl[slot].ulen;
+		S.tile_len = ctl[slot].tile_len;
+		S.begin = ctl[slot].begin;
+		S.niter = ctl[slot].niter;
+		S.tile = my + (size_t)slot * slot_bytes + A.pre - S.begin; // address of tile byte 0 (only the slice window is loaded)
+		Eng::template run<G>(P, S, E, lane);
+		E.flush(A, s, lane);
+		__syncwarp(); // every lane is done reading the slot before it is overwritten
+		if (lane == 0 && nxt < total) issue(slot, nxt, dn);
+		if (++slot == (uint32_t)G::kRing) { slot = 0; phase ^= 1u; }
 	}
 }
 
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-template <class Eng>
-static cudaError_t launch(const ScanArgs &A, const typename Eng::Params &P, int grid, cudaStream_t st)
+template <class Eng, class G>
+static cudaError_t launch_g(const ScanArgs &A, const typename Eng::Params &P, int grid, cudaStream_t st)
 {
-	static bool configured = false; // per instantiation; attribute is per-device but idempotent
-	cudaError_t e = cudaFuncSetAttribute(scan_kernel<Eng>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+	const ScanGeom g{G::kWarps, G::kRing, G::kSlice};
+	const size_t smem = scan_smem_bytes(g, A.pre, A.post);
+	cudaError_t e = cudaFuncSetAttribute(scan_kernel<Eng, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
-	configured = true;
-	(void)configured;
-	scan_kernel<Eng><<<grid, kScanThreads, kSmemBytes, st>>>(A, P);
+	scan_kernel<Eng, G><<<grid, G::kThreads, smem, st>>>(A, P);
 	return cudaGetLastError();
 }
 
-template <int D>
-static cudaError_t launch_fixed_d(const ScanArgs &A, const FixedParams &P, int grid, cudaStream_t st)
+template <class Eng>
+static cudaError_t launch(const ScanArgs &A, const typename Eng::Params &P, const ScanGeom &g, int grid, cudaStream_t st)
 {
-	switch (P.ntests) {
-	case 1: return launch<FixedEngine<D, 1>>(A, P, grid, st);
-	case 2: return launch<FixedEngine<D, 2>>(A, P, grid, st);
-	case 3: return launch<FixedEngine<D, 3>>(A, P, grid, st);
-	case 4: return launch<FixedEngine<D, 4>>(A, P, grid, st);
-	case 5: case 6: return launch<FixedEngine<D, 6>>(A, P, grid, st);
-	default: return launch<FixedEngine<D, 8>>(A, P, grid, st);
+	if (g.warps == GeomStream::kWarps) return launch_g<Eng, GeomStream>(A, P, grid, st);
+	if (g.warps == GeomBalanced::kWarps) return launch_g<Eng, GeomBalanced>(A, P, grid, st);
+	if (g.warps == GeomDense::kWarps) return launch_g<Eng, GeomDense>(A, P, grid, st);
+	return launch_g<Eng, GeomLong>(A, P, grid, st);
+}
+
+static ScanGeom geom_by_index(int i)
+{
+	switch (i) {
+	case 0: return ScanGeom{GeomStream::kWarps, GeomStream::kRing, GeomStream::kSlice};
+	case 1: return ScanGeom{GeomBalanced::kWarps, GeomBalanced::kRing, GeomBalanced::kSlice};
+	case 2: return ScanGeom{GeomDense::kWarps, GeomDense::kRing, GeomDense::kSlice};
+	default: return ScanGeom{GeomLong::kWarps, GeomLong::kRing, GeomLong::kSlice};
 	}
 }
 
-cudaError_t launch_scan_fixed(const ScanArgs &A, const FixedParams &P, int delta, int grid, cudaStream_t st)
+// which geometry an engine runs with; GSCAN_GEOM=0..3 overrides (tuning)
+ScanGeom scan_geom(int engine, uint32_t n_tests_or_ranges, uint32_t pre, uint32_t post)
+{
+	int idx = (engine == 1 /*FIXED*/ && n_tests_or_ranges <= 1) ? 0 : 1;
+	if (const char *e = getenv("GSCAN_GEOM")) idx = atoi(e);
+	if (idx < 0 || idx > 3) idx = 3;
+	if (scan_smem_bytes(geom_by_index(idx), pre, post) <= (size_t)kSmemBudget) return geom_by_index(idx);
+	for (int t = 0; t < 3; t++) // long patterns need big halos: first geometry whose ring still fits
+		if (scan_smem_bytes(geom_by_index(t), pre, post) <= (size_t)kSmemBudget) return geom_by_index(t);
+	return geom_by_index(3);
+}
+
+template <int D>
+static cudaError_t launch_fixed_d(const ScanArgs &A, const FixedParams &P, const ScanGeom &g, int grid, cudaStream_t st)
+{
+	switch (P.ntests) {
+	case 1: return launch<FixedEngine<D, 1>>(A, P, g, grid, st);
+	case 2: return launch<FixedEngine<D, 2>>(A, P, g, grid, st);
+	case 3: return launch<FixedEngine<D, 3>>(A, P, g, grid, st);
+	case 4: return launch<FixedEngine<D, 4>>(A, P, g, grid, st);
+	case 5: case 6: return launch<FixedEngine<D, 6>>(A, P, g, grid, st);
+	default: return launch<FixedEngine<D, 8>>(A, P, g, grid, st);
+	}
+}
+
+cudaError_t launch_scan_fixed(const ScanArgs &A, const FixedParams &P, int delta, const ScanGeom &g, int grid, cudaStream_t st)
 {
 	switch (delta) {
-	case 0: return launch_fixed_d<0>(A, P, grid, st);
-	case 1: return launch_fixed_d<1>(A, P, grid, st);
-	case 2: return launch_fixed_d<2>(A, P, grid, st);
-	default: return launch_fixed_d<3>(A, P, grid, st);
+	case 0: return launch_fixed_d<0>(A, P, g, grid, st);
+	case 1: return launch_fixed_d<1>(A, P, g, grid, st);
+	case 2: return launch_fixed_d<2>(A, P, g, grid, st);
+	default: return launch_fixed_d<3>(A, P, g, grid, st);
 	}
 }
 
 template <int NHI>
-static cudaError_t launch_run_h(const ScanArgs &A, const RunParams &P, int grid, cudaStream_t st)
+static cudaError_t launch_run_h(const ScanArgs &A, const RunParams &P, const ScanGeom &g, int grid, cudaStream_t st)
 {
 	switch (P.nlo) {
-	case 0: case 1: return launch<RunEngine<1, NHI>>(A, P, grid, st);
-	case 2: return launch<RunEngine<2, NHI>>(A, P, grid, st);
-	case 3: return launch<RunEngine<3, NHI>>(A, P, grid, st);
-	case 4: return launch<RunEngine<4, NHI>>(A, P, grid, st);
-	case 5: case 6: return launch<RunEngine<6, NHI>>(A, P, grid, st);
-	default: return launch<RunEngine<8, NHI>>(A, P, grid, st);
+	case 0: case 1: return launch<RunEngine<1, NHI>>(A, P, g, grid, st);
+	case 2: return launch<RunEngine<2, NHI>>(A, P, g, grid, st);
+	case 3: return launch<RunEngine<3, NHI>>(A, P, g, grid, st);
+	case 4: return launch<RunEngine<4, NHI>>(A, P, g, grid, st);
+	case 5: case 6: return launch<RunEngine<6, NHI>>(A, P, g, grid, st);
+	default: return launch<RunEngine<8, NHI>>(A, P, g, grid, st);
 	}
 }
 
-cudaError_t launch_scan_run(const ScanArgs &A, const RunParams &P, int grid, cudaStream_t st)
+cudaError_t launch_scan_run(const ScanArgs &A, const RunParams &P, const ScanGeom &g, int grid, cudaStream_t st)
 {
 	switch (P.nhi) {
-	case 0: return launch_run_h<0>(A, P, grid, st);
-	case 1: return launch_run_h<1>(A, P, grid, st);
-	default: return launch_run_h<2>(A, P, grid, st);
+	case 0: return launch_run_h<0>(A, P, g, grid, st);
+	case 1: return launch_run_h<1>(A, P, g, grid, st);
+	default: return launch_run_h<2>(A, P, g, grid, st);
 	}
 }
 

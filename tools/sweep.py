@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Geometry sweep helper (tuning only): times the scan kernel for GSCAN_GEOM=0..3 on the same
+device-resident corpus.  Usage: python tools/sweep.py [corpus_gib] [geoms]"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHILD = r'''
+import sys, json, os
+sys.path.insert(0, %r)
+sys.path.insert(0, %r + "/tests")
+import numpy as np
+import grab_b200 as G
+import corpus
+gib = float(sys.argv[1])
+ctx = G.Context(0)
+n = int(gib * 1024)
+d = ctx.device_alloc(n << 20)
+ctx.synth_corpus(d, 2, 0, n, 1 << 20, needle=b"foobardoesexist", needle_every=64)
+batch = ctx.batch_create(G.Context.device_units(d, n, 1 << 20))
+out = {}
+for name, pat, lit in (("literal", "foobardoesexist", True), ("alt4", "foo|bar|baz|quux", False), ("run16", "[A-Za-z0-9_]{16,}", False), ("lit2", "qz", False), ("icase", "(?i)linus", False)):
+    p = G.Pattern(pat, literal=lit)
+    ms = []
+    for i in range(6):
+        r = ctx.batch_scan(p, batch)
+        ms.append(ctx.stats()["scan_kernel_ms"])
+    st = ctx.stats()
+    out[name] = {"best_ms": min(ms[1:]), "med_ms": sorted(ms[1:])[len(ms[1:]) // 2], "gbs": (n << 20) / (min(ms[1:]) * 1e-3) / 1e9,
+                 "matches": int(len(r)), "resolve_ms": st["resolve_ms"], "total_ms": st["total_ms"]}
+probe = min(ctx.read_probe(d, n << 20)[0] for _ in range(3))
+out["read_probe_gbs"] = (n << 20) / (probe * 1e-3) / 1e9
+print(json.dumps(out))
+''' % (ROOT, ROOT)
+
+
+def main():
+    gib = sys.argv[1] if len(sys.argv) > 1 else "16"
+    geoms = sys.argv[2].split(",") if len(sys.argv) > 2 else ["0", "1", "2", "3"]
+    for g in geoms:
+        env = dict(os.environ, GSCAN_GEOM=g)
+        p = subprocess.run([sys.executable, "-c", CHILD, gib], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+        if p.returncode != 0:
+            print("geom", g, "FAILED", p.stderr.decode()[-300:])
+            continue
+        o = json.loads(p.stdout.decode().strip().splitlines()[-1])
+        print("geom %s probe %6.0f | " % (g, o["read_probe_gbs"]) + " | ".join(
+            "%s %6.0f GB/s (%d m, res %.2f ms)" % (k, v["gbs"], v["matches"], v["resolve_ms"]) for k, v in o.items() if isinstance(v, dict)), flush=True)
+
+
+if __name__ == "__main__":
+    main()
