@@ -18,7 +18,6 @@ import shutil
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -37,34 +36,47 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe):
+    one nvidia-smi process looping every 20 ms, started just before and stopped just after."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.p = index, [], None
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=5).stdout.decode().strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.05)
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+            time.sleep(0.15)  # first sample lands before the timed region starts
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return
+        time.sleep(0.03)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0].decode()
+        except Exception:
+            out = ""
+        for line in out.splitlines():
+            r = [x.strip() for x in line.split(",")]
+            if len(r) >= 6 and r[0].isdigit():
+                self.rows.append(r)
 
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        sm = sorted(int(r[0]) for r in self.rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        pw = [float(r[6]) for r in self.rows if len(r) > 6 and r[6].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows), "power_w_max": max(pw) if pw else None}
 
 
 def _gen_file(args):
@@ -163,7 +175,7 @@ def run_reference(a, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--corpus-gib", type=float, default=64.0, help="device-resident corpus per GPU")
@@ -208,16 +220,12 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    counts = torch.zeros(world, dtype=torch.int64, device="cuda")
-    mine = torch.zeros(1, dtype=torch.int64, device="cuda")
+    from grab_b200 import shard
+    state = {"counts": None}
 
     def step():
         r = ctx.batch_scan(pat, batch, G.MODE_ALL)
-        if world > 1:  # the one collective of the path: all-gather of per-rank match counts
-            mine[0] = len(r)
-            dist.all_gather_into_tensor(counts, mine)
-        else:
-            counts[0] = len(r)
+        state["counts"] = shard.gather_counts(len(r))  # the one collective of the path (NCCL all-gather of match counts)
         return r
 
     for _ in range(a.warmup):
@@ -241,8 +249,8 @@ def main():
 
     # ---- timed region: K resident steps ----
     sampler = ClockSampler(local_rank)
-    sampler.start()
     kernel_ms, launches = [], 0
+    sampler.start()
     sync_all()
     t0 = time.perf_counter()
     for _ in range(a.steps):
@@ -252,7 +260,7 @@ def main():
         launches += st["total_launches"]
     sync_all()
     dt = time.perf_counter() - t0
-    sampler.stop_flag = True
+    sampler.stop()
     if world > 1:
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -291,7 +299,7 @@ def main():
                        "sharding": "files by rank, no data-path collective; one all-gather of match counts per step",
                        "l2": "inputs larger than L2 (%.0f GiB vs 126 MB), no flush" % (corpus_bytes / GiB)},
             "roofline": roofline, "clocks": sampler.summary(), "gpu_launches": launches,
-            "parity": "ok" if parity else "MISMATCH", "matches_per_step": int(counts.sum().item()), "natural_hits": int(extra)}
+            "parity": "ok" if parity else "MISMATCH", "matches_per_step": int(state["counts"].sum()), "natural_hits": int(extra)}
 
     if rank == 0 and world == 1 and not a.quick:
         # ---- e2e: host buffers through gscan_scan_batch (pinned host memory, H2D + scan + D2H timed) ----

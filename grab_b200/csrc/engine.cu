@@ -79,6 +79,7 @@ struct gscan_batch {
 	uint32_t n_tiles = 0;
 	uint64_t bytes = 0;
 	float h2d_ms = 0;
+	bool pooled = false;         // device buffers belong to the context (gscan_scan_batch's transient batches)
 };
 
 struct gscan_ctx {
@@ -101,6 +102,10 @@ struct gscan_ctx {
 	PinnedBuf readback, out_host, stage[2];
 	DevBuf<unsigned long long> probe_sum;
 	DevBuf<uint8_t> needle;
+	// pools behind the transient batches of gscan_scan_batch (grow-only: no cudaMalloc/cudaFree per call)
+	DevBuf<uint8_t> pool_arena;
+	DevBuf<TileDesc> pool_tiles;
+	DevBuf<DevUnit> pool_units;
 };
 
 static thread_local std::string g_last_error;
@@ -264,6 +269,7 @@ extern "C" void gscan_close(gscan_ctx *c)
 	c->segs.release(); c->cand.release(); c->scratch.release(); c->ord.release(); c->out.release();
 	c->unit_start.release(); c->unit_out.release(); c->blk.release(); c->cursor.release(); c->pat_tables.release();
 	c->probe_sum.release(); c->needle.release();
+	c->pool_arena.release(); c->pool_tiles.release(); c->pool_units.release();
 	c->readback.release(); c->out_host.release(); c->stage[0].release(); c->stage[1].release();
 	for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
 	cudaStreamDestroy(c->stream);
@@ -286,19 +292,29 @@ extern "C" void gscan_batch_free(gscan_ctx *ctx, gscan_batch *b)
 {
 	if (!b) return;
 	if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-	if (b->d_tiles) cudaFree(b->d_tiles);
-	if (b->d_units) cudaFree(b->d_units);
-	if (b->d_arena) cudaFree(b->d_arena);
+	if (!b->pooled) {
+		if (b->d_tiles) cudaFree(b->d_tiles);
+		if (b->d_units) cudaFree(b->d_units);
+		if (b->d_arena) cudaFree(b->d_arena);
+	}
 	delete b;
 }
 
+static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units, bool pooled, gscan_batch **out);
+
 extern "C" int gscan_batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units, gscan_batch **out)
+{
+	return batch_create(ctx, units, n_units, false, out);
+}
+
+static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units, bool pooled, gscan_batch **out)
 {
 	if (!ctx || !out || (n_units && !units)) return fail(ctx, "gscan_batch_create: null argument");
 	*out = nullptr;
 	CK(ctx, cudaSetDevice(ctx->device));
 	gscan_batch *b = new (std::nothrow) gscan_batch;
 	if (!b) return fail(ctx, "gscan_batch_create: out of memory");
+	b->pooled = pooled;
 	struct Guard { gscan_ctx *c; gscan_batch *b; ~Guard() { if (b) gscan_batch_free(c, b); } } guard{ctx, b};
 
 	// pass 1: validate, size the staging arena
@@ -318,7 +334,10 @@ extern "C" int gscan_batch_create(gscan_ctx *ctx, const gscan_unit *units, size_
 		n_tiles64 += (u.len + kTileBytes - 1) / kTileBytes;
 	}
 	if (n_tiles64 >= (1ull << 27)) return fail(ctx, "gscan_batch_create: batch too large (more than 4 TiB of tiles)");
-	if (arena_bytes) CK(ctx, cudaMalloc(&b->d_arena, arena_bytes + 256));
+	if (arena_bytes) {
+		if (pooled) { CK(ctx, ctx->pool_arena.ensure(arena_bytes + 256)); b->d_arena = ctx->pool_arena.p; }
+		else CK(ctx, cudaMalloc(&b->d_arena, arena_bytes + 256));
+	}
 
 	// pass 2: stage host units, build tile and unit tables
 	std::vector<TileDesc> tiles;
@@ -326,6 +345,9 @@ extern "C" int gscan_batch_create(gscan_ctx *ctx, const gscan_unit *units, size_
 	tiles.reserve((size_t)n_tiles64);
 	auto t0 = std::chrono::steady_clock::now();
 	int sb = 0;
+	const uint8_t *run_src = nullptr;
+	uint8_t *run_dst = nullptr;
+	size_t run_len = 0;
 	bool staged[2] = {false, false};
 	cudaEvent_t sev[2] = {ctx->ev[2], ctx->ev[3]};
 	for (size_t i = 0; i < n_units; i++) {
@@ -341,7 +363,13 @@ extern "C" int gscan_batch_create(gscan_ctx *ctx, const gscan_unit *units, size_
 			bool pinned = cudaPointerGetAttributes(&attr, u.ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost;
 			cudaGetLastError();
 			if (pinned) {
-				CK(ctx, cudaMemcpyAsync(dst, u.ptr, u.len, cudaMemcpyHostToDevice, ctx->stream));
+				// host units that are contiguous in memory (and 256-byte multiples, so contiguous in the arena too) go as one copy
+				if (run_len && run_src + run_len == u.ptr && run_dst + run_len == dst && run_len < ((size_t)1 << 30)) {
+					run_len += u.len;
+				} else {
+					if (run_len) CK(ctx, cudaMemcpyAsync(run_dst, run_src, run_len, cudaMemcpyHostToDevice, ctx->stream));
+					run_src = u.ptr; run_dst = dst; run_len = u.len;
+				}
 			} else {
 				// pageable memory (the reference's mmap windows): bounce through two pinned buffers
 				const size_t kChunk = 16u << 20;
@@ -376,10 +404,18 @@ extern "C" int gscan_batch_create(gscan_ctx *ctx, const gscan_unit *units, size_
 		}
 		b->bytes += u.len;
 	}
+	if (run_len) CK(ctx, cudaMemcpyAsync(run_dst, run_src, run_len, cudaMemcpyHostToDevice, ctx->stream));
 	b->n_tiles = (uint32_t)tiles.size();
 	if (!tiles.empty()) {
-		CK(ctx, cudaMalloc(&b->d_tiles, tiles.size() * sizeof(TileDesc)));
-		CK(ctx, cudaMalloc(&b->d_units, dunits.size() * sizeof(DevUnit)));
+		if (pooled) {
+			CK(ctx, ctx->pool_tiles.ensure(tiles.size()));
+			CK(ctx, ctx->pool_units.ensure(dunits.size()));
+			b->d_tiles = ctx->pool_tiles.p;
+			b->d_units = ctx->pool_units.p;
+		} else {
+			CK(ctx, cudaMalloc(&b->d_tiles, tiles.size() * sizeof(TileDesc)));
+			CK(ctx, cudaMalloc(&b->d_units, dunits.size() * sizeof(DevUnit)));
+		}
 		CK(ctx, cudaMemcpyAsync(b->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, ctx->stream));
 		CK(ctx, cudaMemcpyAsync(b->d_units, dunits.data(), dunits.size() * sizeof(DevUnit), cudaMemcpyHostToDevice, ctx->stream));
 	}
@@ -560,7 +596,7 @@ extern "C" int gscan_scan_batch(gscan_ctx *ctx, const gscan_pattern *pat, const 
 	if (!ctx || !pat || !out || !n_out) return fail(ctx, "gscan_scan_batch: null argument");
 	auto t0 = std::chrono::steady_clock::now();
 	gscan_batch *b = nullptr;
-	if (gscan_batch_create(ctx, units, n_units, &b) < 0) return -1;
+	if (batch_create(ctx, units, n_units, true, &b) < 0) return -1;
 	int rc = gscan_batch_scan(ctx, pat, b, mode, out, n_out);
 	gscan_batch_free(ctx, b);
 	ctx->stats.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();

@@ -1,0 +1,251 @@
+// filegrep.cc -- see filegrep.h.  Host C++ only; the scan itself is gscan_scan_batch().
+#include "filegrep.h"
+
+#include <fcntl.h>
+#include <ftw.h>
+#include <pthread.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <cerrno>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+
+#include "../../include/gscan.h"
+
+namespace grab_b200 {
+
+// one lock around stdout, like stdout_lock of grab.cc:56,219-225
+static pthread_mutex_t g_stdout_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static const char kStartInv[] = "\33[7m", kStopInv[] = "\33[27m"; // grab.cc:66-67
+
+FileGrep::FileGrep() : FileGrep(0) {}
+
+FileGrep::FileGrep(int device) : d_device(device) { d_my_uid = geteuid(); }
+
+FileGrep::~FileGrep()
+{
+	flush();
+	if (d_pat) gscan_free_pattern(d_pat);
+	if (d_ctx) gscan_close(d_ctx);
+}
+
+void FileGrep::config(const std::map<std::string, size_t> &config)
+{
+	if (config.count("color") > 0) d_colored = true;
+	if (config.count("noline") > 0) d_print_line = false;
+	if (config.count("offsets") > 0) d_print_offset = true;
+	if (config.count("single") > 0) d_single_match = true;
+	if (config.count("low_mem") > 0) d_low_mem = true;
+	if (config.count("literal") > 0) d_literal = true;
+	if (config.count("lenient") > 0) d_strict = false;
+	auto it = config.find("chunk_size");
+	if (it != config.end()) d_chunk_size = it->second;
+	it = config.find("device");
+	if (it != config.end()) d_device = (int)it->second;
+}
+
+int FileGrep::prepare(const std::string &regex)
+{
+	uint32_t flags = (d_literal ? GSCAN_LITERAL : 0u) | (d_strict ? GSCAN_STRICT_REF : 0u);
+	if (d_pat) { gscan_free_pattern(d_pat); d_pat = nullptr; }
+	if (gscan_compile(regex.c_str(), regex.size(), flags, &d_pat) != 0) {
+		// the reference reports "FileGrep::prepare::pcre_compile error" (grab.cc:107); keep that prefix, add the reason
+		d_err = std::string("FileGrep::prepare::pcre_compile error (") + gscan_last_error() + ")";
+		return -1;
+	}
+	d_minlen = gscan_minlen(d_pat);
+	return 0;
+}
+
+int FileGrep::ensure_ctx()
+{
+	if (d_ctx) return 0;
+	d_ctx = gscan_open(d_device);
+	if (!d_ctx) {
+		d_err = std::string("FileGrep::find::gscan_open: ") + gscan_last_error();
+		return -1;
+	}
+	return 0;
+}
+
+void FileGrep::release(Window &w)
+{
+	if (w.map) munmap(w.map, w.clen); // grab.cc:215
+	w.map = nullptr;
+}
+
+int FileGrep::find(const char *path, const struct stat *st, int)
+{
+	if (!d_pat) { d_err = "FileGrep::find: no pattern prepared"; return -1; }
+	size_t clen = (size_t)st->st_size;
+	if ((size_t)d_minlen > clen) return 0; // grab.cc:133-135
+
+	int fd = -1, flags = O_RDONLY | O_NOCTTY;
+#ifdef __linux__
+	if (st->st_uid == d_my_uid || d_my_uid == 0) flags |= O_NOATIME; // grab.cc:139-143
+#endif
+	if ((fd = open(path, flags)) < 0) {
+		d_err = "FileGrep::find::open: " + std::string(strerror(errno));
+		return -1;
+	}
+	const off_t overlap = 0x1000; // grab.cc:151
+	const uint32_t seq = d_file_seq++;
+	for (off_t off = 0; off < st->st_size; off += ((off_t)d_chunk_size - overlap)) { // grab.cc:154
+		clen = (st->st_size - off < (off_t)d_chunk_size) ? (size_t)(st->st_size - off) : d_chunk_size;
+		void *m = mmap(nullptr, clen, PROT_READ, MAP_PRIVATE | MAP_NORESERVE, fd, off); // grab.cc:126-128,161
+		if (m == MAP_FAILED) {
+			d_err = "FileGrep::find::mmap: " + std::string(strerror(errno));
+			close(fd);
+			return -1;
+		}
+		if (clen > 4 * 0x1000 && !d_single_match) posix_madvise(m, clen, POSIX_MADV_SEQUENTIAL); // grab.cc:168-169
+		Window w;
+		w.path = path;
+		w.map = static_cast<uint8_t *>(m);
+		w.clen = clen;
+		w.off = (uint64_t)off;
+		w.file_seq = seq;
+		d_queue.push_back(std::move(w));
+		d_queued_bytes += clen;
+		if (d_queued_bytes >= d_batch_bytes && flush() < 0) { close(fd); return -1; }
+	}
+	close(fd);
+	return 0;
+}
+
+// the bytes the reference appends to its ostringstream for one window (grab.cc:175-213), given the
+// matches the engine selected for it
+struct gscan_match_view { uint64_t start; uint32_t len; };
+
+void FileGrep::format_window(const Window &w, const gscan_match_view *m, size_t n, std::string &out) const
+{
+	char num[32];
+	uint64_t search_start = w.off; // `start` of grab.cc:172, as an absolute offset
+	for (size_t i = 0; i < n; i++) {
+		if (d_recursive || d_print_path) { out += w.path; out += ':'; }     // grab.cc:182-183
+		if (d_print_offset) {                                               // grab.cc:185-186
+			out += "Match at offset ";
+			snprintf(num, sizeof(num), "%llu", (unsigned long long)m[i].start);
+			out += num;
+			out += '\n';
+		}
+		if (d_print_line) {                                                 // grab.cc:188-203
+			const uint8_t *base = w.map;
+			const size_t ms = (size_t)(m[i].start - w.off), me = ms + m[i].len, lo = (size_t)(search_start - w.off);
+			size_t b = 0, a = 0;
+			while (ms - b > lo && base[ms - b - 1] != '\n' && b < 511) b++;
+			while (me + a < w.clen && base[me + a] != '\n' && a < 511) a++;
+			out.append(reinterpret_cast<const char *>(base + ms - b), b);
+			if (d_colored) out += kStartInv;
+			out.append(reinterpret_cast<const char *>(base + ms), m[i].len);
+			if (d_colored) out += kStopInv;
+			out.append(reinterpret_cast<const char *>(base + me), a);
+			out += '\n';
+			search_start = w.off + me + a;                                  // grab.cc:209
+		} else if (!d_print_offset) {                                       // grab.cc:204-207
+			out += "matches\n";
+			break;
+		} else {
+			search_start = m[i].start + m[i].len;
+		}
+		if (d_single_match) break;                                          // grab.cc:211-212
+	}
+}
+
+int FileGrep::flush()
+{
+	if (d_queue.empty()) return 0;
+	if (ensure_ctx() < 0) {
+		for (auto &w : d_queue) release(w);
+		d_queue.clear();
+		d_queued_bytes = 0;
+		return -1;
+	}
+	std::vector<gscan_unit> units(d_queue.size());
+	for (size_t i = 0; i < d_queue.size(); i++) {
+		units[i].ptr = d_queue[i].map;
+		units[i].len = d_queue[i].clen;
+		units[i].base_off = d_queue[i].off;
+		units[i].file_id = (uint32_t)i; // index of the window in this batch
+		units[i].flags = 0;
+	}
+	uint32_t mode = GSCAN_MODE_ALL;
+	if (d_print_line) mode = GSCAN_MODE_LINE;                 // resume after the printed line (grab.cc:188-209)
+	else if (!d_print_offset) mode = GSCAN_MODE_FIRST;        // "matches" once per window (grab.cc:204-207)
+	if (d_single_match) mode = GSCAN_MODE_FIRST;              // grab.cc:211-212
+	gscan_match *matches = nullptr;
+	size_t n = 0;
+	int rc = gscan_scan_batch(d_ctx, d_pat, units.data(), units.size(), mode, &matches, &n);
+	if (rc < 0) d_err = std::string("FileGrep::find::scan: ") + gscan_why(d_ctx);
+
+	// per window, in queue order: format, then flush under the lock (grab.cc:217-234)
+	std::vector<gscan_match_view> view;
+	std::string out;
+	size_t k = 0;
+	bool have_done = false;
+	uint32_t done_seq = 0;
+	for (size_t i = 0; i < d_queue.size() && rc == 0; i++) {
+		view.clear();
+		while (k < n && matches[k].file_id == (uint32_t)i) {
+			view.push_back(gscan_match_view{matches[k].start, matches[k].match_len});
+			k++;
+		}
+		// -s: once a window of a file printed something, the rest of the file is skipped (grab.cc:232-233)
+		if (d_single_match && have_done && done_seq == d_queue[i].file_seq) continue;
+		if (view.empty()) continue;
+		out.clear();
+		format_window(d_queue[i], view.data(), view.size(), out);
+		if (!out.empty()) {
+			pthread_mutex_lock(&g_stdout_lock);
+			std::cout << out;
+			pthread_mutex_unlock(&g_stdout_lock);
+			if (d_single_match) { have_done = true; done_seq = d_queue[i].file_seq; }
+		}
+	}
+	std::cout.flush();
+	if (matches) gscan_free_matches(d_ctx, matches);
+	for (auto &w : d_queue) release(w);
+	d_queue.clear();
+	d_queued_bytes = 0;
+	return rc;
+}
+
+int FileGrep::find(const std::string &path)
+{
+	struct stat st;
+	if (stat(path.c_str(), &st) < 0) {
+		d_err = "FileGrep::find::stat: " + std::string(strerror(errno));
+		return -1;
+	}
+	int r = 0;
+	if (S_ISREG(st.st_mode)) r = find(path.c_str(), &st, FTW_F);
+	else if (S_ISDIR(st.st_mode)) std::cerr << "Clever boy! Want recursion? Add -R!\n"; // grab.cc:253-254
+	return r;
+}
+
+// nftw has no user pointer: like the reference (grab.cc:260-272) the walker reaches the object
+// through a file-scope pointer, set for the duration of find_recursive()
+static thread_local FileGrep *t_walker = nullptr;
+
+static int walk_cb(const char *path, const struct stat *st, int typeflag, struct FTW *)
+{
+	if (typeflag == FTW_F && S_ISREG(st->st_mode)) {
+		if (t_walker->find(path, st, typeflag) < 0) std::cerr << path << ": " << t_walker->why() << std::endl; // grab.cc:267-268
+	}
+	return 0;
+}
+
+int FileGrep::find_recursive(const std::string &path)
+{
+	d_recursive = true;
+	t_walker = this;
+	int r = nftw(path.c_str(), walk_cb, 1024, FTW_PHYS); // grab.cc:278
+	t_walker = nullptr;
+	if (flush() < 0) return -1;
+	return r;
+}
+
+} // namespace grab_b200

@@ -1,0 +1,64 @@
+"""Multi-GPU plumbing for the scan path: one process per GPU, files sharded by rank, no collective on
+the data path.
+
+The reference's only parallel axis is a static round-robin of files over N threads with nothing
+shared but stdout (/root/reference/src/main.cc:86-100, stride at :94); ranks take the place of
+threads.  The single exchange is at the end: an all-gather of per-rank match counts and, when the
+caller wants the records in one place (BASELINE config 5), a gather of (file_id, start, len)
+records to one rank followed by a merge by file id.  Payload is bytes to megabytes, so the backend
+only matters for latency: NCCL on GPUs, gloo in the CPU tests.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+MATCH_DTYPE = np.dtype([("start", "<u8"), ("file_id", "<u4"), ("match_len", "<u4")])
+
+
+def files_of_rank(n_files, rank, world, mode="stride"):
+    """File ids scanned by `rank`.  'stride' is the reference's rule (main.cc:94: i, i+N, i+2N, ...);
+    'block' gives contiguous, size-balanced ranges (better locality for a device-resident corpus)."""
+    if mode == "stride":
+        return np.arange(rank, n_files, world, dtype=np.int64)
+    per, extra = divmod(n_files, world)
+    lo = rank * per + min(rank, extra)
+    return np.arange(lo, lo + per + (1 if rank < extra else 0), dtype=np.int64)
+
+
+def _device(group=None):
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def gather_counts(n_local, group=None):
+    """All-gather of one int64 per rank: every rank learns every rank's match count."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return np.array([n_local], dtype=np.int64)
+    dev = _device(group)
+    mine = torch.tensor([int(n_local)], dtype=torch.int64, device=dev)
+    out = torch.zeros(dist.get_world_size(group), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return out.cpu().numpy()
+
+
+def gather_matches(local, dst=0, group=None):
+    """Gathers MATCH_DTYPE records of all ranks on `dst`, merged by (file_id, start); others get None.
+    Counts first (all-gather), then one padded all-gather of the raw record bytes."""
+    local = np.ascontiguousarray(local, dtype=MATCH_DTYPE)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return np.sort(local, order=["file_id", "start"], kind="stable")
+    counts = gather_counts(len(local), group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    cap = int(counts.max())
+    dev = _device(group)
+    buf = torch.zeros(max(cap, 1) * MATCH_DTYPE.itemsize, dtype=torch.uint8)
+    if len(local):
+        buf[: local.nbytes] = torch.from_numpy(local.view(np.uint8).reshape(-1).copy())
+    buf = buf.to(dev)
+    out = torch.zeros(world * buf.numel(), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    if rank != dst:
+        return None
+    raw = out.cpu().numpy().reshape(world, -1)
+    parts = [raw[r, : int(counts[r]) * MATCH_DTYPE.itemsize].view(MATCH_DTYPE) for r in range(world)]
+    allm = np.concatenate(parts) if parts else np.zeros(0, dtype=MATCH_DTYPE)
+    return np.sort(allm, order=["file_id", "start"], kind="stable")
