@@ -9,8 +9,6 @@ namespace gscan {
 // parameter of the kernel, chosen per engine (memory-bound filters want big slices and a deep
 // ring, instruction-bound ones want as many warps as fit).
 constexpr int kTileBytes = 65536;
-constexpr int kPreMax = 256;              // most bytes kept in front of a slice (filter anchor look-behind)
-constexpr int kPostMax = 1056;            // most bytes kept behind a slice (verification look-ahead)
 constexpr int kSmemBudget = 227 * 1024;
 
 template <int W, int R, int S>
@@ -23,8 +21,6 @@ struct Geom {
 };
 typedef Geom<16, 3, 4096> GeomStream;  // memory-bound: single-test literal filter
 typedef Geom<24, 4, 2048> GeomBalanced;
-typedef Geom<32, 3, 2048> GeomDense;   // instruction-bound: many filter tests / class runs
-typedef Geom<8, 3, 4096> GeomLong;     // patterns whose halo (up to 256 + 1056 bytes per slice) leaves room for few slots
 
 struct ScanGeom { int warps, ring, slice; }; // host-side mirror of the chosen Geom
 
@@ -50,6 +46,8 @@ struct Cand { uint32_t pos, len; };
 struct OutRec { uint32_t unit, pos, len, pad; };
 
 struct FixedParams {
+	uint32_t one;         // == 1, opaque to the compiler: x * one + c issues as IMAD (FMA pipe) instead of IADD (ALU pipe)
+	uint32_t exact;       // every filter mask is 0xff
 	uint32_t ntests;
 	uint32_t m0[8], v0[8], m1[8], v1[8]; // byte replicated x4
 	uint32_t anchor;      // pattern byte the filter stream is anchored on
@@ -60,9 +58,13 @@ struct FixedParams {
 	const uint32_t *seq_off;  // [nseq] index into seq_pos
 	const uint32_t *seq_pos;  // per position: mask | val << 8 | cls << 16 (cls 0xffff: none)
 	const uint32_t *cls_bm;   // [ncls][8] bitmaps for positions that are not a masked equality
+	// stage 2 (flagged rows only): triples with a third pattern byte at anchor + d2
+	uint32_t n2, d2;
+	uint32_t t2_m0[16], t2_v0[16], t2_m1[16], t2_v1[16], t2_m2[16], t2_v2[16];
 };
 
 struct RunParams {
+	uint32_t one;         // == 1, opaque (see FixedParams)
 	uint32_t nlo, nhi;
 	uint32_t add_ge_lo[8], add_gt_lo[8]; // (0x80-lo)*0x01010101, (0x7f-hi)*0x01010101 for ranges in 0x00-0x7f
 	uint32_t add_ge_hi[2], add_gt_hi[2]; // same for ranges in 0x80-0xff (after clearing bit 7)
@@ -73,8 +75,6 @@ struct RunParams {
 struct ScanArgs {
 	const TileDesc *tiles;
 	uint32_t n_tiles;
-	uint32_t pre;   // bytes to load in front of a tile that is not the first of its unit (multiple of 16)
-	uint32_t post;  // bytes to load behind a tile (multiple of 16)
 	Cand *cand;
 	uint32_t cand_cap;
 	unsigned long long *cursor; // [0]: candidates reserved so far

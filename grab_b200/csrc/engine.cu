@@ -32,7 +32,6 @@ struct gscan_pattern {
 	std::vector<uint32_t> seq_off, seq_pos, cls_bm;
 	FixedParams fixed; // device pointers filled per context
 	RunParams run;
-	uint32_t pre = 16, post = 32;
 };
 
 template <class T>
@@ -147,7 +146,18 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 	memset(&p->run, 0, sizeof(p->run));
 	if (pr.kind == ENGINE_FIXED) {
 		FixedParams &F = p->fixed;
+		F.one = 1;
 		F.ntests = (uint32_t)pr.tests.size();
+		F.exact = 1;
+		for (auto &t : pr.tests) if (t.m0 != 0xff || (pr.delta && t.m1 != 0xff)) F.exact = 0;
+		if (!pr.delta) F.exact = 0; // single-byte filter: the second term must vanish through its zero mask
+		F.n2 = (uint32_t)pr.triples.size();
+		F.d2 = (uint32_t)pr.delta2;
+		for (size_t k = 0; k < pr.triples.size(); k++) {
+			F.t2_m0[k] = rep4(pr.triples[k].m0); F.t2_v0[k] = rep4(pr.triples[k].v0);
+			F.t2_m1[k] = rep4(pr.triples[k].m1); F.t2_v1[k] = rep4(pr.triples[k].v1);
+			F.t2_m2[k] = rep4(pr.triples[k].m2); F.t2_v2[k] = rep4(pr.triples[k].v2);
+		}
 		for (int k = 0; k < 8; k++) { // unused slots: a test no byte can pass
 			F.m0[k] = 0; F.v0[k] = 0xffffffffu; F.m1[k] = 0; F.v1[k] = 0;
 		}
@@ -178,10 +188,9 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 			}
 		}
 		for (auto &c : classes) for (int i = 0; i < 8; i++) p->cls_bm.push_back(c.w[i]);
-		p->pre = std::max(16u, round16((uint32_t)pr.anchor));
-		p->post = round16((uint32_t)std::max(pr.maxlen - pr.anchor, 4) + 16u);
 	} else if (pr.kind == ENGINE_RUN) {
 		RunParams &R = p->run;
+		R.one = 1;
 		R.nlo = (uint32_t)pr.ranges_low.size();
 		R.nhi = (uint32_t)pr.ranges_high.size();
 		for (size_t i = 0; i < pr.ranges_low.size(); i++) {
@@ -194,13 +203,6 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 		}
 		R.run_min = (uint32_t)pr.run_min;
 		for (int i = 0; i < 8; i++) R.bitmap[i] = pr.run_class.w[i];
-		p->pre = 16;
-		p->post = round16((uint32_t)pr.run_min + 32u);
-	}
-	if (p->pre > (uint32_t)kPreMax || p->post > (uint32_t)kPostMax || scan_smem_bytes(ScanGeom{8, 3, 4096}, p->pre, p->post) > (size_t)kSmemBudget) {
-		g_last_error = "gscan_compile: pattern too long for the shared-memory halo";
-		delete p;
-		return -1;
 	}
 	*out = p;
 	return 0;
@@ -471,7 +473,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	}
 	if (ensure_pattern(ctx, pat) < 0) return -1;
 
-	const ScanGeom geom = scan_geom((int)pat->prog.kind, pat->prog.kind == ENGINE_FIXED ? (uint32_t)pat->prog.tests.size() : 99u, pat->pre, pat->post);
+	const ScanGeom geom = scan_geom((int)pat->prog.kind, pat->prog.kind == ENGINE_FIXED ? (uint32_t)pat->prog.tests.size() : 99u);
 	const uint32_t spt = (uint32_t)(kTileBytes / geom.slice);
 	const uint32_t n_segs = b->n_tiles * spt;
 	const int grid = (int)std::min<uint32_t>((uint32_t)ctx->num_sms, b->n_tiles);
@@ -487,8 +489,6 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	ScanArgs A;
 	A.tiles = b->d_tiles;
 	A.n_tiles = b->n_tiles;
-	A.pre = pat->pre;
-	A.post = pat->post;
 	A.cursor = ctx->cursor.p;
 	A.segs = ctx->segs.p;
 	A.scratch = ctx->scratch.p;

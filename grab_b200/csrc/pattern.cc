@@ -732,6 +732,26 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 	out.delta = best_d;
 	out.tests = best_tests;
 
+	// ---- stage 2: a third byte (anchor + d2, d2 in 0..3 other than 0 and delta) narrows flagged rows ----
+	{
+		double best_p = 1e300;
+		for (int d2 = 1; d2 <= 3; d2++) {
+			if (d2 == out.delta || out.anchor + d2 >= (int)mn) continue;
+			std::vector<Program::Triple> tr;
+			double p = 0;
+			for (auto &s : out.seqs) {
+				MaskedEq e0 = masked_superset(s[out.anchor]);
+				MaskedEq e1 = out.delta ? masked_superset(s[out.anchor + out.delta]) : MaskedEq{0, 0, false, 256};
+				MaskedEq e2 = masked_superset(s[out.anchor + d2]);
+				Program::Triple t{e0.mask, e0.val, e1.mask, e1.val, e2.mask, e2.val};
+				bool dup = false;
+				for (auto &x : tr) dup = dup || !memcmp(&x, &t, sizeof(t));
+				if (!dup) { tr.push_back(t); p += test_prior(e0) * (out.delta ? test_prior(e1) : 1.0) * test_prior(e2); }
+			}
+			if (tr.size() <= 16 && p < best_p) { best_p = p; out.triples = tr; out.delta2 = d2; }
+		}
+	}
+
 	// ---- can two matches overlap?  If not, the greedy resolve keeps every candidate ----
 	bool disjoint = true;
 	for (auto &a : out.seqs) {

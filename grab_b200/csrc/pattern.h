@@ -68,6 +68,9 @@ struct Program {
 	std::vector<Sequence> seqs;       // in PCRE preference order
 	std::vector<FilterTest> tests;    // deduplicated
 	int anchor = 0, delta = 0;        // filter bytes are pattern[anchor], pattern[anchor+delta]
+	struct Triple { uint8_t m0, v0, m1, v1, m2, v2; };
+	std::vector<Triple> triples;      // stage-2 refinement with a third byte at anchor+delta2 (empty: none)
+	int delta2 = 0;
 	bool disjoint = false;            // no two matches can ever overlap => resolve is a pure copy
 
 	// RUN

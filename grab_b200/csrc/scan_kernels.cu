@@ -8,15 +8,15 @@
 //   signalled through the slot's mbarrier (complete_tx::bytes); the warp waits on the barrier, reads
 //   the slice with conflict-free 16-byte LDS (lane l <- bytes [16l,16l+16) of a 512-byte row), runs
 //   the SWAR filter (4 bytes per 32-bit op) over the whole slice and, on the rare flagged lane,
-//   verifies from shared memory, then re-arms the slot for the slice kRing steps ahead.  Matches
-//   cross lane / row / slice / tile borders through the halo loaded in front of and behind a slice.
+//   verifies, then re-arms the slot for the slice kRing steps ahead.  Matches cross lane / row borders
+//   inside the slot; across slice / tile borders the few neighbouring bytes come from global memory.
 // Output order: each warp appends its candidates in position order to a private scratch list and,
 // at the end of its slice, reserves a contiguous range of the global candidate buffer with one
 // atomicAdd and records (base, n) in the segment table.  Segment ids are position ordered, so the
 // resolve pass needs no sort.
 //
-// HBM traffic: every byte once (the halos of neighbouring slices are fetched within microseconds of
-// each other and hit L2), 8 bytes of segment table written per slice, candidates only where they exist.
+// HBM traffic: every byte once, in 512-byte-aligned bulk copies; 8 bytes of segment table written per
+// slice; candidates only where they exist.
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdlib>
@@ -70,23 +70,29 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
 }
 
 // ------------------------------------------------------------------------------------------
-// shared-memory layout: every warp owns kRing slots of (pre + kSliceBytes + post) bytes, one
-// mbarrier and one 32-byte slice descriptor per slot.  Nothing is shared between warps.
+// shared-memory layout: every warp owns kRing slots of 16 + kSlice + 16 bytes, one mbarrier and one slice
+// descriptor per slot.  The slice itself arrives as ONE bulk copy that is 512-byte aligned on both sides;
+// the 16 bytes after it (shifted filter stream, run look-ahead) and, for the RUN engine, the 16 bytes
+// before it (is the previous byte in the class?) arrive as separate 16-byte bulk copies on the same
+// mbarrier.  Whatever else a verification touches is read from global memory (L2).  Nothing is shared
+// between warps.
+constexpr uint32_t kHalo = 16;
 // ------------------------------------------------------------------------------------------
 struct __align__(16) SlotCtl {
 	uint64_t full;
+	uint64_t src; // global address of tile byte 0
 	uint32_t off, ulen, tile_len, begin, niter, pad;
 };
 
-size_t scan_smem_bytes(const ScanGeom &g, uint32_t pre, uint32_t post)
+size_t scan_smem_bytes(const ScanGeom &g)
 {
-	const size_t slot = (size_t)pre + g.slice + post;
-	return (size_t)g.warps * g.ring * (slot + sizeof(SlotCtl));
+	return (size_t)g.warps * g.ring * ((size_t)g.slice + 2 * kHalo + sizeof(SlotCtl)) + 64;
 }
 
 // what a warp knows about the slice it is scanning
 struct Slice {
-	const uint8_t *tile; // shared-memory address of the tile's byte 0
+	const uint8_t *tile;  // shared-memory address of the tile's byte 0 (only the slice itself is resident)
+	const uint8_t *gtile; // global address of the tile's byte 0 (neighbouring bytes, verification)
 	uint32_t off;        // offset of the tile in its unit
 	uint32_t ulen;       // unit length
 	uint32_t tile_len;
@@ -143,14 +149,16 @@ struct Emitter {
 // ------------------------------------------------------------------------------------------
 // FIXED engine: alternation of fixed-length byte-class sequences
 // ------------------------------------------------------------------------------------------
-template <int D, int K>
+template <int D, int K, bool EX>
 struct FixedEngine {
 	typedef FixedParams Params;
+	static constexpr bool kLookBehind = false, kLookAhead = D != 0;
 
 	// first sequence (in preference order) matching with its anchor byte at tile position p; 0: none
+	// reads the unit's bytes from global memory (tile = global address of tile byte 0)
 	static __device__ uint32_t verify(const FixedParams &P, const uint8_t *tile, uint32_t off, uint32_t ulen, int p)
 	{
-		const int q = p - (int)P.anchor;              // match start in tile coordinates (may be < 0: pre-halo)
+		const int q = p - (int)P.anchor;              // match start in tile coordinates (may be < 0: previous tile)
 		const long long qu = (long long)off + q;      // ... in unit coordinates
 		if (qu < 0) return 0;
 		for (uint32_t s = 0; s < P.nseq; s++) {
@@ -172,29 +180,55 @@ struct FixedEngine {
 		return 0;
 	}
 
-	// SWAR filter over the lane's 16 bytes (+ D bytes of the next chunk); bit 7 of a byte set => candidate
-	static __device__ __forceinline__ uint32_t filter(const FixedParams &P, const uint32_t (&w)[5], uint32_t (&f)[4])
+	// Stage-1 SWAR filter of one word pair: bit 7 of a byte of the result set (superset) where some test
+	// passes at that byte.  EX: every mask is 0xff, two LOP3 per test instead of three.  The decrement of
+	// the zero-byte trick is written t * one + 0xfefefeff (one == 1, opaque to the compiler) so that it
+	// issues as IMAD on the FMA pipe instead of crowding the ALU pipe the LOP3/SHF already fill.
+	static __device__ __forceinline__ uint32_t word_flags(const FixedParams &P, uint32_t w, uint32_t s)
+	{
+		uint32_t f = 0;
+#pragma unroll
+		for (int k = 0; k < K; k++) {
+			const uint32_t t = EX ? ((w ^ P.v0[k]) | (s ^ P.v1[k])) : (((w & P.m0[k]) ^ P.v0[k]) | ((s & P.m1[k]) ^ P.v1[k]));
+			f |= (t * P.one + 0xfefefeffu) & ~t;
+		}
+		return f;
+	}
+
+	static __device__ __forceinline__ uint32_t row_any(const FixedParams &P, const uint32_t (&w)[5])
 	{
 		uint32_t acc = 0;
 #pragma unroll
-		for (int j = 0; j < 4; j++) {
-			const uint32_t s = D ? __funnelshift_r(w[j], w[j + 1], 8 * D) : w[j];
-			uint32_t t = 0;
-#pragma unroll
-			for (int k = 0; k < K; k++) t |= pair_test(w[j], s, P.m0[k], P.v0[k], P.m1[k], P.v1[k]);
-			f[j] = t;
-			acc |= t;
-		}
-		return acc & kHigh;
+		for (int j = 0; j < 4; j++) acc |= word_flags(P, w[j], D ? __funnelshift_r(w[j], w[j + 1], 8 * D) : w[j]);
+		return acc;
 	}
 
-	// rare path for one 512-byte row: exact verification of every flagged byte, ordered emission
+	// Rare path for one flagged 512-byte row (warp-converged).  Stage 2 first narrows the flags with a
+	// third pattern byte (SWAR again, a handful of ops), only then are the survivors verified byte by
+	// byte (global memory / L2), in preference order, and appended in position order.
 	static __device__ __noinline__ uint32_t slow_row(const FixedParams &P, const uint8_t *tile, uint32_t off, uint32_t ulen,
 	                                                 uint32_t tile_len, Cand *dst, uint32_t lane, uint32_t c0,
-	                                                 uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3)
+	                                                 uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4)
 	{
+		const uint32_t w[5] = {w0, w1, w2, w3, w4};
+		uint32_t f[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const uint32_t s1 = D ? __funnelshift_r(w[j], w[j + 1], 8 * D) : w[j];
+			if (P.n2) {
+				const uint32_t s2 = __funnelshift_r(w[j], w[j + 1], 8 * P.d2);
+				uint32_t g = 0;
+				for (uint32_t k = 0; k < P.n2; k++) {
+					const uint32_t t = ((w[j] & P.t2_m0[k]) ^ P.t2_v0[k]) | ((s1 & P.t2_m1[k]) ^ P.t2_v1[k]) | ((s2 & P.t2_m2[k]) ^ P.t2_v2[k]);
+					g |= (t - kOnes) & ~t;
+				}
+				f[j] = g & kHigh;
+			} else {
+				f[j] = word_flags(P, w[j], s1) & kHigh;
+			}
+		}
+		if (!__any_sync(0xffffffffu, (f[0] | f[1] | f[2] | f[3]) != 0)) return 0;
 		uint32_t mm = 0;
-		const uint32_t f[4] = {f0 & kHigh, f1 & kHigh, f2 & kHigh, f3 & kHigh};
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
 			uint32_t t = f[j];
@@ -211,6 +245,8 @@ struct FixedEngine {
 		}, lane);
 	}
 
+	// lane's 16 bytes + the 4 bytes after them (next lane's / next row's first word; after the last chunk of the
+	// slice: the 16-byte look-ahead copy that sits right behind the slice in the slot)
 	static __device__ __forceinline__ void load_row(const Slice &S, uint32_t c0, uint32_t (&w)[5])
 	{
 		const uint4 a = *reinterpret_cast<const uint4 *>(S.tile + c0);
@@ -222,31 +258,35 @@ struct FixedEngine {
 	static __device__ __forceinline__ void run(const FixedParams &P, const Slice &S, Emitter &E, uint32_t lane)
 	{
 		constexpr int kRows = G::kSlice / 512;
+		if (S.niter == 0) return;
 		const uint32_t base = S.begin + lane * 16;
 		if (S.niter == (uint32_t)kRows) {
-			// whole slice at once: all loads first, one vote for the slice
-			uint32_t w[kRows][5], f[kRows][4];
+			// full slice: groups of 4 rows -- all 8 loads of a group first, one vote per group
+			constexpr int kGroup = 4;
 #pragma unroll
-			for (int r = 0; r < kRows; r++) load_row(S, base + r * 512, w[r]);
-			uint32_t acc = 0;
+			for (int g0 = 0; g0 < kRows; g0 += kGroup) {
+				uint32_t w[kGroup][5];
 #pragma unroll
-			for (int r = 0; r < kRows; r++) acc |= filter(P, w[r], f[r]);
-			if (__any_sync(0xffffffffu, acc != 0)) {
+				for (int r = 0; r < kGroup; r++) load_row(S, base + (g0 + r) * 512, w[r]);
+				uint32_t acc = 0, ra[kGroup];
 #pragma unroll
-				for (int r = 0; r < kRows; r++) {
-					const uint32_t a = (f[r][0] | f[r][1] | f[r][2] | f[r][3]) & kHigh;
-					if (__any_sync(0xffffffffu, a != 0))
-						E.n += slow_row(P, S.tile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, base + r * 512, f[r][0], f[r][1], f[r][2], f[r][3]);
+				for (int r = 0; r < kGroup; r++) { ra[r] = row_any(P, w[r]); acc |= ra[r]; }
+				if (__any_sync(0xffffffffu, (acc & kHigh) != 0)) {
+#pragma unroll
+					for (int r = 0; r < kGroup; r++) {
+						if (__any_sync(0xffffffffu, (ra[r] & kHigh) != 0))
+							E.n += slow_row(P, S.gtile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, base + (g0 + r) * 512,
+							                w[r][0], w[r][1], w[r][2], w[r][3], w[r][4]);
+					}
 				}
 			}
 			return;
 		}
 		for (uint32_t it = 0; it < S.niter; it++) {
-			uint32_t w[5], f[4];
+			uint32_t w[5];
 			load_row(S, base + it * 512, w);
-			const uint32_t acc = filter(P, w, f);
-			if (__any_sync(0xffffffffu, acc != 0))
-				E.n += slow_row(P, S.tile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, base + it * 512, f[0], f[1], f[2], f[3]);
+			if (__any_sync(0xffffffffu, (row_any(P, w) & kHigh) != 0))
+				E.n += slow_row(P, S.gtile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, base + it * 512, w[0], w[1], w[2], w[3], w[4]);
 		}
 	}
 };
@@ -257,15 +297,22 @@ struct FixedEngine {
 template <int NLO, int NHI>
 struct RunEngine {
 	typedef RunParams Params;
+	static constexpr bool kLookBehind = true, kLookAhead = true;
 
 	static __device__ __forceinline__ uint32_t class_flags(const RunParams &P, uint32_t x)
 	{
 		const uint32_t x7 = x & kLow7;
 		uint32_t lo = 0, hi = 0;
 #pragma unroll
-		for (int r = 0; r < NLO; r++) lo |= range7(x7, P.add_ge_lo[r], P.add_gt_lo[r]);
+		for (int r = 0; r < NLO; r++) {
+			// adds as IMAD (x7 * one + c, one == 1 opaque): FMA pipe, the ALU pipe is the bottleneck; keep the
+			// first add on the ALU pipe for balance
+			const uint32_t ge = r == 0 ? x7 + P.add_ge_lo[r] : x7 * P.one + P.add_ge_lo[r];
+			const uint32_t gt = x7 * P.one + P.add_gt_lo[r];
+			lo |= ge & ~gt;
+		}
 #pragma unroll
-		for (int r = 0; r < NHI; r++) hi |= range7(x7, P.add_ge_hi[r], P.add_gt_hi[r]);
+		for (int r = 0; r < NHI; r++) hi |= (x7 * P.one + P.add_ge_hi[r]) & ~(x7 * P.one + P.add_gt_hi[r]);
 		if (NHI) return ((lo & ~x) | (hi & x)) & kHigh;
 		return lo & ~x & kHigh;
 	}
@@ -283,7 +330,7 @@ struct RunEngine {
 		r = __funnelshift_l(pack_top_nibble(class_flags(P, a.x)), r, 4);
 		const long long rem = (long long)S.ulen - (long long)S.off - (long long)c;
 		const uint32_t valid = rem >= 16 ? 0xffffu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u));
-		return r & valid;
+		return r & valid; // the tail of the last 16-byte granule of a unit is whatever follows it in memory
 	}
 
 	template <class G>
@@ -293,7 +340,7 @@ struct RunEngine {
 		const uint32_t nf = P.run_min < 17u ? P.run_min : 17u;
 		// is the byte just before the slice in the class?  (the unit's first byte has no predecessor)
 		uint32_t prevbit = 0;
-		if (S.off + S.begin > 0) prevbit = in_class(P, S.tile[(int)S.begin - 1]);
+		if (S.off + S.begin > 0) prevbit = in_class(P, S.tile[(int)S.begin - 1]); // 16-byte look-behind copy
 		uint32_t cm_next = mask16(P, S, S.begin + lane * 16);
 		for (uint32_t it = 0; it < S.niter; it++) {
 			const uint32_t c0 = S.begin + it * 512 + lane * 16;
@@ -301,14 +348,14 @@ struct RunEngine {
 			if (it + 1 < S.niter) {
 				cm_next = mask16(P, S, c0 + 512);
 			} else {
-				// the 16 bytes after this slice (next warp's slice, next tile via the post-halo, or past
-				// the unit end): lanes 0..3 each classify one word, lane 0 assembles the mask
+				// the 16 bytes after this slice (another warp's slice, or past the unit end): lanes 0..3 each
+				// classify one word of the look-ahead copy, lane 0 assembles the mask
 				const uint32_t cb = S.begin + S.niter * 512 + (lane & 3) * 4;
-				const uint32_t x = *reinterpret_cast<const uint32_t *>(S.tile + cb);
+				const long long rem = (long long)S.ulen - (long long)S.off - (long long)(S.begin + S.niter * 512);
+				const uint32_t x = *reinterpret_cast<const uint32_t *>(S.tile + cb); // 16-byte look-ahead copy (masked by `valid`)
 				uint32_t nib = (pack_top_nibble(class_flags(P, x)) >> 28) << ((lane & 3) * 4);
 				nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
 				nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
-				const long long rem = (long long)S.ulen - (long long)S.off - (long long)(S.begin + S.niter * 512);
 				const uint32_t valid = rem >= 16 ? 0xffffu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u));
 				cm_next = nib & valid;
 			}
@@ -330,7 +377,7 @@ struct RunEngine {
 						t &= t - 1;
 						const uint32_t p = c0 + b;
 						bool ok = (unsigned long long)S.off + p + P.run_min <= S.ulen;
-						for (uint32_t i = 17; ok && i < P.run_min; i++) ok = in_class(P, S.tile[p + i]);
+						for (uint32_t i = 17; ok && i < P.run_min; i++) ok = in_class(P, S.gtile[p + i]);
 						if (ok) keep |= 1u << b;
 					}
 					cand = keep;
@@ -366,7 +413,7 @@ scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename
 {
 	extern __shared__ __align__(128) uint8_t smem[];
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t slot_bytes = A.pre + G::kSlice + A.post;
+	constexpr uint32_t slot_bytes = G::kSlice + 2 * kHalo;
 	uint8_t *my = smem + (size_t)warp * G::kRing * slot_bytes;
 	SlotCtl *ctl = reinterpret_cast<SlotCtl *>(smem + (size_t)G::kWarps * G::kRing * slot_bytes) + warp * G::kRing;
 
@@ -385,16 +432,17 @@ scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename
 		uint32_t begin, niter;
 		slice_geometry<G>(d, s % G::kSlicesPerTile, begin, niter);
 		SlotCtl *c = &ctl[slot];
-		c->off = d.off; c->ulen = d.ulen; c->tile_len = d.len; c->begin = begin; c->niter = niter;
+		c->src = d.src; c->off = d.off; c->ulen = d.ulen; c->tile_len = d.len; c->begin = begin; c->niter = niter;
 		if (niter == 0) { mbar_arrive(&c->full); return; }
-		const uint32_t pre = (d.off + begin) ? A.pre : 0u;
-		uint32_t body = (d.ulen - d.off - begin + 15u) & ~15u; // rest of the unit from the slice start, padded to 16
-		const uint32_t want = niter * 512u + A.post;
-		if (body > want) body = want;
-		const uint32_t bytes = pre + body;
-		uint8_t *dst = my + (size_t)slot * slot_bytes + A.pre - pre;
-		mbar_arrive_expect_tx(&c->full, bytes);
-		tma_load_1d(dst, reinterpret_cast<const void *>(d.src + begin - pre), bytes, &c->full);
+		const uint32_t rest = (d.ulen - d.off - begin + 15u) & ~15u; // rest of the unit from the slice start, padded to 16
+		const uint32_t bytes = rest > niter * 512u ? niter * 512u : rest;
+		const bool behind = Eng::kLookBehind && (d.off + begin) != 0;
+		const bool ahead = Eng::kLookAhead && rest >= niter * 512u + kHalo;
+		uint8_t *dst = my + (size_t)slot * slot_bytes + kHalo;
+		mbar_arrive_expect_tx(&c->full, bytes + (behind ? kHalo : 0u) + (ahead ? kHalo : 0u));
+		tma_load_1d(dst, reinterpret_cast<const void *>(d.src + begin), bytes, &c->full);
+		if (behind) tma_load_1d(dst - kHalo, reinterpret_cast<const void *>(d.src + begin - kHalo), kHalo, &c->full);
+		if (ahead) tma_load_1d(dst + niter * 512u, reinterpret_cast<const void *>(d.src + begin + niter * 512u), kHalo, &c->full);
 	};
 
 	if (lane == 0) {
@@ -422,7 +470,8 @@ scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename
 		S.tile_len = ctl[slot].tile_len;
 		S.begin = ctl[slot].begin;
 		S.niter = ctl[slot].niter;
-		S.tile = my + (size_t)slot * slot_bytes + A.pre - S.begin; // address of tile byte 0 (only the slice window is loaded)
+		S.tile = my + (size_t)slot * slot_bytes + kHalo - S.begin; // address of tile byte 0 (only the slice window is resident)
+		S.gtile = reinterpret_cast<const uint8_t *>(ctl[slot].src);
 		Eng::template run<G>(P, S, E, lane);
 		E.flush(A, s, lane);
 		__syncwarp(); // every lane is done reading the slot before it is overwritten
@@ -438,64 +487,49 @@ template <class Eng, class G>
 static cudaError_t launch_g(const ScanArgs &A, const typename Eng::Params &P, int grid, cudaStream_t st)
 {
 	const ScanGeom g{G::kWarps, G::kRing, G::kSlice};
-	const size_t smem = scan_smem_bytes(g, A.pre, A.post);
+	const size_t smem = scan_smem_bytes(g);
 	cudaError_t e = cudaFuncSetAttribute(scan_kernel<Eng, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	scan_kernel<Eng, G><<<grid, G::kThreads, smem, st>>>(A, P);
 	return cudaGetLastError();
 }
 
-template <class Eng>
-static cudaError_t launch(const ScanArgs &A, const typename Eng::Params &P, const ScanGeom &g, int grid, cudaStream_t st)
+// Instantiated geometries: the streaming one for single-test filters, the balanced one for everything else.
+template <class Eng, bool STREAM>
+static cudaError_t launch(const ScanArgs &A, const typename Eng::Params &P, const ScanGeom &, int grid, cudaStream_t st)
 {
-	if (g.warps == GeomStream::kWarps) return launch_g<Eng, GeomStream>(A, P, grid, st);
-	if (g.warps == GeomBalanced::kWarps) return launch_g<Eng, GeomBalanced>(A, P, grid, st);
-	if (g.warps == GeomDense::kWarps) return launch_g<Eng, GeomDense>(A, P, grid, st);
-	return launch_g<Eng, GeomLong>(A, P, grid, st);
+	if constexpr (STREAM) return launch_g<Eng, GeomStream>(A, P, grid, st);
+	else return launch_g<Eng, GeomBalanced>(A, P, grid, st);
 }
 
-static ScanGeom geom_by_index(int i)
+// which geometry an engine runs with
+ScanGeom scan_geom(int engine, uint32_t n_tests_or_ranges)
 {
-	switch (i) {
-	case 0: return ScanGeom{GeomStream::kWarps, GeomStream::kRing, GeomStream::kSlice};
-	case 1: return ScanGeom{GeomBalanced::kWarps, GeomBalanced::kRing, GeomBalanced::kSlice};
-	case 2: return ScanGeom{GeomDense::kWarps, GeomDense::kRing, GeomDense::kSlice};
-	default: return ScanGeom{GeomLong::kWarps, GeomLong::kRing, GeomLong::kSlice};
-	}
+	if (engine == 1 /*FIXED*/ && n_tests_or_ranges <= 1) return ScanGeom{GeomStream::kWarps, GeomStream::kRing, GeomStream::kSlice};
+	return ScanGeom{GeomBalanced::kWarps, GeomBalanced::kRing, GeomBalanced::kSlice};
 }
 
-// which geometry an engine runs with; GSCAN_GEOM=0..3 overrides (tuning)
-ScanGeom scan_geom(int engine, uint32_t n_tests_or_ranges, uint32_t pre, uint32_t post)
-{
-	int idx = (engine == 1 /*FIXED*/ && n_tests_or_ranges <= 1) ? 0 : 1;
-	if (const char *e = getenv("GSCAN_GEOM")) idx = atoi(e);
-	if (idx < 0 || idx > 3) idx = 3;
-	if (scan_smem_bytes(geom_by_index(idx), pre, post) <= (size_t)kSmemBudget) return geom_by_index(idx);
-	for (int t = 0; t < 3; t++) // long patterns need big halos: first geometry whose ring still fits
-		if (scan_smem_bytes(geom_by_index(t), pre, post) <= (size_t)kSmemBudget) return geom_by_index(t);
-	return geom_by_index(3);
-}
-
-template <int D>
-static cudaError_t launch_fixed_d(const ScanArgs &A, const FixedParams &P, const ScanGeom &g, int grid, cudaStream_t st)
+template <int D, bool EX>
+static cudaError_t launch_fixed_de(const ScanArgs &A, const FixedParams &P, const ScanGeom &g, int grid, cudaStream_t st)
 {
 	switch (P.ntests) {
-	case 1: return launch<FixedEngine<D, 1>>(A, P, g, grid, st);
-	case 2: return launch<FixedEngine<D, 2>>(A, P, g, grid, st);
-	case 3: return launch<FixedEngine<D, 3>>(A, P, g, grid, st);
-	case 4: return launch<FixedEngine<D, 4>>(A, P, g, grid, st);
-	case 5: case 6: return launch<FixedEngine<D, 6>>(A, P, g, grid, st);
-	default: return launch<FixedEngine<D, 8>>(A, P, g, grid, st);
+	case 1: return launch<FixedEngine<D, 1, EX>, true>(A, P, g, grid, st);
+	case 2: return launch<FixedEngine<D, 2, EX>, false>(A, P, g, grid, st);
+	case 3: return launch<FixedEngine<D, 3, EX>, false>(A, P, g, grid, st);
+	case 4: return launch<FixedEngine<D, 4, EX>, false>(A, P, g, grid, st);
+	case 5: case 6: return launch<FixedEngine<D, 6, EX>, false>(A, P, g, grid, st);
+	default: return launch<FixedEngine<D, 8, EX>, false>(A, P, g, grid, st);
 	}
 }
 
 cudaError_t launch_scan_fixed(const ScanArgs &A, const FixedParams &P, int delta, const ScanGeom &g, int grid, cudaStream_t st)
 {
+	const bool ex = P.exact != 0;
 	switch (delta) {
-	case 0: return launch_fixed_d<0>(A, P, g, grid, st);
-	case 1: return launch_fixed_d<1>(A, P, g, grid, st);
-	case 2: return launch_fixed_d<2>(A, P, g, grid, st);
-	default: return launch_fixed_d<3>(A, P, g, grid, st);
+	case 0: return ex ? launch_fixed_de<0, true>(A, P, g, grid, st) : launch_fixed_de<0, false>(A, P, g, grid, st);
+	case 1: return ex ? launch_fixed_de<1, true>(A, P, g, grid, st) : launch_fixed_de<1, false>(A, P, g, grid, st);
+	case 2: return ex ? launch_fixed_de<2, true>(A, P, g, grid, st) : launch_fixed_de<2, false>(A, P, g, grid, st);
+	default: return ex ? launch_fixed_de<3, true>(A, P, g, grid, st) : launch_fixed_de<3, false>(A, P, g, grid, st);
 	}
 }
 
@@ -503,12 +537,12 @@ template <int NHI>
 static cudaError_t launch_run_h(const ScanArgs &A, const RunParams &P, const ScanGeom &g, int grid, cudaStream_t st)
 {
 	switch (P.nlo) {
-	case 0: case 1: return launch<RunEngine<1, NHI>>(A, P, g, grid, st);
-	case 2: return launch<RunEngine<2, NHI>>(A, P, g, grid, st);
-	case 3: return launch<RunEngine<3, NHI>>(A, P, g, grid, st);
-	case 4: return launch<RunEngine<4, NHI>>(A, P, g, grid, st);
-	case 5: case 6: return launch<RunEngine<6, NHI>>(A, P, g, grid, st);
-	default: return launch<RunEngine<8, NHI>>(A, P, g, grid, st);
+	case 0: case 1: return launch<RunEngine<1, NHI>, false>(A, P, g, grid, st);
+	case 2: return launch<RunEngine<2, NHI>, false>(A, P, g, grid, st);
+	case 3: return launch<RunEngine<3, NHI>, false>(A, P, g, grid, st);
+	case 4: return launch<RunEngine<4, NHI>, false>(A, P, g, grid, st);
+	case 5: case 6: return launch<RunEngine<6, NHI>, false>(A, P, g, grid, st);
+	default: return launch<RunEngine<8, NHI>, false>(A, P, g, grid, st);
 	}
 }
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Geometry sweep helper (tuning only): times the scan kernel for GSCAN_GEOM=0..3 on the same
-device-resident corpus.  Usage: python tools/sweep.py [corpus_gib] [geoms]"""
+"""Kernel timing helper (tuning only): scan-kernel GB/s for a handful of patterns on a device-resident
+synthetic corpus.  Usage: python tools/sweep.py [corpus_gib]"""
 import json
 import os
 import subprocess
@@ -22,7 +22,7 @@ d = ctx.device_alloc(n << 20)
 ctx.synth_corpus(d, 2, 0, n, 1 << 20, needle=b"foobardoesexist", needle_every=64)
 batch = ctx.batch_create(G.Context.device_units(d, n, 1 << 20))
 out = {}
-for name, pat, lit in (("literal", "foobardoesexist", True), ("alt4", "foo|bar|baz|quux", False), ("run16", "[A-Za-z0-9_]{16,}", False), ("lit2", "qz", False), ("icase", "(?i)linus", False)):
+for name, pat, lit in (("literal", "foobardoesexist", True), ("alt4", "foo|bar|baz|quux", False), ("run16", "[A-Za-z0-9_]{16,}", False), ("lit2", "qz", False), ("icase", "(?i)linus", False), ("lits8", "alpha|bravo|charlie|delta|echo|foxtrot|golf|hotel", False), ("digits", r"\\d{3}-\\d{4}", False), ("run4", "[0-9]{4,}", False)):
     p = G.Pattern(pat, literal=lit)
     ms = []
     for i in range(6):
@@ -39,16 +39,15 @@ print(json.dumps(out))
 
 def main():
     gib = sys.argv[1] if len(sys.argv) > 1 else "16"
-    geoms = sys.argv[2].split(",") if len(sys.argv) > 2 else ["0", "1", "2", "3"]
-    for g in geoms:
-        env = dict(os.environ, GSCAN_GEOM=g)
-        p = subprocess.run([sys.executable, "-c", CHILD, gib], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
-        if p.returncode != 0:
-            print("geom", g, "FAILED", p.stderr.decode()[-300:])
-            continue
-        o = json.loads(p.stdout.decode().strip().splitlines()[-1])
-        print("geom %s probe %6.0f | " % (g, o["read_probe_gbs"]) + " | ".join(
-            "%s %6.0f GB/s (%d m, res %.2f ms)" % (k, v["gbs"], v["matches"], v["resolve_ms"]) for k, v in o.items() if isinstance(v, dict)), flush=True)
+    p = subprocess.run([sys.executable, "-c", CHILD, gib], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+    if p.returncode != 0:
+        print("FAILED", p.stderr.decode()[-500:])
+        return
+    o = json.loads(p.stdout.decode().strip().splitlines()[-1])
+    print("read probe %6.0f GB/s" % o["read_probe_gbs"])
+    for k, v in o.items():
+        if isinstance(v, dict):
+            print("%-8s %6.0f GB/s  (%8d matches, kernel %.3f ms, resolve %.2f ms, call %.2f ms)" % (k, v["gbs"], v["matches"], v["best_ms"], v["resolve_ms"], v["total_ms"]), flush=True)
 
 
 if __name__ == "__main__":
