@@ -78,6 +78,7 @@ _PROTOS = {
                                           ctypes.c_uint64, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32]),
     "gscan_read_probe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_float),
                                         ctypes.POINTER(ctypes.c_uint64)]),
+    "gscan_tma_probe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
     "gscan_abi_version": (ctypes.c_int, []),
 }
 
@@ -258,6 +259,11 @@ class Context:
         stride = file_len if stride is None else stride
         self._check(lib().gscan_synth_corpus(self._h, dptr, seed, first_file_id, n_files, file_len, stride,
                                              needle, len(needle) if needle else 0, needle_every))
+
+    def tma_probe(self, batch, geom=0):
+        ms = ctypes.c_float()
+        self._check(lib().gscan_tma_probe(self._h, batch._h, geom, ctypes.byref(ms)))
+        return ms.value
 
     def read_probe(self, dptr, nbytes):
         ms, cs = ctypes.c_float(), ctypes.c_uint64()

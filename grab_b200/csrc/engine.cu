@@ -500,6 +500,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		A.cand_cap = (uint32_t)std::min<size_t>(ctx->cand.cap, 0xffffffffu);
 		CK(ctx, cudaMemsetAsync(ctx->cursor.p, 0, 16, ctx->stream));
 		CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+		CK(ctx, cudaMemsetAsync(ctx->segs.p, 0, (size_t)n_segs * sizeof(SegEntry), ctx->stream)); // inside the timed region
 		if (pat->prog.kind == ENGINE_FIXED) CK(ctx, launch_scan_fixed(A, ctx->pat_fixed, pat->prog.delta, geom, grid, ctx->stream));
 		else CK(ctx, launch_scan_run(A, pat->run, geom, grid, ctx->stream));
 		CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -663,6 +664,31 @@ extern "C" int gscan_synth_corpus(gscan_ctx *ctx, void *dptr, uint64_t seed, uin
 	}
 	CK(ctx, launch_synth_corpus((uint8_t *)dptr, seed, first_file_id, n_files, file_len, stride, dn, needle_len, needle_every, ctx->stream));
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+extern "C" int gscan_tma_probe(gscan_ctx *ctx, gscan_batch *b, int geom, float *ms)
+{
+	if (!ctx || !b || !b->n_tiles) return fail(ctx, "gscan_tma_probe: null argument");
+	CK(ctx, cudaSetDevice(ctx->device));
+	const ScanGeom g = geom == 0 ? ScanGeom{GeomStream::kWarps, GeomStream::kRing, GeomStream::kSlice}
+	                             : ScanGeom{GeomBalanced::kWarps, GeomBalanced::kRing, GeomBalanced::kSlice};
+	const uint32_t n_segs = b->n_tiles * (uint32_t)(kTileBytes / g.slice);
+	CK(ctx, ctx->segs.ensure(n_segs));
+	CK(ctx, ctx->scratch.ensure((size_t)ctx->num_sms * g.warps * g.slice));
+	CK(ctx, ctx->cursor.ensure(2));
+	if (ctx->cand.cap == 0) CK(ctx, ctx->cand.ensure(1u << 20));
+	ScanArgs A;
+	A.tiles = b->d_tiles; A.n_tiles = b->n_tiles; A.cand = ctx->cand.p; A.cand_cap = (uint32_t)ctx->cand.cap;
+	A.cursor = ctx->cursor.p; A.segs = ctx->segs.p; A.scratch = ctx->scratch.p;
+	CK(ctx, cudaMemsetAsync(ctx->cursor.p, 0, 16, ctx->stream));
+	CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+	CK(ctx, launch_scan_null(A, geom, (int)std::min<uint32_t>((uint32_t)ctx->num_sms, b->n_tiles), ctx->stream));
+	CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	float t = 0;
+	cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]);
+	if (ms) *ms = t;
 	return 0;
 }
 

@@ -141,7 +141,7 @@ struct Emitter {
 			}
 			// else: the host sees cursor > cand_cap, grows the buffer and re-runs the scan
 		}
-		if (lane == 0) A.segs[seg] = SegEntry{base, n};
+		if (n && lane == 0) A.segs[seg] = SegEntry{base, n}; // empty segments stay {0,0}: the table is zeroed before the launch
 		n = 0;
 	}
 };
@@ -195,11 +195,17 @@ struct FixedEngine {
 		return f;
 	}
 
+	// the bytes D positions further on: D == 4 is the next word itself (no funnel shift at all)
+	static __device__ __forceinline__ uint32_t second(uint32_t lo, uint32_t hi)
+	{
+		return D == 0 ? lo : (D == 4 ? hi : __funnelshift_r(lo, hi, 8 * (D & 3)));
+	}
+
 	static __device__ __forceinline__ uint32_t row_any(const FixedParams &P, const uint32_t (&w)[5])
 	{
 		uint32_t acc = 0;
 #pragma unroll
-		for (int j = 0; j < 4; j++) acc |= word_flags(P, w[j], D ? __funnelshift_r(w[j], w[j + 1], 8 * D) : w[j]);
+		for (int j = 0; j < 4; j++) acc |= word_flags(P, w[j], second(w[j], w[j + 1]));
 		return acc;
 	}
 
@@ -214,7 +220,7 @@ struct FixedEngine {
 		uint32_t f[4];
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
-			const uint32_t s1 = D ? __funnelshift_r(w[j], w[j + 1], 8 * D) : w[j];
+			const uint32_t s1 = second(w[j], w[j + 1]);
 			if (P.n2) {
 				const uint32_t s2 = __funnelshift_r(w[j], w[j + 1], 8 * P.d2);
 				uint32_t g = 0;
@@ -389,6 +395,24 @@ struct RunEngine {
 };
 
 // ------------------------------------------------------------------------------------------
+// NULL engine: moves every slice through the ring and looks at nothing.  Measures what the TMA
+// streaming structure itself can pull from HBM (gscan_tma_probe) -- the ceiling of the scan kernels.
+// ------------------------------------------------------------------------------------------
+struct NullParams { uint32_t unused; };
+struct NullEngine {
+	typedef NullParams Params;
+	static constexpr bool kLookBehind = false, kLookAhead = false;
+	template <class G>
+	static __device__ __forceinline__ void run(const NullParams &, const Slice &S, Emitter &E, uint32_t lane)
+	{
+		// touch one word per row so the copy cannot be elided and the slot is really consumed
+		uint32_t x = 0;
+		for (uint32_t it = 0; it < S.niter; it++) x ^= *reinterpret_cast<const uint32_t *>(S.tile + S.begin + it * 512 + lane * 16);
+		if (x == 0x9e3779b9u && S.ulen == 0xffffffffu) E.n += 1; // never true; keeps x alive
+	}
+};
+
+// ------------------------------------------------------------------------------------------
 // the persistent kernel: warp-private TMA rings
 // ------------------------------------------------------------------------------------------
 // Slice s = 16 * tile + j is the j-th of the (up to) 16 contiguous 512-byte-row-aligned parts of a
@@ -509,6 +533,13 @@ ScanGeom scan_geom(int engine, uint32_t n_tests_or_ranges)
 	return ScanGeom{GeomBalanced::kWarps, GeomBalanced::kRing, GeomBalanced::kSlice};
 }
 
+cudaError_t launch_scan_null(const ScanArgs &A, int geom, int grid, cudaStream_t st)
+{
+	NullParams P{0};
+	if (geom == 0) return launch_g<NullEngine, GeomStream>(A, P, grid, st);
+	return launch_g<NullEngine, GeomBalanced>(A, P, grid, st);
+}
+
 template <int D, bool EX>
 static cudaError_t launch_fixed_de(const ScanArgs &A, const FixedParams &P, const ScanGeom &g, int grid, cudaStream_t st)
 {
@@ -529,7 +560,8 @@ cudaError_t launch_scan_fixed(const ScanArgs &A, const FixedParams &P, int delta
 	case 0: return ex ? launch_fixed_de<0, true>(A, P, g, grid, st) : launch_fixed_de<0, false>(A, P, g, grid, st);
 	case 1: return ex ? launch_fixed_de<1, true>(A, P, g, grid, st) : launch_fixed_de<1, false>(A, P, g, grid, st);
 	case 2: return ex ? launch_fixed_de<2, true>(A, P, g, grid, st) : launch_fixed_de<2, false>(A, P, g, grid, st);
-	default: return ex ? launch_fixed_de<3, true>(A, P, g, grid, st) : launch_fixed_de<3, false>(A, P, g, grid, st);
+	case 3: return ex ? launch_fixed_de<3, true>(A, P, g, grid, st) : launch_fixed_de<3, false>(A, P, g, grid, st);
+	default: return ex ? launch_fixed_de<4, true>(A, P, g, grid, st) : launch_fixed_de<4, false>(A, P, g, grid, st);
 	}
 }
 

@@ -147,6 +147,9 @@ int gscan_synth_corpus(gscan_ctx *ctx, void *dptr, uint64_t seed, uint64_t first
 /* Read-only streaming probe (16-byte loads + trivial reduce) over [dptr, dptr+bytes): the
  * measured HBM read roofline of this GPU in the same run.  ms = kernel time. */
 int gscan_read_probe(gscan_ctx *ctx, const void *dptr, uint64_t bytes, float *ms, uint64_t *checksum);
+/* The scan kernel's TMA ring with a consumer that looks at nothing: what the streaming structure itself pulls
+ * from HBM for this batch (geom 0: streaming geometry, 1: balanced).  ms = kernel time. */
+int gscan_tma_probe(gscan_ctx *ctx, gscan_batch *batch, int geom, float *ms);
 int gscan_abi_version(void);
 
 #ifdef __cplusplus

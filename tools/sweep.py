@@ -33,6 +33,8 @@ for name, pat, lit in (("literal", "foobardoesexist", True), ("alt4", "foo|bar|b
                  "matches": int(len(r)), "resolve_ms": st["resolve_ms"], "total_ms": st["total_ms"]}
 probe = min(ctx.read_probe(d, n << 20)[0] for _ in range(3))
 out["read_probe_gbs"] = (n << 20) / (probe * 1e-3) / 1e9
+for g in (0, 1):
+    out["tma_probe_" + str(g)] = (n << 20) / (min(ctx.tma_probe(batch, g) for _ in range(4)) * 1e-3) / 1e9
 print(json.dumps(out))
 ''' % (ROOT, ROOT)
 
@@ -44,7 +46,7 @@ def main():
         print("FAILED", p.stderr.decode()[-500:])
         return
     o = json.loads(p.stdout.decode().strip().splitlines()[-1])
-    print("read probe %6.0f GB/s" % o["read_probe_gbs"])
+    print("read probe %6.0f GB/s; TMA ring with null consumer: stream geom %6.0f, balanced geom %6.0f GB/s" % (o["read_probe_gbs"], o["tma_probe_0"], o["tma_probe_1"]))
     for k, v in o.items():
         if isinstance(v, dict):
             print("%-8s %6.0f GB/s  (%8d matches, kernel %.3f ms, resolve %.2f ms, call %.2f ms)" % (k, v["gbs"], v["matches"], v["best_ms"], v["resolve_ms"], v["total_ms"]), flush=True)
