@@ -70,8 +70,7 @@ struct PinnedBuf {
 };
 
 struct gscan_batch {
-	struct HostUnit { uint64_t base_off; uint32_t file_id; uint32_t len; };
-	std::vector<HostUnit> units; // device-unit order (zero-length units dropped), == caller order
+	uint32_t n_units = 0;        // units with len > 0, in caller order
 	TileDesc *d_tiles = nullptr;
 	DevUnit *d_units = nullptr;
 	uint8_t *d_arena = nullptr;  // staged copies of host units (owned)
@@ -92,13 +91,17 @@ struct gscan_ctx {
 	DevBuf<SegEntry> segs;
 	DevBuf<Cand> cand;
 	DevBuf<Cand> scratch;
-	DevBuf<OutRec> ord, out;
+	DevBuf<OutRec> ord;
+	DevBuf<FinalRec> out;
+	// pinned result buffers handed to the caller (gscan_match arrays), recycled by gscan_free_matches
+	struct ResultBuf { void *p; size_t cap; bool lent; };
+	std::vector<ResultBuf> results;
 	DevBuf<uint32_t> unit_start, unit_out, blk;
 	DevBuf<unsigned long long> cursor; // [0] cursor, then 2 x u32 totals behind it
 	DevBuf<uint8_t> pat_tables;
 	uint64_t pat_id = 0;
 	FixedParams pat_fixed; // with this context's device pointers
-	PinnedBuf readback, out_host, stage[2];
+	PinnedBuf readback, stage[2];
 	DevBuf<unsigned long long> probe_sum;
 	DevBuf<uint8_t> needle;
 	// pools behind the transient batches of gscan_scan_batch (grow-only: no cudaMalloc/cudaFree per call)
@@ -272,7 +275,8 @@ extern "C" void gscan_close(gscan_ctx *c)
 	c->unit_start.release(); c->unit_out.release(); c->blk.release(); c->cursor.release(); c->pat_tables.release();
 	c->probe_sum.release(); c->needle.release();
 	c->pool_arena.release(); c->pool_tiles.release(); c->pool_units.release();
-	c->readback.release(); c->out_host.release(); c->stage[0].release(); c->stage[1].release();
+	c->readback.release(); c->stage[0].release(); c->stage[1].release();
+	for (auto &rb : c->results) if (rb.p) cudaFreeHost(rb.p);
 	for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
 	cudaStreamDestroy(c->stream);
 	delete c;
@@ -389,11 +393,13 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 		}
 		DevUnit du;
 		du.ptr = (uint64_t)(uintptr_t)dptr;
+		du.base_off = u.base_off;
 		du.len = (uint32_t)u.len;
 		du.first_tile = (uint32_t)tiles.size();
+		du.file_id = u.file_id;
+		du.pad = 0;
 		const uint32_t unit_index = (uint32_t)dunits.size();
 		dunits.push_back(du);
-		b->units.push_back(gscan_batch::HostUnit{u.base_off, u.file_id, (uint32_t)u.len});
 		for (uint64_t off = 0; off < u.len; off += kTileBytes) {
 			TileDesc t;
 			t.src = du.ptr + off;
@@ -408,6 +414,7 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 	}
 	if (run_len) CK(ctx, cudaMemcpyAsync(run_dst, run_src, run_len, cudaMemcpyHostToDevice, ctx->stream));
 	b->n_tiles = (uint32_t)tiles.size();
+	b->n_units = (uint32_t)dunits.size();
 	if (!tiles.empty()) {
 		if (pooled) {
 			CK(ctx, ctx->pool_tiles.ensure(tiles.size()));
@@ -464,7 +471,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	gscan_stats &S = ctx->stats;
 	memset(&S, 0, sizeof(S));
 	S.bytes_scanned = b->bytes;
-	S.n_units = (uint32_t)b->units.size();
+	S.n_units = b->n_units;
 	S.n_tiles = b->n_tiles;
 	S.h2d_ms = b->h2d_ms;
 	if (pat->prog.kind == ENGINE_NONE || b->n_tiles == 0) {
@@ -521,12 +528,13 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	S.n_candidates = total_cand;
 
 	size_t n = 0;
-	const OutRec *h_recs = nullptr;
+	gscan_match *m = nullptr;
+	static_assert(sizeof(FinalRec) == sizeof(gscan_match), "device records are gscan_match");
 	if (total_cand) {
-		const uint32_t nb_seg = (n_segs + 2047) / 2048, nb_u = (uint32_t)((b->units.size() + 2047) / 2048);
+		const uint32_t nb_seg = (n_segs + 2047) / 2048, nb_u = (uint32_t)((b->n_units + 2047) / 2048);
 		CK(ctx, ctx->ord.ensure((size_t)total_cand));
-		CK(ctx, ctx->unit_start.ensure(b->units.size() + 1));
-		CK(ctx, ctx->unit_out.ensure(b->units.size() + 1));
+		CK(ctx, ctx->unit_start.ensure((size_t)b->n_units + 1));
+		CK(ctx, ctx->unit_out.ensure((size_t)b->n_units + 1));
 		CK(ctx, ctx->blk.ensure((size_t)nb_seg + nb_u + 4));
 		ResolveArgs R;
 		R.tiles = b->d_tiles;
@@ -535,7 +543,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		R.slices_per_tile = spt;
 		R.cand = ctx->cand.p;
 		R.units = b->d_units;
-		R.n_units = (uint32_t)b->units.size();
+		R.n_units = b->n_units;
 		R.ord = ctx->ord.p;
 		R.out = nullptr;
 		R.unit_start = ctx->unit_start.p;
@@ -557,13 +565,27 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		if (h_tot[0] != (uint32_t)total_cand) return fail(ctx, "gscan_batch_scan: internal: segment counts disagree with the cursor");
 		n = h_tot[1];
 		if (n) {
+			// the records are written on the device in their final form and land in a pinned buffer that is lent
+			// to the caller until gscan_free_matches()
+			gscan_ctx::ResultBuf *rb = nullptr;
+			for (auto &x : ctx->results) if (!x.lent && (!rb || x.cap > rb->cap)) rb = &x;
+			if (!rb) { ctx->results.push_back(gscan_ctx::ResultBuf{nullptr, 0, false}); rb = &ctx->results.back(); }
+			if (rb->cap < n * sizeof(gscan_match)) {
+				if (rb->p) cudaFreeHost(rb->p);
+				rb->p = nullptr;
+				rb->cap = 0;
+				const size_t want = std::max<size_t>(n * sizeof(gscan_match) * 5 / 4, (size_t)1 << 16);
+				CK(ctx, cudaHostAlloc(&rb->p, want, cudaHostAllocDefault));
+				rb->cap = want;
+			}
 			CK(ctx, ctx->out.ensure(n));
-			CK(ctx, ctx->out_host.ensure(n * sizeof(OutRec)));
 			R.out = ctx->out.p;
 			CK(ctx, launch_resolve_write(R, ctx->stream, &nl));
 			S.total_launches += nl;
 			CK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-			CK(ctx, cudaMemcpyAsync(ctx->out_host.p, ctx->out.p, n * sizeof(OutRec), cudaMemcpyDeviceToHost, ctx->stream));
+			CK(ctx, cudaMemcpyAsync(rb->p, ctx->out.p, n * sizeof(FinalRec), cudaMemcpyDeviceToHost, ctx->stream));
+			rb->lent = true;
+			m = static_cast<gscan_match *>(rb->p);
 		} else {
 			CK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
 		}
@@ -571,18 +593,6 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		float ms = 0;
 		cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
 		S.resolve_ms = ms;
-		h_recs = reinterpret_cast<const OutRec *>(ctx->out_host.p);
-	}
-	gscan_match *m = nullptr;
-	if (n) {
-		m = (gscan_match *)malloc(n * sizeof(gscan_match));
-		if (!m) return fail(ctx, "gscan_batch_scan: out of memory for results");
-		for (size_t i = 0; i < n; i++) {
-			const gscan_batch::HostUnit &hu = b->units[h_recs[i].unit];
-			m[i].start = hu.base_off + h_recs[i].pos; // grab.cc:186: off + (start - content) + ovector[0]
-			m[i].file_id = hu.file_id;
-			m[i].match_len = h_recs[i].len;
-		}
 	}
 	*out = m;
 	*n_out = n;
@@ -604,7 +614,11 @@ extern "C" int gscan_scan_batch(gscan_ctx *ctx, const gscan_pattern *pat, const 
 	return rc;
 }
 
-extern "C" void gscan_free_matches(gscan_ctx *, gscan_match *m) { free(m); }
+extern "C" void gscan_free_matches(gscan_ctx *ctx, gscan_match *m)
+{
+	if (!ctx || !m) return;
+	for (auto &rb : ctx->results) if (rb.p == m) rb.lent = false;
+}
 
 // ------------------------------------------------------------------------------------------
 // utilities

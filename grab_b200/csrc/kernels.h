@@ -16,8 +16,18 @@ cudaError_t launch_scan_run(const ScanArgs &A, const RunParams &P, const ScanGeo
 
 struct DevUnit {
 	uint64_t ptr;        // device address of the unit's bytes
+	uint64_t base_off;   // file offset of the unit (grab.cc:154 `off`)
 	uint32_t len;
 	uint32_t first_tile; // index of the unit's first tile
+	uint32_t file_id;
+	uint32_t pad;
+};
+
+// what goes back to the caller: byte-for-byte a gscan_match (include/gscan.h)
+struct FinalRec {
+	uint64_t start;      // base_off + pos == off + (start - content) + ovector[0]   (grab.cc:186)
+	uint32_t file_id;
+	uint32_t len;
 };
 
 struct ResolveArgs {
@@ -29,7 +39,7 @@ struct ResolveArgs {
 	const DevUnit *units;
 	uint32_t n_units;
 	OutRec *ord;          // candidates in (unit, pos) order
-	OutRec *out;          // selected matches, same order (capacity known after the count pass)
+	FinalRec *out;        // selected matches, same order (capacity known after the count pass)
 	uint32_t *unit_start; // [n_units + 1] first candidate of each unit in ord
 	uint32_t *unit_out;   // [n_units] matches per unit, then (exclusive scan) first output slot
 	uint32_t *blk;        // block-sum scratch

@@ -136,7 +136,7 @@ __global__ void k_walk(const ResolveArgs R)
 	uint32_t i = R.unit_start[u];
 	const uint32_t end = R.unit_start[u + 1];
 	uint32_t n = 0;
-	OutRec *o = WRITE ? R.out + R.unit_out[u] : nullptr;
+	FinalRec *o = WRITE ? R.out + R.unit_out[u] : nullptr;
 	if (i != end) {
 		const DevUnit du = R.units[u];
 		const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
@@ -164,7 +164,7 @@ __global__ void k_walk(const ResolveArgs R)
 				}
 				i++;
 			}
-			if (WRITE) { OutRec r; r.unit = u; r.pos = (uint32_t)pos; r.len = (uint32_t)(e - pos); r.pad = 0; o[n] = r; }
+			if (WRITE) { FinalRec r; r.start = du.base_off + pos; r.file_id = du.file_id; r.len = (uint32_t)(e - pos); o[n] = r; }
 			n++;
 			if (R.mode == GSCAN_MODE_FIRST) break;                 // grab.cc:206 / :211
 			if (R.mode == GSCAN_MODE_LINE) {                       // grab.cc:194-196: a = bytes to '\n', <= 511
