@@ -21,6 +21,7 @@ struct Geom {
 };
 typedef Geom<16, 3, 4096> GeomStream;  // memory-bound: single-test literal filter
 typedef Geom<24, 4, 2048> GeomBalanced;
+typedef Geom<16, 4, 2048> GeomHash;     // leaves 32 KiB of shared memory for the hash table
 
 struct ScanGeom { int warps, ring, slice; }; // host-side mirror of the chosen Geom
 
@@ -63,6 +64,25 @@ struct FixedParams {
 	uint32_t t2_m0[16], t2_v0[16], t2_m1[16], t2_v1[16], t2_m2[16], t2_v2[16];
 };
 
+// FIXED, hashed: exact membership of the 2 or 3 bytes at every position in a perfect-hash table held in
+// shared memory; hits are verified against the alternatives sharing the key
+struct HashParams {
+	uint32_t mul;        // slot byte offset = umulhi(key, mul) & slot_mask
+	uint32_t slot_mask;  // (slots - 1) << 2
+	uint32_t key_mask;   // 0xffff or 0xffffff
+	uint32_t nslots;
+	const uint32_t *table;      // [nslots] key or 0xffffffff (copied to shared memory at kernel start)
+	const uint32_t *slot_first; // [nslots] first index into slot_seqs
+	const uint32_t *slot_count; // [nslots]
+	const uint32_t *slot_seqs;  // alternatives of a key, preference order
+	uint32_t uniform_len, maxlen;
+	const uint16_t *seq_len;
+	const uint32_t *seq_off;
+	const uint32_t *seq_pos;
+	const uint32_t *cls_bm;
+};
+constexpr int kHashMaxSlots = 8192;
+
 struct RunParams {
 	uint32_t one;         // == 1, opaque (see FixedParams)
 	uint32_t nlo, nhi;
@@ -80,6 +100,7 @@ struct ScanArgs {
 	unsigned long long *cursor; // [0]: candidates reserved so far
 	SegEntry *segs;
 	Cand *scratch;  // [gridDim.x * warps][slice bytes]: one private list per warp
+	uint32_t extra_smem; // bytes of engine-private shared memory behind the rings (hash table)
 };
 
 } // namespace gscan

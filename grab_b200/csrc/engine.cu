@@ -31,6 +31,7 @@ struct gscan_pattern {
 	std::vector<uint16_t> seq_len;
 	std::vector<uint32_t> seq_off, seq_pos, cls_bm;
 	FixedParams fixed; // device pointers filled per context
+	HashParams hash;
 	RunParams run;
 };
 
@@ -98,9 +99,10 @@ struct gscan_ctx {
 	std::vector<ResultBuf> results;
 	DevBuf<uint32_t> unit_start, unit_out, blk;
 	DevBuf<unsigned long long> cursor; // [0] cursor, then 2 x u32 totals behind it
-	DevBuf<uint8_t> pat_tables;
+	DevBuf<uint8_t> pat_tables, hash_tables;
 	uint64_t pat_id = 0;
 	FixedParams pat_fixed; // with this context's device pointers
+	HashParams pat_hash;
 	PinnedBuf readback, stage[2];
 	DevBuf<unsigned long long> probe_sum;
 	DevBuf<uint8_t> needle;
@@ -147,6 +149,7 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 	const Program &pr = p->prog;
 	memset(&p->fixed, 0, sizeof(p->fixed));
 	memset(&p->run, 0, sizeof(p->run));
+	memset(&p->hash, 0, sizeof(p->hash));
 	if (pr.kind == ENGINE_FIXED) {
 		FixedParams &F = p->fixed;
 		F.one = 1;
@@ -191,6 +194,15 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 			}
 		}
 		for (auto &c : classes) for (int i = 0; i < 8; i++) p->cls_bm.push_back(c.w[i]);
+		if (pr.use_hash) {
+			HashParams &H = p->hash;
+			H.mul = pr.hash_mul;
+			H.nslots = pr.hash_slots;
+			H.slot_mask = (pr.hash_slots - 1) << 2;
+			H.key_mask = pr.hash_len == 2 ? 0xffffu : 0xffffffu;
+			H.uniform_len = F.uniform_len;
+			H.maxlen = F.maxlen;
+		}
 	} else if (pr.kind == ENGINE_RUN) {
 		RunParams &R = p->run;
 		R.one = 1;
@@ -224,7 +236,7 @@ extern "C" int gscan_pattern_get_info(const gscan_pattern *p, gscan_pattern_info
 	o->captures = p->prog.captures;
 	o->engine = (int32_t)p->prog.kind;
 	o->n_sequences = (int32_t)p->prog.seqs.size();
-	o->n_filter_tests = (int32_t)p->prog.tests.size();
+	o->n_filter_tests = p->prog.use_hash ? -(int32_t)p->prog.hash_slots : (int32_t)p->prog.tests.size();
 	o->filter_anchor = p->prog.anchor;
 	o->filter_delta = p->prog.delta;
 	return 0;
@@ -272,7 +284,7 @@ extern "C" void gscan_close(gscan_ctx *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->segs.release(); c->cand.release(); c->scratch.release(); c->ord.release(); c->out.release();
-	c->unit_start.release(); c->unit_out.release(); c->blk.release(); c->cursor.release(); c->pat_tables.release();
+	c->unit_start.release(); c->unit_out.release(); c->blk.release(); c->cursor.release(); c->pat_tables.release(); c->hash_tables.release();
 	c->probe_sum.release(); c->needle.release();
 	c->pool_arena.release(); c->pool_tiles.release(); c->pool_units.release();
 	c->readback.release(); c->stage[0].release(); c->stage[1].release();
@@ -454,6 +466,26 @@ static int ensure_pattern(gscan_ctx *ctx, const gscan_pattern *pat)
 		ctx->pat_fixed.seq_off = reinterpret_cast<const uint32_t *>(d + b_len);
 		ctx->pat_fixed.seq_pos = reinterpret_cast<const uint32_t *>(d + b_len + b_off);
 		ctx->pat_fixed.cls_bm = reinterpret_cast<const uint32_t *>(d + b_len + b_off + b_pos);
+		if (pat->prog.use_hash) {
+			const Program &pr = pat->prog;
+			const size_t nt = pr.hash_table.size() * 4, ns = pr.slot_seqs.size() * 4;
+			CK(ctx, ctx->hash_tables.ensure(3 * nt + ns + 64));
+			uint8_t *h = ctx->hash_tables.p;
+			CK(ctx, cudaMemcpyAsync(h, pr.hash_table.data(), nt, cudaMemcpyHostToDevice, ctx->stream));
+			CK(ctx, cudaMemcpyAsync(h + nt, pr.slot_first.data(), nt, cudaMemcpyHostToDevice, ctx->stream));
+			CK(ctx, cudaMemcpyAsync(h + 2 * nt, pr.slot_count.data(), nt, cudaMemcpyHostToDevice, ctx->stream));
+			if (ns) CK(ctx, cudaMemcpyAsync(h + 3 * nt, pr.slot_seqs.data(), ns, cudaMemcpyHostToDevice, ctx->stream));
+			CK(ctx, cudaStreamSynchronize(ctx->stream));
+			ctx->pat_hash = pat->hash;
+			ctx->pat_hash.table = reinterpret_cast<const uint32_t *>(h);
+			ctx->pat_hash.slot_first = reinterpret_cast<const uint32_t *>(h + nt);
+			ctx->pat_hash.slot_count = reinterpret_cast<const uint32_t *>(h + 2 * nt);
+			ctx->pat_hash.slot_seqs = reinterpret_cast<const uint32_t *>(h + 3 * nt);
+			ctx->pat_hash.seq_len = ctx->pat_fixed.seq_len;
+			ctx->pat_hash.seq_off = ctx->pat_fixed.seq_off;
+			ctx->pat_hash.seq_pos = ctx->pat_fixed.seq_pos;
+			ctx->pat_hash.cls_bm = ctx->pat_fixed.cls_bm;
+		}
 	}
 	ctx->pat_id = pat->prog.id;
 	return 0;
@@ -480,7 +512,8 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	}
 	if (ensure_pattern(ctx, pat) < 0) return -1;
 
-	const ScanGeom geom = scan_geom((int)pat->prog.kind, pat->prog.kind == ENGINE_FIXED ? (uint32_t)pat->prog.tests.size() : 99u);
+	const bool hashed = pat->prog.kind == ENGINE_FIXED && pat->prog.use_hash;
+	const ScanGeom geom = scan_geom(hashed ? 4 : (int)pat->prog.kind, pat->prog.kind == ENGINE_FIXED ? (uint32_t)pat->prog.tests.size() : 99u);
 	const uint32_t spt = (uint32_t)(kTileBytes / geom.slice);
 	const uint32_t n_segs = b->n_tiles * spt;
 	const int grid = (int)std::min<uint32_t>((uint32_t)ctx->num_sms, b->n_tiles);
@@ -499,6 +532,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	A.cursor = ctx->cursor.p;
 	A.segs = ctx->segs.p;
 	A.scratch = ctx->scratch.p;
+	A.extra_smem = hashed ? pat->prog.hash_slots * 4u : 0u;
 
 	unsigned long long *h_cursor = reinterpret_cast<unsigned long long *>(ctx->readback.p);
 	unsigned long long total_cand = 0;
@@ -508,7 +542,8 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		CK(ctx, cudaMemsetAsync(ctx->cursor.p, 0, 16, ctx->stream));
 		CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
 		CK(ctx, cudaMemsetAsync(ctx->segs.p, 0, (size_t)n_segs * sizeof(SegEntry), ctx->stream)); // inside the timed region
-		if (pat->prog.kind == ENGINE_FIXED) CK(ctx, launch_scan_fixed(A, ctx->pat_fixed, pat->prog.delta, geom, grid, ctx->stream));
+		if (hashed) CK(ctx, launch_scan_hash(A, ctx->pat_hash, grid, ctx->stream));
+		else if (pat->prog.kind == ENGINE_FIXED) CK(ctx, launch_scan_fixed(A, ctx->pat_fixed, pat->prog.delta, geom, grid, ctx->stream));
 		else CK(ctx, launch_scan_run(A, pat->run, geom, grid, ctx->stream));
 		CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 		CK(ctx, cudaMemcpyAsync(h_cursor, ctx->cursor.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -694,7 +729,7 @@ extern "C" int gscan_tma_probe(gscan_ctx *ctx, gscan_batch *b, int geom, float *
 	if (ctx->cand.cap == 0) CK(ctx, ctx->cand.ensure(1u << 20));
 	ScanArgs A;
 	A.tiles = b->d_tiles; A.n_tiles = b->n_tiles; A.cand = ctx->cand.p; A.cand_cap = (uint32_t)ctx->cand.cap;
-	A.cursor = ctx->cursor.p; A.segs = ctx->segs.p; A.scratch = ctx->scratch.p;
+	A.cursor = ctx->cursor.p; A.segs = ctx->segs.p; A.scratch = ctx->scratch.p; A.extra_smem = 0;
 	CK(ctx, cudaMemsetAsync(ctx->cursor.p, 0, 16, ctx->stream));
 	CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
 	CK(ctx, launch_scan_null(A, geom, (int)std::min<uint32_t>((uint32_t)ctx->num_sms, b->n_tiles), ctx->stream));

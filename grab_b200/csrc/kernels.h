@@ -11,6 +11,7 @@ namespace gscan {
 size_t scan_smem_bytes(const ScanGeom &g);
 ScanGeom scan_geom(int engine, uint32_t n_tests_or_ranges);
 cudaError_t launch_scan_fixed(const ScanArgs &A, const FixedParams &P, int delta, const ScanGeom &g, int grid, cudaStream_t st);
+cudaError_t launch_scan_hash(const ScanArgs &A, const HashParams &P, int grid, cudaStream_t st);
 cudaError_t launch_scan_null(const ScanArgs &A, int geom, int grid, cudaStream_t st);
 cudaError_t launch_scan_run(const ScanArgs &A, const RunParams &P, const ScanGeom &g, int grid, cudaStream_t st);
 

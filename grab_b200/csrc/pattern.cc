@@ -606,6 +606,69 @@ bool can_overlap(const Sequence &a, const Sequence &b, size_t shift)
 
 std::atomic<uint64_t> g_next_id{1};
 
+uint32_t umulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+
+// Perfect hash over the distinct values of the first L bytes (little endian, like a 32-bit load) of all
+// alternatives.  Classes in the leading positions are enumerated (e.g. (?i) doubles per letter).
+bool build_hash(Program &out, int L)
+{
+	std::vector<std::pair<uint32_t, uint32_t>> kv; // (key, sequence index)
+	size_t total = 0;
+	for (size_t si = 0; si < out.seqs.size(); si++) {
+		const Sequence &s = out.seqs[si];
+		size_t combos = 1;
+		for (int i = 0; i < L; i++) combos *= (size_t)s[i].count();
+		total += combos;
+		if (combos == 0 || total > 4096) return false;
+		std::vector<uint32_t> keys(1, 0);
+		for (int i = 0; i < L; i++) {
+			std::vector<uint32_t> next;
+			for (uint32_t k : keys)
+				for (unsigned b = 0; b < 256; b++)
+					if (s[i].has(b)) next.push_back(k | (b << (8 * i)));
+			keys.swap(next);
+		}
+		for (uint32_t k : keys) kv.push_back(std::make_pair(k, (uint32_t)si));
+	}
+	std::vector<uint32_t> distinct;
+	for (auto &e : kv) distinct.push_back(e.first);
+	std::sort(distinct.begin(), distinct.end());
+	distinct.erase(std::unique(distinct.begin(), distinct.end()), distinct.end());
+	uint32_t slots = 256;
+	while (slots < 2 * distinct.size()) slots <<= 1;
+	uint64_t rng = 0x9E3779B97F4A7C15ull ^ (distinct.size() * 0xD1B54A32D192ED03ull);
+	for (; slots <= 8192; slots <<= 1) {
+		for (int attempt = 0; attempt < 4000; attempt++) {
+			rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+			const uint32_t mul = (uint32_t)(rng >> 32) | 1u;
+			std::vector<uint32_t> table(slots, 0xffffffffu);
+			bool ok = true;
+			for (uint32_t k : distinct) {
+				const uint32_t sl = (umulhi32(k, mul) >> 2) & (slots - 1);
+				if (table[sl] != 0xffffffffu) { ok = false; break; }
+				table[sl] = k;
+			}
+			if (!ok) continue;
+			out.use_hash = true;
+			out.hash_len = L;
+			out.hash_mul = mul;
+			out.hash_slots = slots;
+			out.hash_table = table;
+			out.slot_first.assign(slots, 0);
+			out.slot_count.assign(slots, 0);
+			out.slot_seqs.clear();
+			for (uint32_t sl = 0; sl < slots; sl++) {
+				if (table[sl] == 0xffffffffu) continue;
+				out.slot_first[sl] = (uint32_t)out.slot_seqs.size();
+				for (auto &e : kv) // kv is in preference order of the alternatives
+					if (e.first == table[sl]) { out.slot_seqs.push_back(e.second); out.slot_count[sl]++; }
+			}
+			return true;
+		}
+	}
+	return false;
+}
+
 } // namespace
 
 bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, std::string &err)
@@ -725,9 +788,24 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 		}
 		if (mn < 2) break;
 	}
-	if (best_tests.empty()) {
-		err = "alternation needs more than 8 distinct byte-pair filter tests (large literal sets: hashed engine not built yet)";
+	// many distinct byte pairs: the pair filter gets slow (4 ops per test and word) -- switch to the hashed engine
+	if ((best_tests.empty() || best_tests.size() > 4) && mn >= 2 && build_hash(out, (int)std::min<size_t>(mn, 3))) {
+		out.anchor = 0;
+		out.delta = 0;
+		out.tests.clear();
+	} else if (best_tests.empty()) {
+		err = "alternation needs more than 8 distinct byte-pair filter tests and its leading bytes cannot be hashed "
+		      "(an alternative shorter than 2 bytes, or more than 4096 distinct leading byte combinations)";
 		return false;
+	}
+	if (out.use_hash) {
+		bool dj = out.seqs.size() <= 256;
+		for (size_t i = 0; i < out.seqs.size() && dj; i++)
+			for (size_t j = 0; j < out.seqs.size() && dj; j++)
+				for (size_t sh = 1; sh < out.seqs[i].size() && dj; sh++)
+					if (can_overlap(out.seqs[i], out.seqs[j], sh)) dj = false;
+		out.disjoint = dj;
+		return true;
 	}
 	out.anchor = best_a;
 	out.delta = best_d;

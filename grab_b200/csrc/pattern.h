@@ -73,6 +73,15 @@ struct Program {
 	int delta2 = 0;
 	bool disjoint = false;            // no two matches can ever overlap => resolve is a pure copy
 
+	// FIXED, hashed variant (many alternatives): the first hash_len bytes of every alternative are keys of
+	// a perfect-hash table; membership of the text's bytes at p is EXACT, then only the alternatives that
+	// share the key are verified
+	bool use_hash = false;
+	int hash_len = 0;                       // 2 or 3 key bytes
+	uint32_t hash_mul = 0, hash_slots = 0;  // slot = (umulhi(key, mul) >> 2) & (slots - 1)
+	std::vector<uint32_t> hash_table;       // [slots] key, 0xffffffff = empty
+	std::vector<uint32_t> slot_first, slot_count, slot_seqs; // alternatives per slot, preference order
+
 	// RUN
 	ByteSet run_class;
 	int run_min = 0;

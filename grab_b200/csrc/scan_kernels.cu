@@ -93,6 +93,7 @@ size_t scan_smem_bytes(const ScanGeom &g)
 struct Slice {
 	const uint8_t *tile;  // shared-memory address of the tile's byte 0 (only the slice itself is resident)
 	const uint8_t *gtile; // global address of the tile's byte 0 (neighbouring bytes, verification)
+	const uint8_t *extra; // engine-private shared memory (hash table)
 	uint32_t off;        // offset of the tile in its unit
 	uint32_t ulen;       // unit length
 	uint32_t tile_len;
@@ -153,6 +154,7 @@ template <int D, int K, bool EX>
 struct FixedEngine {
 	typedef FixedParams Params;
 	static constexpr bool kLookBehind = false, kLookAhead = D != 0;
+	static __device__ __forceinline__ void prologue(const FixedParams &, uint8_t *) {}
 
 	// first sequence (in preference order) matching with its anchor byte at tile position p; 0: none
 	// reads the unit's bytes from global memory (tile = global address of tile byte 0)
@@ -298,12 +300,119 @@ struct FixedEngine {
 };
 
 // ------------------------------------------------------------------------------------------
+// HASH engine: FIXED with many alternatives (literal sets).  The first L = 2 or 3 bytes at every position
+// are looked up in a perfect-hash table in shared memory -- exact membership, one multiply (FMA pipe),
+// one LDS and four ALU ops per position, independent of how many alternatives there are.  Only true
+// key hits are verified, against the alternatives that share the key, in preference order.
+// ------------------------------------------------------------------------------------------
+struct HashEngine {
+	typedef HashParams Params;
+	static constexpr bool kLookBehind = false, kLookAhead = true;
+
+	static __device__ __forceinline__ void prologue(const HashParams &P, uint8_t *extra)
+	{
+		uint32_t *t = reinterpret_cast<uint32_t *>(extra);
+		for (uint32_t i = threadIdx.x; i < P.nslots; i += blockDim.x) t[i] = P.table[i];
+		__syncthreads();
+	}
+
+	// first alternative (preference order) with this key that matches at tile position p; 0: none
+	static __device__ uint32_t verify(const HashParams &P, const uint8_t *tile, uint32_t off, uint32_t ulen, int p, uint32_t slot)
+	{
+		const unsigned long long qu = (unsigned long long)off + (unsigned)p;
+		const uint32_t first = P.slot_first[slot], cnt = P.slot_count[slot];
+		for (uint32_t k = 0; k < cnt; k++) {
+			const uint32_t s = P.slot_seqs[first + k];
+			const uint32_t len = P.seq_len[s];
+			if (qu + len > ulen) continue;
+			const uint32_t *pp = P.seq_pos + P.seq_off[s];
+			uint32_t i = 0;
+			for (; i < len; i++) {
+				const uint32_t e = pp[i];
+				const uint32_t b = tile[p + (int)i];
+				const uint32_t cls = e >> 16;
+				bool ok;
+				if (cls == 0xffffu) ok = (b & (e & 0xffu)) == ((e >> 8) & 0xffu);
+				else ok = (P.cls_bm[cls * 8 + (b >> 5)] >> (b & 31)) & 1u;
+				if (!ok) break;
+			}
+			if (i == len) return len;
+		}
+		return 0;
+	}
+
+	static __device__ __forceinline__ uint32_t key_at(const HashParams &P, uint32_t lo, uint32_t hi, int k)
+	{
+		return (k ? __funnelshift_r(lo, hi, 8 * k) : lo) & P.key_mask;
+	}
+
+	// min over the 16 positions of (table[slot(key)] ^ key): zero <=> some position holds a key of the set
+	static __device__ __forceinline__ uint32_t row_min(const HashParams &P, const uint8_t *tbl, const uint32_t (&w)[5])
+	{
+		uint32_t mn = 0xffffffffu;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const uint32_t y = key_at(P, w[j], w[j + 1], k);
+				const uint32_t e = *reinterpret_cast<const uint32_t *>(tbl + (__umulhi(y, P.mul) & P.slot_mask));
+				mn = min(mn, e ^ y);
+			}
+		}
+		return mn;
+	}
+
+	static __device__ __noinline__ uint32_t slow_row(const HashParams &P, const uint8_t *tbl, const uint8_t *gtile, uint32_t off,
+	                                                 uint32_t ulen, uint32_t tile_len, Cand *dst, uint32_t lane, uint32_t c0,
+	                                                 uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4)
+	{
+		const uint32_t w[5] = {w0, w1, w2, w3, w4};
+		uint32_t mm = 0;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const uint32_t y = key_at(P, w[j], w[j + 1], k);
+				const uint32_t so = __umulhi(y, P.mul) & P.slot_mask;
+				const uint32_t e = *reinterpret_cast<const uint32_t *>(tbl + so);
+				const int p = (int)c0 + j * 4 + k;
+				if (e == y && p < (int)tile_len && verify(P, gtile, off, ulen, p, so >> 2)) mm |= 1u << (j * 4 + k);
+			}
+		}
+		return Emitter::emit_at(dst, mm, off + c0, [&](uint32_t b) -> uint32_t {
+			if (P.uniform_len) return P.uniform_len;
+			const int j = (int)b >> 2, k = (int)b & 3;
+			const uint32_t y = key_at(P, w[j], w[j + 1], k);
+			return verify(P, gtile, off, ulen, (int)(c0 + b), (__umulhi(y, P.mul) & P.slot_mask) >> 2);
+		}, lane);
+	}
+
+	template <class G>
+	static __device__ __forceinline__ void run(const HashParams &P, const Slice &S, Emitter &E, uint32_t lane)
+	{
+		const uint8_t *tbl = S.extra;
+		const uint32_t base = S.begin + lane * 16;
+		for (uint32_t it = 0; it < S.niter; it++) {
+			const uint32_t c0 = base + it * 512;
+			uint32_t w[5];
+			const uint4 a = *reinterpret_cast<const uint4 *>(S.tile + c0);
+			w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+			w[4] = *reinterpret_cast<const uint32_t *>(S.tile + c0 + 16);
+			const uint32_t mn = row_min(P, tbl, w);
+			if (__any_sync(0xffffffffu, mn == 0))
+				E.n += slow_row(P, tbl, S.gtile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, c0, w[0], w[1], w[2], w[3], w[4]);
+		}
+	}
+};
+
+// ------------------------------------------------------------------------------------------
 // RUN engine: one byte class repeated {n,}: one candidate per maximal run of >= n class bytes
 // ------------------------------------------------------------------------------------------
 template <int NLO, int NHI>
 struct RunEngine {
 	typedef RunParams Params;
 	static constexpr bool kLookBehind = true, kLookAhead = true;
+	static __device__ __forceinline__ void prologue(const RunParams &, uint8_t *) {}
 
 	static __device__ __forceinline__ uint32_t class_flags(const RunParams &P, uint32_t x)
 	{
@@ -402,6 +511,7 @@ struct NullParams { uint32_t unused; };
 struct NullEngine {
 	typedef NullParams Params;
 	static constexpr bool kLookBehind = false, kLookAhead = false;
+	static __device__ __forceinline__ void prologue(const NullParams &, uint8_t *) {}
 	template <class G>
 	static __device__ __forceinline__ void run(const NullParams &, const Slice &S, Emitter &E, uint32_t lane)
 	{
@@ -440,6 +550,8 @@ scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename
 	constexpr uint32_t slot_bytes = G::kSlice + 2 * kHalo;
 	uint8_t *my = smem + (size_t)warp * G::kRing * slot_bytes;
 	SlotCtl *ctl = reinterpret_cast<SlotCtl *>(smem + (size_t)G::kWarps * G::kRing * slot_bytes) + warp * G::kRing;
+	uint8_t *extra = smem + (size_t)G::kWarps * G::kRing * (slot_bytes + sizeof(SlotCtl)) + 64;
+	Eng::prologue(P, extra);
 
 	const uint32_t total = A.n_tiles * G::kSlicesPerTile;
 	const uint32_t stride = gridDim.x * G::kWarps;
@@ -496,6 +608,7 @@ scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename
 		S.niter = ctl[slot].niter;
 		S.tile = my + (size_t)slot * slot_bytes + kHalo - S.begin; // address of tile byte 0 (only the slice window is resident)
 		S.gtile = reinterpret_cast<const uint8_t *>(ctl[slot].src);
+		S.extra = extra;
 		Eng::template run<G>(P, S, E, lane);
 		E.flush(A, s, lane);
 		__syncwarp(); // every lane is done reading the slot before it is overwritten
@@ -511,7 +624,7 @@ template <class Eng, class G>
 static cudaError_t launch_g(const ScanArgs &A, const typename Eng::Params &P, int grid, cudaStream_t st)
 {
 	const ScanGeom g{G::kWarps, G::kRing, G::kSlice};
-	const size_t smem = scan_smem_bytes(g);
+	const size_t smem = scan_smem_bytes(g) + A.extra_smem;
 	cudaError_t e = cudaFuncSetAttribute(scan_kernel<Eng, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	scan_kernel<Eng, G><<<grid, G::kThreads, smem, st>>>(A, P);
@@ -529,6 +642,7 @@ static cudaError_t launch(const ScanArgs &A, const typename Eng::Params &P, cons
 // which geometry an engine runs with
 ScanGeom scan_geom(int engine, uint32_t n_tests_or_ranges)
 {
+	if (engine == 4 /*FIXED, hashed*/) return ScanGeom{GeomHash::kWarps, GeomHash::kRing, GeomHash::kSlice};
 	if (engine == 1 /*FIXED*/ && n_tests_or_ranges <= 1) return ScanGeom{GeomStream::kWarps, GeomStream::kRing, GeomStream::kSlice};
 	return ScanGeom{GeomBalanced::kWarps, GeomBalanced::kRing, GeomBalanced::kSlice};
 }
@@ -538,6 +652,11 @@ cudaError_t launch_scan_null(const ScanArgs &A, int geom, int grid, cudaStream_t
 	NullParams P{0};
 	if (geom == 0) return launch_g<NullEngine, GeomStream>(A, P, grid, st);
 	return launch_g<NullEngine, GeomBalanced>(A, P, grid, st);
+}
+
+cudaError_t launch_scan_hash(const ScanArgs &A, const HashParams &P, int grid, cudaStream_t st)
+{
+	return launch_g<HashEngine, GeomHash>(A, P, grid, st);
 }
 
 template <int D, bool EX>

@@ -66,7 +66,7 @@ typedef struct gscan_pattern_info {
 	int32_t captures;     /* capturing groups in the pattern (Q2) */
 	int32_t engine;       /* GSCAN_ENGINE_* below */
 	int32_t n_sequences;  /* alternatives after expansion (fixed engine) */
-	int32_t n_filter_tests;
+	int32_t n_filter_tests; /* byte-pair tests of the SWAR filter; negative: hashed engine, -(table slots) */
 	int32_t filter_anchor; /* byte of the pattern the SWAR filter is anchored on */
 	int32_t filter_delta;  /* distance to the second filter byte (0: single-byte filter) */
 } gscan_pattern_info;

@@ -70,6 +70,10 @@ def test_engine_selection_and_filter():
     assert G.Pattern("a{2,4}").info["n_sequences"] == 3  # aaaa, aaa, aa (greedy order)
     assert G.Pattern("fo|foo|foobar").info["n_sequences"] == 1  # later alternatives are shadowed by fo
     assert G.Pattern("colou?r").info["n_sequences"] == 2
+    # many alternatives: hashed engine (negative n_filter_tests = -(table slots))
+    import corpus
+    i = G.Pattern(corpus.literals100()).info
+    assert i["engine"] == G.ENGINE_FIXED and i["n_filter_tests"] < 0 and i["minlen"] == 3 and i["maxlen"] == 5
 
 
 @pytest.mark.parametrize("pat,frag", [

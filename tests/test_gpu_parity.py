@@ -83,7 +83,10 @@ def test_kat_all_modes_vs_oracle(ctx, case):
 # ---- seeded differential: random small-alphabet inputs ------------------------------------
 DIFF_PATTERNS = ["ab", "aa", "aba", "abab", "a", "abc|bc|c", "ab|abc", "abc|ab", "a|b", "aab|ab|b", "[ab]{3,}", "[ab]{2}",
                  "a{2,}", "b+", "[^a\\n]{2,}", "a.b", "a..", "(?i)AB", "(?:ab|ba)a", "a[ab]b", "ab{2}", "[a-c]{4,}", "b[^b]b",
-                 "abcabc", "cab|abc|bca", "a{2,3}", "(?:ab){1,2}c", "b?ac", "[ab]c{0,2}a"]
+                 "abcabc", "cab|abc|bca", "a{2,3}", "(?:ab){1,2}c", "b?ac", "[ab]c{0,2}a",
+                 # > 4 distinct leading byte pairs => hashed engine (2- and 3-byte keys, shared prefixes, preference order)
+                 "ab|ba|ca|cb|bc|ac", "aab|aba|abb|baa|bab|bba|cab|cba", "abc|ab|bca|bc|cab|ca|aab|bb", "(?i)ab|ba|ca|cb|bc",
+                 "a[ab]c|b[bc]a|c[ac]b|ab[ab]|ba[bc]", "abca|abcb|bcab|bcaa|cabc|caba|aabb|bbaa|ccaa"]
 
 
 @pytest.mark.parametrize("pat", DIFF_PATTERNS)
@@ -111,7 +114,8 @@ def test_differential_small_alphabet(ctx, pat):
 
 # ---- boundaries: lane (16 B), warp row (512 B), warp slice (2 KiB), tile (32 KiB), unit end ----
 @pytest.mark.parametrize("pat,needle", [("NEEDLE", b"NEEDLE"), ("foo|quux|NEEDLES", b"NEEDLES"), ("[A-Z]{6,}", b"NEEDLE"),
-                                         ("(?i)needle", b"nEeDlE"), ("N.{4}E", b"NEEDLE"), ("Q{20,}", b"Q" * 23)])
+                                         ("(?i)needle", b"nEeDlE"), ("N.{4}E", b"NEEDLE"), ("Q{20,}", b"Q" * 23),
+                                         ("alpha|bravo|charlie|delta|echo|NEEDLE|golf|hotel", b"NEEDLE")])
 def test_boundary_straddles(ctx, pat, needle):
     size = 3 * 32768 + 777
     base = np.full(size, ord("."), dtype=np.uint8)
