@@ -59,8 +59,9 @@ struct FixedParams {
 	const uint32_t *seq_off;  // [nseq] index into seq_pos
 	const uint32_t *seq_pos;  // per position: mask | val << 8 | cls << 16 (cls 0xffff: none)
 	const uint32_t *cls_bm;   // [ncls][8] bitmaps for positions that are not a masked equality
-	// stage 2 (flagged rows only): triples with a third pattern byte at anchor + d2
-	uint32_t n2, d2;
+	// triples (anchor, anchor + delta, anchor + d2): stage 2 of the pair filter (flagged rows only), or --
+	// stage1_triples -- the stage-1 filter itself (Fixed3Engine; sh1/sh2 = 8*delta, 8*d2 funnel-shift amounts)
+	uint32_t n2, d2, stage1_triples, exact3, sh1, sh2;
 	uint32_t t2_m0[16], t2_v0[16], t2_m1[16], t2_v1[16], t2_m2[16], t2_v2[16];
 };
 
@@ -89,6 +90,7 @@ struct RunParams {
 	uint32_t add_ge_lo[8], add_gt_lo[8]; // (0x80-lo)*0x01010101, (0x7f-hi)*0x01010101 for ranges in 0x00-0x7f
 	uint32_t add_ge_hi[2], add_gt_hi[2]; // same for ranges in 0x80-0xff (after clearing bit 7)
 	uint32_t run_min;
+	uint32_t sh[5];      // w &= w >> sh[i], i = 0..4: leaves the bits where min(run_min, 17) ones start (0 = no-op)
 	uint32_t bitmap[8];
 };
 

@@ -159,6 +159,12 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 		if (!pr.delta) F.exact = 0; // single-byte filter: the second term must vanish through its zero mask
 		F.n2 = (uint32_t)pr.triples.size();
 		F.d2 = (uint32_t)pr.delta2;
+		F.stage1_triples = pr.stage1_triples ? 1u : 0u;
+		F.sh1 = 8u * (uint32_t)pr.delta;
+		F.sh2 = 8u * (uint32_t)pr.delta2;
+		F.exact3 = 1;
+		for (int k = 0; k < 16; k++) { F.t2_m0[k] = 0; F.t2_v0[k] = 0xffffffffu; F.t2_m1[k] = 0; F.t2_v1[k] = 0; F.t2_m2[k] = 0; F.t2_v2[k] = 0; }
+		for (auto &t : pr.triples) if (t.m0 != 0xff || t.m1 != 0xff || t.m2 != 0xff) F.exact3 = 0;
 		for (size_t k = 0; k < pr.triples.size(); k++) {
 			F.t2_m0[k] = rep4(pr.triples[k].m0); F.t2_v0[k] = rep4(pr.triples[k].v0);
 			F.t2_m1[k] = rep4(pr.triples[k].m1); F.t2_v1[k] = rep4(pr.triples[k].v1);
@@ -217,6 +223,14 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 			R.add_gt_hi[i] = rep4((uint8_t)(0x7f - (pr.ranges_high[i].hi - 0x80)));
 		}
 		R.run_min = (uint32_t)pr.run_min;
+		{ // AND-with-shift schedule for "at least nf consecutive ones": doubling while 2*len <= nf, then the remainder
+			const uint32_t nf = std::min<uint32_t>((uint32_t)pr.run_min, 17u);
+			uint32_t len = 1;
+			int k = 0;
+			for (int i = 0; i < 5; i++) R.sh[i] = 0;
+			while (len * 2 <= nf) { R.sh[k++] = len; len *= 2; }
+			if (len < nf) R.sh[k++] = nf - len;
+		}
 		for (int i = 0; i < 8; i++) R.bitmap[i] = pr.run_class.w[i];
 	}
 	*out = p;

@@ -764,7 +764,7 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 	// (minlen from the tree equals mn unless shadowing removed the shortest: keep PCRE's figure)
 
 	// ---- choose the SWAR filter: anchor byte + second byte `delta` further on ----
-	double best_score = 1e300;
+	double best_score = 1e300, best_p = 1.0;
 	int best_a = 0, best_d = 0;
 	std::vector<FilterTest> best_tests;
 	for (int d = (mn >= 2 ? 1 : 0); d <= 4; d++) {
@@ -784,7 +784,7 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 			// each test costs ~4 ALU ops per 4 bytes (a distance of exactly one word needs no funnel shift:
 			// ~20 % cheaper); each flagged position costs a slow-path visit
 			double score = (p * 4000.0 + (double)tests.size()) * (d == 4 ? 0.8 : 1.0);
-			if (score < best_score) { best_score = score; best_a = a; best_d = d; best_tests = tests; }
+			if (score < best_score) { best_score = score; best_a = a; best_d = d; best_tests = tests; best_p = p; }
 		}
 		if (mn < 2) break;
 	}
@@ -830,6 +830,11 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 			if (tr.size() <= 16 && p < best_p) { best_p = p; out.triples = tr; out.delta2 = d2; }
 		}
 	}
+
+	// a 4 KiB slice has 8 rows of 512 bytes; once more than a few percent of the rows get flagged the slow path
+	// dominates, and three filter bytes (+2 ops per word) are cheaper than visiting it
+	out.pair_flag_prior = best_p;
+	out.stage1_triples = !out.triples.empty() && out.triples.size() <= 8 && out.delta >= 1 && out.delta <= 3 && best_p * 512.0 > 0.01;
 
 	// ---- can two matches overlap?  If not, the greedy resolve keeps every candidate ----
 	bool disjoint = true;

@@ -150,6 +150,64 @@ struct Emitter {
 // ------------------------------------------------------------------------------------------
 // FIXED engine: alternation of fixed-length byte-class sequences
 // ------------------------------------------------------------------------------------------
+// what a slow path needs to read bytes around a candidate: the slot (shared memory, fast) when the bytes
+// lie inside the resident window, global memory (L2) otherwise
+struct ByteSrc {
+	const uint8_t *stile; // shared-memory address of tile byte 0
+	const uint8_t *gtile; // global address of tile byte 0
+	int lo, hi;           // tile coordinates resident in shared memory: [lo, hi)
+};
+
+// first sequence (in preference order) matching with its anchor byte at tile position p; 0: none
+static __device__ uint32_t fixed_verify(const FixedParams &P, const ByteSrc &B, uint32_t off, uint32_t ulen, int p)
+{
+	const int q = p - (int)P.anchor;              // match start in tile coordinates (may be < 0: previous tile)
+	const long long qu = (long long)off + q;      // ... in unit coordinates
+	if (qu < 0) return 0;
+	const uint8_t *src = (q >= B.lo && q + (int)P.maxlen <= B.hi) ? B.stile : B.gtile;
+	for (uint32_t s = 0; s < P.nseq; s++) {
+		const uint32_t len = P.seq_len[s];
+		if ((unsigned long long)qu + len > ulen) continue;
+		const uint32_t *pp = P.seq_pos + P.seq_off[s];
+		uint32_t i = 0;
+		for (; i < len; i++) {
+			const uint32_t e = pp[i];
+			const uint32_t b = src[q + (int)i];
+			const uint32_t cls = e >> 16;
+			bool ok;
+			if (cls == 0xffffu) ok = (b & (e & 0xffu)) == ((e >> 8) & 0xffu);
+			else ok = (P.cls_bm[cls * 8 + (b >> 5)] >> (b & 31)) & 1u;
+			if (!ok) break;
+		}
+		if (i == len) return len;
+	}
+	return 0;
+}
+
+// rare path shared by the pair and the triple filter: verify the flagged bytes of one row, append in order
+static __device__ __noinline__ uint32_t fixed_slow_row(const FixedParams &P, const uint8_t *stile, const uint8_t *gtile, int lo, int hi,
+                                                       uint32_t off, uint32_t ulen, uint32_t tile_len, Cand *dst, uint32_t lane,
+                                                       uint32_t c0, uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3)
+{
+	const ByteSrc B{stile, gtile, lo, hi};
+	const uint32_t f[4] = {f0 & kHigh, f1 & kHigh, f2 & kHigh, f3 & kHigh};
+	uint32_t mm = 0;
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		uint32_t t = f[j];
+		while (t) {
+			const int byte = (__ffs(t) - 1) >> 3;
+			t &= t - 1;
+			const int p = (int)c0 + j * 4 + byte;
+			if (p < (int)tile_len && fixed_verify(P, B, off, ulen, p)) mm |= 1u << (j * 4 + byte);
+		}
+	}
+	const uint32_t pos0 = off + c0 - P.anchor; // unit offset of a match anchored at chunk byte 0
+	return Emitter::emit_at(dst, mm, pos0, [&](uint32_t b) -> uint32_t {
+		return P.uniform_len ? P.uniform_len : fixed_verify(P, B, off, ulen, (int)(c0 + b));
+	}, lane);
+}
+
 template <int D, int K, bool EX>
 struct FixedEngine {
 	typedef FixedParams Params;
@@ -157,31 +215,6 @@ struct FixedEngine {
 	static __device__ __forceinline__ void prologue(const FixedParams &, uint8_t *) {}
 
 	// first sequence (in preference order) matching with its anchor byte at tile position p; 0: none
-	// reads the unit's bytes from global memory (tile = global address of tile byte 0)
-	static __device__ uint32_t verify(const FixedParams &P, const uint8_t *tile, uint32_t off, uint32_t ulen, int p)
-	{
-		const int q = p - (int)P.anchor;              // match start in tile coordinates (may be < 0: previous tile)
-		const long long qu = (long long)off + q;      // ... in unit coordinates
-		if (qu < 0) return 0;
-		for (uint32_t s = 0; s < P.nseq; s++) {
-			const uint32_t len = P.seq_len[s];
-			if ((unsigned long long)qu + len > ulen) continue;
-			const uint32_t *pp = P.seq_pos + P.seq_off[s];
-			uint32_t i = 0;
-			for (; i < len; i++) {
-				const uint32_t e = pp[i];
-				const uint32_t b = tile[q + (int)i];
-				const uint32_t cls = e >> 16;
-				bool ok;
-				if (cls == 0xffffu) ok = (b & (e & 0xffu)) == ((e >> 8) & 0xffu);
-				else ok = (P.cls_bm[cls * 8 + (b >> 5)] >> (b & 31)) & 1u;
-				if (!ok) break;
-			}
-			if (i == len) return len;
-		}
-		return 0;
-	}
-
 	// Stage-1 SWAR filter of one word pair: bit 7 of a byte of the result set (superset) where some test
 	// passes at that byte.  EX: every mask is 0xff, two LOP3 per test instead of three.  The decrement of
 	// the zero-byte trick is written t * one + 0xfefefeff (one == 1, opaque to the compiler) so that it
@@ -212,45 +245,32 @@ struct FixedEngine {
 	}
 
 	// Rare path for one flagged 512-byte row (warp-converged).  Stage 2 first narrows the flags with a
-	// third pattern byte (SWAR again, a handful of ops), only then are the survivors verified byte by
-	// byte (global memory / L2), in preference order, and appended in position order.
-	static __device__ __noinline__ uint32_t slow_row(const FixedParams &P, const uint8_t *tile, uint32_t off, uint32_t ulen,
-	                                                 uint32_t tile_len, Cand *dst, uint32_t lane, uint32_t c0,
+	// third pattern byte (SWAR again), only then are the survivors verified byte by byte.
+	static __device__ __noinline__ uint32_t slow_row(const FixedParams &P, const uint8_t *stile, const uint8_t *gtile, int lo, int hi,
+	                                                 uint32_t off, uint32_t ulen, uint32_t tile_len, Cand *dst, uint32_t lane, uint32_t c0,
 	                                                 uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4)
 	{
 		const uint32_t w[5] = {w0, w1, w2, w3, w4};
 		uint32_t f[4];
 #pragma unroll
-		for (int j = 0; j < 4; j++) {
-			const uint32_t s1 = second(w[j], w[j + 1]);
-			if (P.n2) {
-				const uint32_t s2 = __funnelshift_r(w[j], w[j + 1], 8 * P.d2);
-				uint32_t g = 0;
-				for (uint32_t k = 0; k < P.n2; k++) {
-					const uint32_t t = ((w[j] & P.t2_m0[k]) ^ P.t2_v0[k]) | ((s1 & P.t2_m1[k]) ^ P.t2_v1[k]) | ((s2 & P.t2_m2[k]) ^ P.t2_v2[k]);
-					g |= (t - kOnes) & ~t;
+		for (int j = 0; j < 4; j++) f[j] = word_flags(P, w[j], second(w[j], w[j + 1])) & kHigh;
+		for (uint32_t k = 0; P.n2 && k < 1; k++) { // stage 2 (one pass; the loop only scopes the constants)
+			uint32_t g[4] = {0, 0, 0, 0};
+			for (uint32_t t3 = 0; t3 < P.n2; t3++) {
+				const uint32_t m0 = P.t2_m0[t3], v0 = P.t2_v0[t3], m1 = P.t2_m1[t3], v1 = P.t2_v1[t3], m2 = P.t2_m2[t3], v2 = P.t2_v2[t3];
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const uint32_t s1 = second(w[j], w[j + 1]);
+					const uint32_t s2 = __funnelshift_r(w[j], w[j + 1], 8 * P.d2);
+					const uint32_t t = ((w[j] & m0) ^ v0) | ((s1 & m1) ^ v1) | ((s2 & m2) ^ v2);
+					g[j] |= (t - kOnes) & ~t;
 				}
-				f[j] = g & kHigh;
-			} else {
-				f[j] = word_flags(P, w[j], s1) & kHigh;
 			}
+#pragma unroll
+			for (int j = 0; j < 4; j++) f[j] &= g[j];
 		}
 		if (!__any_sync(0xffffffffu, (f[0] | f[1] | f[2] | f[3]) != 0)) return 0;
-		uint32_t mm = 0;
-#pragma unroll
-		for (int j = 0; j < 4; j++) {
-			uint32_t t = f[j];
-			while (t) {
-				const int byte = (__ffs(t) - 1) >> 3;
-				t &= t - 1;
-				const int p = (int)c0 + j * 4 + byte;
-				if (p < (int)tile_len && verify(P, tile, off, ulen, p)) mm |= 1u << (j * 4 + byte);
-			}
-		}
-		const uint32_t pos0 = off + c0 - P.anchor; // unit offset of a match anchored at chunk byte 0
-		return Emitter::emit_at(dst, mm, pos0, [&](uint32_t b) -> uint32_t {
-			return P.uniform_len ? P.uniform_len : verify(P, tile, off, ulen, (int)(c0 + b));
-		}, lane);
+		return fixed_slow_row(P, stile, gtile, lo, hi, off, ulen, tile_len, dst, lane, c0, f[0], f[1], f[2], f[3]);
 	}
 
 	// lane's 16 bytes + the 4 bytes after them (next lane's / next row's first word; after the last chunk of the
@@ -283,8 +303,8 @@ struct FixedEngine {
 #pragma unroll
 					for (int r = 0; r < kGroup; r++) {
 						if (__any_sync(0xffffffffu, (ra[r] & kHigh) != 0))
-							E.n += slow_row(P, S.gtile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, base + (g0 + r) * 512,
-							                w[r][0], w[r][1], w[r][2], w[r][3], w[r][4]);
+							E.n += slow_row(P, S.tile, S.gtile, (int)S.begin, (int)(S.begin + S.niter * 512 + (D ? kHalo : 0u)), S.off, S.ulen, S.tile_len,
+							                E.scratch + E.n, lane, base + (g0 + r) * 512, w[r][0], w[r][1], w[r][2], w[r][3], w[r][4]);
 					}
 				}
 			}
@@ -294,7 +314,60 @@ struct FixedEngine {
 			uint32_t w[5];
 			load_row(S, base + it * 512, w);
 			if (__any_sync(0xffffffffu, (row_any(P, w) & kHigh) != 0))
-				E.n += slow_row(P, S.gtile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, base + it * 512, w[0], w[1], w[2], w[3], w[4]);
+				E.n += slow_row(P, S.tile, S.gtile, (int)S.begin, (int)(S.begin + S.niter * 512 + (D ? kHalo : 0u)), S.off, S.ulen, S.tile_len,
+				                E.scratch + E.n, lane, base + it * 512, w[0], w[1], w[2], w[3], w[4]);
+		}
+	}
+};
+
+// ------------------------------------------------------------------------------------------
+// FIXED engine, triple filter: when the best byte pair would flag too many rows (short or
+// case-insensitive patterns, several alternatives) stage 1 tests three pattern bytes (anchor, anchor + d1,
+// anchor + d2, all within one word of each other) -- 2 funnel shifts and 4 ops per test and word, and the
+// slow path is entered ~100x less often.
+// ------------------------------------------------------------------------------------------
+template <int K, bool EX>
+struct Fixed3Engine {
+	typedef FixedParams Params;
+	static constexpr bool kLookBehind = false, kLookAhead = true;
+	static __device__ __forceinline__ void prologue(const FixedParams &, uint8_t *) {}
+
+	static __device__ __forceinline__ uint32_t word_flags(const FixedParams &P, uint32_t w, uint32_t s1, uint32_t s2)
+	{
+		uint32_t f = 0;
+#pragma unroll
+		for (int k = 0; k < K; k++) {
+			const uint32_t t = EX ? ((w ^ P.t2_v0[k]) | (s1 ^ P.t2_v1[k]) | (s2 ^ P.t2_v2[k]))
+			                      : (((w & P.t2_m0[k]) ^ P.t2_v0[k]) | ((s1 & P.t2_m1[k]) ^ P.t2_v1[k]) | ((s2 & P.t2_m2[k]) ^ P.t2_v2[k]));
+			f |= (t * P.one + 0xfefefeffu) & ~t;
+		}
+		return f;
+	}
+	static __device__ __forceinline__ uint32_t row_any(const FixedParams &P, const uint32_t (&w)[5], uint32_t (&f)[4])
+	{
+		uint32_t acc = 0;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			f[j] = word_flags(P, w[j], __funnelshift_r(w[j], w[j + 1], P.sh1), __funnelshift_r(w[j], w[j + 1], P.sh2));
+			acc |= f[j];
+		}
+		return acc;
+	}
+
+	template <class G>
+	static __device__ __forceinline__ void run(const FixedParams &P, const Slice &S, Emitter &E, uint32_t lane)
+	{
+		const uint32_t base = S.begin + lane * 16;
+#pragma unroll 2
+		for (uint32_t it = 0; it < S.niter; it++) {
+			const uint32_t c0 = base + it * 512;
+			uint32_t w[5], f[4];
+			const uint4 a = *reinterpret_cast<const uint4 *>(S.tile + c0);
+			w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+			w[4] = *reinterpret_cast<const uint32_t *>(S.tile + c0 + 16);
+			if (__any_sync(0xffffffffu, (row_any(P, w, f) & kHigh) != 0))
+				E.n += fixed_slow_row(P, S.tile, S.gtile, (int)S.begin, (int)(S.begin + S.niter * 512 + kHalo), S.off, S.ulen, S.tile_len,
+				                      E.scratch + E.n, lane, c0, f[0], f[1], f[2], f[3]);
 		}
 	}
 };
@@ -448,14 +521,94 @@ struct RunEngine {
 		return r & valid; // the tail of the last 16-byte granule of a unit is whatever follows it in memory
 	}
 
+	// class mask of 16 bytes that are known to lie inside the unit
+	static __device__ __forceinline__ uint32_t mask16_inner(const RunParams &P, const uint8_t *p)
+	{
+		const uint4 a = *reinterpret_cast<const uint4 *>(p);
+		uint32_t r = pack_top_nibble(class_flags(P, a.w)) >> 28;
+		r = __funnelshift_l(pack_top_nibble(class_flags(P, a.z)), r, 4);
+		r = __funnelshift_l(pack_top_nibble(class_flags(P, a.y)), r, 4);
+		return __funnelshift_l(pack_top_nibble(class_flags(P, a.x)), r, 4);
+	}
+
+	// positions whose bit and the following run_min-1 bits are set (window: own 16 bits + next 16): five
+	// AND-with-shift steps whose shift amounts the host derived from run_min (doubling, then the remainder)
+	static __device__ __forceinline__ uint32_t runs(const RunParams &P, uint32_t w)
+	{
+#pragma unroll
+		for (int i = 0; i < 5; i++) w &= w >> P.sh[i];
+		return w;
+	}
+
+	// candidates of one row -> private list, in position order.  Common case (every lane has at most one):
+	// rank by ballot; otherwise the general prefix sum.
+	static __device__ __forceinline__ void emit_row(const RunParams &P, const Slice &S, Emitter &E, uint32_t lane, uint32_t cand, uint32_t c0)
+	{
+		if (P.run_min > 17u) {
+			// long minimum: confirm bytes 17..n-1 (global memory: they may lie in another warp's slice)
+			uint32_t keep = 0, t = cand;
+			while (t) {
+				const uint32_t b = __ffs(t) - 1;
+				t &= t - 1;
+				const uint32_t p = c0 + b;
+				bool ok = (unsigned long long)S.off + p + P.run_min <= S.ulen;
+				for (uint32_t i = 17; ok && i < P.run_min; i++) ok = in_class(P, S.gtile[p + i]);
+				if (ok) keep |= 1u << b;
+			}
+			cand = keep;
+		}
+		if (!__any_sync(0xffffffffu, (cand & (cand - 1)) != 0)) {
+			const uint32_t has = __ballot_sync(0xffffffffu, cand != 0);
+			if (cand) {
+				Cand c;
+				c.pos = S.off + c0 + (__ffs(cand) - 1);
+				c.len = 0;
+				E.scratch[E.n + __popc(has & ((1u << lane) - 1u))] = c;
+			}
+			E.n += __popc(has);
+		} else {
+			E.n += Emitter::emit_at(E.scratch + E.n, cand, S.off + c0, [](uint32_t) -> uint32_t { return 0u; }, lane);
+		}
+	}
+
 	template <class G>
 	static __device__ __forceinline__ void run(const RunParams &P, const Slice &S, Emitter &E, uint32_t lane)
 	{
+		constexpr int kRows = G::kSlice / 512;
 		if (S.niter == 0) return;
-		const uint32_t nf = P.run_min < 17u ? P.run_min : 17u;
 		// is the byte just before the slice in the class?  (the unit's first byte has no predecessor)
 		uint32_t prevbit = 0;
 		if (S.off + S.begin > 0) prevbit = in_class(P, S.tile[(int)S.begin - 1]); // 16-byte look-behind copy
+		const uint32_t send = S.begin + S.niter * 512;
+		if (S.niter == (uint32_t)kRows && (unsigned long long)S.off + send + 16 <= S.ulen) {
+			// ---- full slice strictly inside the unit: no validity masks, everything in registers ----
+			uint32_t cm[kRows + 1];
+#pragma unroll
+			for (int r = 0; r < kRows; r++) cm[r] = mask16_inner(P, S.tile + S.begin + r * 512 + lane * 16);
+			{ // the 16 bytes after the slice: lanes 0..3 classify one word each of the look-ahead copy
+				const uint32_t x = *reinterpret_cast<const uint32_t *>(S.tile + send + (lane & 3) * 4);
+				uint32_t nib = (pack_top_nibble(class_flags(P, x)) >> 28) << ((lane & 3) * 4);
+				nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
+				nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
+				cm[kRows] = nib; // correct in lanes 0..3; only lane 0's copy is consumed (by lane 31)
+			}
+			const uint32_t nxt_lane = (lane + 1) & 31, prv_lane = (lane + 31) & 31;
+#pragma unroll
+			for (int r = 0; r < kRows; r++) {
+				// one shuffle brings the next lane's mask of this row and (for lane 31) lane 0's mask of the next row
+				const uint32_t v = __shfl_sync(0xffffffffu, cm[r] | (cm[r + 1] << 16), nxt_lane);
+				const uint32_t nx = lane == 31 ? v >> 16 : v & 0xffffu;
+				// one shuffle brings the previous lane's last bit and (for lane 0) lane 31's last bit of the previous row
+				const uint32_t below = r ? cm[r - 1] : prevbit << 15;
+				const uint32_t u = __shfl_sync(0xffffffffu, cm[r] | (below << 16), prv_lane);
+				const uint32_t pv = lane == 0 ? u >> 31 : (u >> 15) & 1u;
+				const uint32_t starts = cm[r] & ~((cm[r] << 1) | pv);
+				const uint32_t cand = starts & runs(P, cm[r] | (nx << 16)) & 0xffffu;
+				if (__any_sync(0xffffffffu, cand != 0)) emit_row(P, S, E, lane, cand, S.begin + r * 512 + lane * 16);
+			}
+			return;
+		}
+		// ---- slices at the end of a unit / short tiles: same logic with per-byte validity ----
 		uint32_t cm_next = mask16(P, S, S.begin + lane * 16);
 		for (uint32_t it = 0; it < S.niter; it++) {
 			const uint32_t c0 = S.begin + it * 512 + lane * 16;
@@ -463,11 +616,9 @@ struct RunEngine {
 			if (it + 1 < S.niter) {
 				cm_next = mask16(P, S, c0 + 512);
 			} else {
-				// the 16 bytes after this slice (another warp's slice, or past the unit end): lanes 0..3 each
-				// classify one word of the look-ahead copy, lane 0 assembles the mask
-				const uint32_t cb = S.begin + S.niter * 512 + (lane & 3) * 4;
-				const long long rem = (long long)S.ulen - (long long)S.off - (long long)(S.begin + S.niter * 512);
-				const uint32_t x = *reinterpret_cast<const uint32_t *>(S.tile + cb); // 16-byte look-ahead copy (masked by `valid`)
+				const uint32_t cb = send + (lane & 3) * 4;
+				const long long rem = (long long)S.ulen - (long long)S.off - (long long)send;
+				const uint32_t x = *reinterpret_cast<const uint32_t *>(S.tile + cb); // look-ahead copy (masked by `valid`)
 				uint32_t nib = (pack_top_nibble(class_flags(P, x)) >> 28) << ((lane & 3) * 4);
 				nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
 				nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
@@ -481,24 +632,8 @@ struct RunEngine {
 			if (lane == 0) pv = prevbit;
 			prevbit = __shfl_sync(0xffffffffu, cm, 31) >> 15;
 			const uint32_t starts = cm & ~((cm << 1) | pv);
-			uint32_t cand = starts & runs_at_least(cm | (nx << 16), nf) & 0xffffu;
-			if (__any_sync(0xffffffffu, cand != 0)) {
-				if (P.run_min > 17u) {
-					// long minimum: confirm bytes 17..n-1 from shared memory (post-halo covers n)
-					uint32_t keep = 0;
-					uint32_t t = cand;
-					while (t) {
-						const uint32_t b = __ffs(t) - 1;
-						t &= t - 1;
-						const uint32_t p = c0 + b;
-						bool ok = (unsigned long long)S.off + p + P.run_min <= S.ulen;
-						for (uint32_t i = 17; ok && i < P.run_min; i++) ok = in_class(P, S.gtile[p + i]);
-						if (ok) keep |= 1u << b;
-					}
-					cand = keep;
-				}
-				E.n += Emitter::emit_at(E.scratch + E.n, cand, S.off + c0, [](uint32_t) -> uint32_t { return 0u; }, lane);
-			}
+			const uint32_t cand = starts & runs(P, cm | (nx << 16)) & 0xffffu;
+			if (__any_sync(0xffffffffu, cand != 0)) emit_row(P, S, E, lane, cand, c0);
 		}
 	}
 };
@@ -643,7 +778,7 @@ static cudaError_t launch(const ScanArgs &A, const typename Eng::Params &P, cons
 ScanGeom scan_geom(int engine, uint32_t n_tests_or_ranges)
 {
 	if (engine == 4 /*FIXED, hashed*/) return ScanGeom{GeomHash::kWarps, GeomHash::kRing, GeomHash::kSlice};
-	if (engine == 1 /*FIXED*/ && n_tests_or_ranges <= 1) return ScanGeom{GeomStream::kWarps, GeomStream::kRing, GeomStream::kSlice};
+	if (engine == 1 /*FIXED*/) return ScanGeom{GeomStream::kWarps, GeomStream::kRing, GeomStream::kSlice};
 	return ScanGeom{GeomBalanced::kWarps, GeomBalanced::kRing, GeomBalanced::kSlice};
 }
 
@@ -652,6 +787,19 @@ cudaError_t launch_scan_null(const ScanArgs &A, int geom, int grid, cudaStream_t
 	NullParams P{0};
 	if (geom == 0) return launch_g<NullEngine, GeomStream>(A, P, grid, st);
 	return launch_g<NullEngine, GeomBalanced>(A, P, grid, st);
+}
+
+template <bool EX>
+static cudaError_t launch_fixed3(const ScanArgs &A, const FixedParams &P, const ScanGeom &g, int grid, cudaStream_t st)
+{
+	switch (P.n2) {
+	case 1: return launch<Fixed3Engine<1, EX>, true>(A, P, g, grid, st);
+	case 2: return launch<Fixed3Engine<2, EX>, true>(A, P, g, grid, st);
+	case 3: return launch<Fixed3Engine<3, EX>, true>(A, P, g, grid, st);
+	case 4: return launch<Fixed3Engine<4, EX>, true>(A, P, g, grid, st);
+	case 5: case 6: return launch<Fixed3Engine<6, EX>, true>(A, P, g, grid, st);
+	default: return launch<Fixed3Engine<8, EX>, true>(A, P, g, grid, st);
+	}
 }
 
 cudaError_t launch_scan_hash(const ScanArgs &A, const HashParams &P, int grid, cudaStream_t st)
@@ -664,16 +812,17 @@ static cudaError_t launch_fixed_de(const ScanArgs &A, const FixedParams &P, cons
 {
 	switch (P.ntests) {
 	case 1: return launch<FixedEngine<D, 1, EX>, true>(A, P, g, grid, st);
-	case 2: return launch<FixedEngine<D, 2, EX>, false>(A, P, g, grid, st);
-	case 3: return launch<FixedEngine<D, 3, EX>, false>(A, P, g, grid, st);
-	case 4: return launch<FixedEngine<D, 4, EX>, false>(A, P, g, grid, st);
-	case 5: case 6: return launch<FixedEngine<D, 6, EX>, false>(A, P, g, grid, st);
-	default: return launch<FixedEngine<D, 8, EX>, false>(A, P, g, grid, st);
+	case 2: return launch<FixedEngine<D, 2, EX>, true>(A, P, g, grid, st);
+	case 3: return launch<FixedEngine<D, 3, EX>, true>(A, P, g, grid, st);
+	case 4: return launch<FixedEngine<D, 4, EX>, true>(A, P, g, grid, st);
+	case 5: case 6: return launch<FixedEngine<D, 6, EX>, true>(A, P, g, grid, st);
+	default: return launch<FixedEngine<D, 8, EX>, true>(A, P, g, grid, st);
 	}
 }
 
 cudaError_t launch_scan_fixed(const ScanArgs &A, const FixedParams &P, int delta, const ScanGeom &g, int grid, cudaStream_t st)
 {
+	if (P.stage1_triples) return P.exact3 ? launch_fixed3<true>(A, P, g, grid, st) : launch_fixed3<false>(A, P, g, grid, st);
 	const bool ex = P.exact != 0;
 	switch (delta) {
 	case 0: return ex ? launch_fixed_de<0, true>(A, P, g, grid, st) : launch_fixed_de<0, false>(A, P, g, grid, st);
