@@ -38,7 +38,8 @@ static_assert(sizeof(TileDesc) == 32, "TileDesc layout");
 
 // One segment == one slice; candidates of a segment are contiguous and ordered in the candidate
 // buffer.  seg id = tile * slices_per_tile + slice.
-struct SegEntry { uint32_t base, n; };
+struct SegEntry { uint32_t base, n; }; // n: low 16 bits count (<= slice bytes), high 16 bits generation tag of the scan that wrote it
+__host__ __device__ inline uint32_t seg_count(const SegEntry &e, uint32_t tag) { return (e.n >> 16) == tag ? (e.n & 0xffffu) : 0u; }
 
 // A candidate / match inside a unit.
 struct Cand { uint32_t pos, len; };
@@ -103,6 +104,7 @@ struct ScanArgs {
 	SegEntry *segs;
 	Cand *scratch;  // [gridDim.x * warps][slice bytes]: one private list per warp
 	uint32_t extra_smem; // bytes of engine-private shared memory behind the rings (hash table)
+	uint32_t tag;        // generation of this scan (1..65535), stored in the segment entries it writes
 };
 
 } // namespace gscan

@@ -90,6 +90,7 @@ struct gscan_ctx {
 	gscan_stats stats;
 
 	DevBuf<SegEntry> segs;
+	uint32_t seg_tag = 0;      // generation of the last scan that wrote segs (0: table freshly zeroed)
 	DevBuf<Cand> cand;
 	DevBuf<Cand> scratch;
 	DevBuf<OutRec> ord;
@@ -461,6 +462,20 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 	return 0;
 }
 
+// the segment table is never cleared between scans: entries carry a 16-bit generation tag.  It is zeroed (with
+// plain stores) when it is (re)allocated and when the tag wraps.
+static int ensure_segs(gscan_ctx *ctx, uint32_t n_segs)
+{
+	const size_t before = ctx->segs.cap;
+	CK(ctx, ctx->segs.ensure(n_segs));
+	if (ctx->segs.cap != before || ctx->seg_tag >= 0xfffeu) {
+		CK(ctx, launch_fill_u32(reinterpret_cast<uint32_t *>(ctx->segs.p), ctx->segs.cap * 2, 0u, ctx->stream));
+		ctx->seg_tag = 0;
+	}
+	ctx->seg_tag++;
+	return 0;
+}
+
 static int ensure_pattern(gscan_ctx *ctx, const gscan_pattern *pat)
 {
 	if (ctx->pat_id == pat->prog.id) return 0;
@@ -531,7 +546,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	const uint32_t spt = (uint32_t)(kTileBytes / geom.slice);
 	const uint32_t n_segs = b->n_tiles * spt;
 	const int grid = (int)std::min<uint32_t>((uint32_t)ctx->num_sms, b->n_tiles);
-	CK(ctx, ctx->segs.ensure(n_segs));
+	if (ensure_segs(ctx, n_segs) < 0) return -1;
 	CK(ctx, ctx->scratch.ensure((size_t)ctx->num_sms * geom.warps * geom.slice));
 	CK(ctx, ctx->cursor.ensure(2));
 	CK(ctx, ctx->readback.ensure(64));
@@ -547,15 +562,15 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	A.segs = ctx->segs.p;
 	A.scratch = ctx->scratch.p;
 	A.extra_smem = hashed ? pat->prog.hash_slots * 4u : 0u;
+	A.tag = ctx->seg_tag;
 
 	unsigned long long *h_cursor = reinterpret_cast<unsigned long long *>(ctx->readback.p);
 	unsigned long long total_cand = 0;
 	for (int attempt = 0;; attempt++) {
 		A.cand = ctx->cand.p;
 		A.cand_cap = (uint32_t)std::min<size_t>(ctx->cand.cap, 0xffffffffu);
-		CK(ctx, cudaMemsetAsync(ctx->cursor.p, 0, 16, ctx->stream));
+		CK(ctx, launch_fill_u32(reinterpret_cast<uint32_t *>(ctx->cursor.p), 4, 0u, ctx->stream));
 		CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-		CK(ctx, cudaMemsetAsync(ctx->segs.p, 0, (size_t)n_segs * sizeof(SegEntry), ctx->stream)); // inside the timed region
 		if (hashed) CK(ctx, launch_scan_hash(A, ctx->pat_hash, grid, ctx->stream));
 		else if (pat->prog.kind == ENGINE_FIXED) CK(ctx, launch_scan_fixed(A, ctx->pat_fixed, pat->prog.delta, geom, grid, ctx->stream));
 		else CK(ctx, launch_scan_run(A, pat->run, geom, grid, ctx->stream));
@@ -590,6 +605,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		R.segs = ctx->segs.p;
 		R.n_segs = n_segs;
 		R.slices_per_tile = spt;
+		R.tag = ctx->seg_tag;
 		R.cand = ctx->cand.p;
 		R.units = b->d_units;
 		R.n_units = b->n_units;
@@ -737,14 +753,14 @@ extern "C" int gscan_tma_probe(gscan_ctx *ctx, gscan_batch *b, int geom, float *
 	const ScanGeom g = geom == 0 ? ScanGeom{GeomStream::kWarps, GeomStream::kRing, GeomStream::kSlice}
 	                             : ScanGeom{GeomBalanced::kWarps, GeomBalanced::kRing, GeomBalanced::kSlice};
 	const uint32_t n_segs = b->n_tiles * (uint32_t)(kTileBytes / g.slice);
-	CK(ctx, ctx->segs.ensure(n_segs));
+	if (ensure_segs(ctx, n_segs) < 0) return -1;
 	CK(ctx, ctx->scratch.ensure((size_t)ctx->num_sms * g.warps * g.slice));
 	CK(ctx, ctx->cursor.ensure(2));
 	if (ctx->cand.cap == 0) CK(ctx, ctx->cand.ensure(1u << 20));
 	ScanArgs A;
 	A.tiles = b->d_tiles; A.n_tiles = b->n_tiles; A.cand = ctx->cand.p; A.cand_cap = (uint32_t)ctx->cand.cap;
-	A.cursor = ctx->cursor.p; A.segs = ctx->segs.p; A.scratch = ctx->scratch.p; A.extra_smem = 0;
-	CK(ctx, cudaMemsetAsync(ctx->cursor.p, 0, 16, ctx->stream));
+	A.cursor = ctx->cursor.p; A.segs = ctx->segs.p; A.scratch = ctx->scratch.p; A.extra_smem = 0; A.tag = ctx->seg_tag;
+	CK(ctx, launch_fill_u32(reinterpret_cast<uint32_t *>(ctx->cursor.p), 4, 0u, ctx->stream));
 	CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
 	CK(ctx, launch_scan_null(A, geom, (int)std::min<uint32_t>((uint32_t)ctx->num_sms, b->n_tiles), ctx->stream));
 	CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));

@@ -36,6 +36,7 @@ struct ResolveArgs {
 	const SegEntry *segs;
 	uint32_t n_segs;
 	uint32_t slices_per_tile;
+	uint32_t tag;         // generation of the scan that filled segs
 	const Cand *cand;
 	const DevUnit *units;
 	uint32_t n_units;
@@ -57,6 +58,7 @@ cudaError_t launch_resolve_write(const ResolveArgs &R, cudaStream_t st, uint32_t
 cudaError_t launch_synth_corpus(uint8_t *dptr, uint64_t seed, uint64_t first_file_id, uint64_t n_files, uint64_t file_len,
                                 uint64_t stride, const uint8_t *d_needle, uint32_t needle_len, uint32_t needle_every,
                                 cudaStream_t st);
+cudaError_t launch_fill_u32(uint32_t *p, size_t n, uint32_t v, cudaStream_t st);
 cudaError_t launch_read_probe(const void *dptr, uint64_t bytes, unsigned long long *d_sum, int grid, cudaStream_t st);
 
 } // namespace gscan

@@ -54,13 +54,13 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
 }
 
 // ---- 1. segment counts -> block sums ----
-__global__ void k_seg_sums(const SegEntry *segs, uint32_t n_segs, uint32_t *blk)
+__global__ void k_seg_sums(const SegEntry *segs, uint32_t n_segs, uint32_t tag, uint32_t *blk)
 {
 	const uint32_t base = blockIdx.x * kPerBlock + threadIdx.x * kPerThread;
 	uint32_t s = 0;
 #pragma unroll
 	for (int i = 0; i < kPerThread; i++)
-		if (base + i < n_segs) s += segs[base + i].n;
+		if (base + i < n_segs) s += seg_count(segs[base + i], tag);
 	uint32_t total;
 	block_exclusive_scan(s, &total);
 	if (threadIdx.x == 0) blk[blockIdx.x] = total;
@@ -97,7 +97,7 @@ __global__ void k_gather(const ResolveArgs R)
 	uint32_t s = 0;
 #pragma unroll
 	for (int i = 0; i < kPerThread; i++) {
-		cnt[i] = base + i < R.n_segs ? R.segs[base + i].n : 0u;
+		cnt[i] = base + i < R.n_segs ? seg_count(R.segs[base + i], R.tag) : 0u;
 		s += cnt[i];
 	}
 	uint32_t total;
@@ -209,7 +209,7 @@ cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t
 {
 	uint32_t nl = 0;
 	const uint32_t nb_seg = (R.n_segs + kPerBlock - 1) / kPerBlock;
-	k_seg_sums<<<nb_seg, kScanBlock, 0, st>>>(R.segs, R.n_segs, R.blk); nl++;
+	k_seg_sums<<<nb_seg, kScanBlock, 0, st>>>(R.segs, R.n_segs, R.tag, R.blk); nl++;
 	k_scan_blk<<<1, kScanBlock, 0, st>>>(R.blk, nb_seg, R.totals, R.unit_start + R.n_units); nl++;
 	k_gather<<<nb_seg, kScanBlock, 0, st>>>(R); nl++;
 	k_walk<false><<<(R.n_units + 127) / 128, 128, 0, st>>>(R); nl++;

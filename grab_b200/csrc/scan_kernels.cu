@@ -60,12 +60,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 	    "r"(parity)
 	    : "memory");
 }
-// global -> shared bulk copy executed by the TMA unit; bytes and both addresses multiples of 16
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+// L2 eviction policy for the corpus stream: every byte is read exactly once, so its lines are the first to go.
+// Without it the stream (126 MB of L2 turn over every ~18 us) evicts the rarely executed slow-path code and the
+// pattern tables from L2, and a warp that finally hits a match fetches its instructions from DRAM one line at a
+// time (measured: +0.5 ms per 32 GiB scan with one match every 64 MiB).
+#ifndef GS_L2_POLICY
+#define GS_L2_POLICY 0
+#endif
+__device__ __forceinline__ uint64_t l2_stream_policy()
 {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+	uint64_t p;
+#if GS_L2_POLICY == 1
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+#elif GS_L2_POLICY == 2
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 0.5;" : "=l"(p));
+#else
+	asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+#endif
+	return p;
+}
+// global -> shared bulk copy executed by the TMA unit; bytes and both addresses multiples of 16
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
 	                 smem_u32(smem_dst)),
-	             "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+	             "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
 	             : "memory");
 }
 
@@ -142,7 +161,9 @@ struct Emitter {
 			}
 			// else: the host sees cursor > cand_cap, grows the buffer and re-runs the scan
 		}
-		if (n && lane == 0) A.segs[seg] = SegEntry{base, n}; // empty segments stay {0,0}: the table is zeroed before the launch
+		// only non-empty segments are written; the entry carries this scan's generation tag, so stale entries of
+		// earlier scans read as empty and the table never has to be cleared between scans
+		if (n && lane == 0) A.segs[seg] = SegEntry{base, n | (A.tag << 16)};
 		n = 0;
 	}
 };
@@ -159,7 +180,7 @@ struct ByteSrc {
 };
 
 // first sequence (in preference order) matching with its anchor byte at tile position p; 0: none
-static __device__ uint32_t fixed_verify(const FixedParams &P, const ByteSrc &B, uint32_t off, uint32_t ulen, int p)
+static __device__ __noinline__ uint32_t fixed_verify(const FixedParams &P, const ByteSrc &B, uint32_t off, uint32_t ulen, int p)
 {
 	const int q = p - (int)P.anchor;              // match start in tile coordinates (may be < 0: previous tile)
 	const long long qu = (long long)off + q;      // ... in unit coordinates
@@ -291,7 +312,7 @@ struct FixedEngine {
 		if (S.niter == (uint32_t)kRows) {
 			// full slice: groups of 4 rows -- all 8 loads of a group first, one vote per group
 			constexpr int kGroup = 4;
-#pragma unroll
+#pragma unroll 1
 			for (int g0 = 0; g0 < kRows; g0 += kGroup) {
 				uint32_t w[kGroup][5];
 #pragma unroll
@@ -390,7 +411,7 @@ struct HashEngine {
 	}
 
 	// first alternative (preference order) with this key that matches at tile position p; 0: none
-	static __device__ uint32_t verify(const HashParams &P, const uint8_t *tile, uint32_t off, uint32_t ulen, int p, uint32_t slot)
+	static __device__ __noinline__ uint32_t verify(const HashParams &P, const uint8_t *tile, uint32_t off, uint32_t ulen, int p, uint32_t slot)
 	{
 		const unsigned long long qu = (unsigned long long)off + (unsigned)p;
 		const uint32_t first = P.slot_first[slot], cnt = P.slot_count[slot];
@@ -441,21 +462,24 @@ struct HashEngine {
 	{
 		const uint32_t w[5] = {w0, w1, w2, w3, w4};
 		uint32_t mm = 0;
+		uint32_t hits = 0; // positions whose leading bytes are a key of the set (unrolled: straight-line, no divergence yet)
 #pragma unroll
-		for (int j = 0; j < 4; j++) {
-#pragma unroll
-			for (int k = 0; k < 4; k++) {
-				const uint32_t y = key_at(P, w[j], w[j + 1], k);
-				const uint32_t so = __umulhi(y, P.mul) & P.slot_mask;
-				const uint32_t e = *reinterpret_cast<const uint32_t *>(tbl + so);
-				const int p = (int)c0 + j * 4 + k;
-				if (e == y && p < (int)tile_len && verify(P, gtile, off, ulen, p, so >> 2)) mm |= 1u << (j * 4 + k);
-			}
+		for (int b = 0; b < 16; b++) {
+			const uint32_t y = key_at(P, w[b >> 2], w[(b >> 2) + 1], b & 3);
+			const uint32_t e = *reinterpret_cast<const uint32_t *>(tbl + (__umulhi(y, P.mul) & P.slot_mask));
+			hits |= (e == y ? 1u : 0u) << b;
+		}
+		while (hits) { // verify() is out of line: one copy, the kernel stays instruction-cache resident
+			const int b = __ffs(hits) - 1;
+			hits &= hits - 1;
+			const uint32_t y = __funnelshift_r(w[b >> 2], w[(b >> 2) + 1], 8 * (b & 3)) & P.key_mask;
+			const int p = (int)c0 + b;
+			if (p < (int)tile_len && verify(P, gtile, off, ulen, p, (__umulhi(y, P.mul) & P.slot_mask) >> 2)) mm |= 1u << b;
 		}
 		return Emitter::emit_at(dst, mm, off + c0, [&](uint32_t b) -> uint32_t {
 			if (P.uniform_len) return P.uniform_len;
 			const int j = (int)b >> 2, k = (int)b & 3;
-			const uint32_t y = key_at(P, w[j], w[j + 1], k);
+			const uint32_t y = __funnelshift_r(w[j], w[j + 1], 8 * k) & P.key_mask;
 			return verify(P, gtile, off, ulen, (int)(c0 + b), (__umulhi(y, P.mul) & P.slot_mask) >> 2);
 		}, lane);
 	}
@@ -542,7 +566,9 @@ struct RunEngine {
 
 	// candidates of one row -> private list, in position order.  Common case (every lane has at most one):
 	// rank by ballot; otherwise the general prefix sum.
-	static __device__ __forceinline__ void emit_row(const RunParams &P, const Slice &S, Emitter &E, uint32_t lane, uint32_t cand, uint32_t c0)
+	// candidates of one row -> private list, in position order; returns how many
+	static __device__ __forceinline__ uint32_t emit_row(const RunParams &P, const uint8_t *gtile, uint32_t off, uint32_t ulen, Cand *dst,
+	                                                 uint32_t lane, uint32_t cand, uint32_t c0)
 	{
 		if (P.run_min > 17u) {
 			// long minimum: confirm bytes 17..n-1 (global memory: they may lie in another warp's slice)
@@ -551,8 +577,8 @@ struct RunEngine {
 				const uint32_t b = __ffs(t) - 1;
 				t &= t - 1;
 				const uint32_t p = c0 + b;
-				bool ok = (unsigned long long)S.off + p + P.run_min <= S.ulen;
-				for (uint32_t i = 17; ok && i < P.run_min; i++) ok = in_class(P, S.gtile[p + i]);
+				bool ok = (unsigned long long)off + p + P.run_min <= ulen;
+				for (uint32_t i = 17; ok && i < P.run_min; i++) ok = in_class(P, gtile[p + i]);
 				if (ok) keep |= 1u << b;
 			}
 			cand = keep;
@@ -561,14 +587,13 @@ struct RunEngine {
 			const uint32_t has = __ballot_sync(0xffffffffu, cand != 0);
 			if (cand) {
 				Cand c;
-				c.pos = S.off + c0 + (__ffs(cand) - 1);
+				c.pos = off + c0 + (__ffs(cand) - 1);
 				c.len = 0;
-				E.scratch[E.n + __popc(has & ((1u << lane) - 1u))] = c;
+				dst[__popc(has & ((1u << lane) - 1u))] = c;
 			}
-			E.n += __popc(has);
-		} else {
-			E.n += Emitter::emit_at(E.scratch + E.n, cand, S.off + c0, [](uint32_t) -> uint32_t { return 0u; }, lane);
+			return __popc(has);
 		}
+		return Emitter::emit_at(dst, cand, off + c0, [](uint32_t) -> uint32_t { return 0u; }, lane);
 	}
 
 	template <class G>
@@ -604,11 +629,21 @@ struct RunEngine {
 				const uint32_t pv = lane == 0 ? u >> 31 : (u >> 15) & 1u;
 				const uint32_t starts = cm[r] & ~((cm[r] << 1) | pv);
 				const uint32_t cand = starts & runs(P, cm[r] | (nx << 16)) & 0xffffu;
-				if (__any_sync(0xffffffffu, cand != 0)) emit_row(P, S, E, lane, cand, S.begin + r * 512 + lane * 16);
+				if (__any_sync(0xffffffffu, cand != 0)) E.n += emit_row(P, S.gtile, S.off, S.ulen, E.scratch + E.n, lane, cand, S.begin + r * 512 + lane * 16);
 			}
 			return;
 		}
-		// ---- slices at the end of a unit / short tiles: same logic with per-byte validity ----
+		// ---- slices at the end of a unit / short tiles: same logic with per-byte validity, out of line ----
+		E.n += run_tail(P, S.tile, S.gtile, S.off, S.ulen, S.begin, S.niter, prevbit, E.scratch + E.n, lane);
+	}
+
+	static __device__ __noinline__ uint32_t run_tail(const RunParams &P, const uint8_t *tile, const uint8_t *gtile, uint32_t off, uint32_t ulen,
+	                                                 uint32_t begin, uint32_t niter, uint32_t prevbit, Cand *dst, uint32_t lane)
+	{
+		Slice S;
+		S.tile = tile; S.gtile = gtile; S.extra = nullptr; S.off = off; S.ulen = ulen; S.tile_len = 0; S.begin = begin; S.niter = niter;
+		const uint32_t send = begin + niter * 512;
+		uint32_t n = 0;
 		uint32_t cm_next = mask16(P, S, S.begin + lane * 16);
 		for (uint32_t it = 0; it < S.niter; it++) {
 			const uint32_t c0 = S.begin + it * 512 + lane * 16;
@@ -633,8 +668,9 @@ struct RunEngine {
 			prevbit = __shfl_sync(0xffffffffu, cm, 31) >> 15;
 			const uint32_t starts = cm & ~((cm << 1) | pv);
 			const uint32_t cand = starts & runs(P, cm | (nx << 16)) & 0xffffu;
-			if (__any_sync(0xffffffffu, cand != 0)) emit_row(P, S, E, lane, cand, c0);
+			if (__any_sync(0xffffffffu, cand != 0)) n += emit_row(P, gtile, off, ulen, dst + n, lane, cand, c0);
 		}
+		return n;
 	}
 };
 
@@ -698,6 +734,7 @@ scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename
 	}
 	__syncwarp();
 
+	const uint64_t policy = l2_stream_policy();
 	// lane 0: describe slice `s` in slot `slot` and start its copy
 	auto issue = [&](uint32_t slot, uint32_t s, const TileDesc &d) {
 		uint32_t begin, niter;
@@ -711,9 +748,9 @@ scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename
 		const bool ahead = Eng::kLookAhead && rest >= niter * 512u + kHalo;
 		uint8_t *dst = my + (size_t)slot * slot_bytes + kHalo;
 		mbar_arrive_expect_tx(&c->full, bytes + (behind ? kHalo : 0u) + (ahead ? kHalo : 0u));
-		tma_load_1d(dst, reinterpret_cast<const void *>(d.src + begin), bytes, &c->full);
-		if (behind) tma_load_1d(dst - kHalo, reinterpret_cast<const void *>(d.src + begin - kHalo), kHalo, &c->full);
-		if (ahead) tma_load_1d(dst + niter * 512u, reinterpret_cast<const void *>(d.src + begin + niter * 512u), kHalo, &c->full);
+		tma_load_1d(dst, reinterpret_cast<const void *>(d.src + begin), bytes, &c->full, policy);
+		if (behind) tma_load_1d(dst - kHalo, reinterpret_cast<const void *>(d.src + begin - kHalo), kHalo, &c->full, policy);
+		if (ahead) tma_load_1d(dst + niter * 512u, reinterpret_cast<const void *>(d.src + begin + niter * 512u), kHalo, &c->full, policy);
 	};
 
 	if (lane == 0) {

@@ -22,7 +22,7 @@ d = ctx.device_alloc(n << 20)
 ctx.synth_corpus(d, 2, 0, n, 1 << 20, needle=b"foobardoesexist", needle_every=64)
 batch = ctx.batch_create(G.Context.device_units(d, n, 1 << 20))
 out = {}
-for name, pat, lit in (("literal", "foobardoesexist", True), ("alt4", "foo|bar|baz|quux", False), ("run16", "[A-Za-z0-9_]{16,}", False), ("lit2", "qz", False), ("icase", "(?i)linus", False), ("lits8", "alpha|bravo|charlie|delta|echo|foxtrot|golf|hotel", False), ("digits", r"\\d{3}-\\d{4}", False), ("run4", "[0-9]{4,}", False), ("lits100", corpus.literals100(), False)):
+for name, pat, lit in (("literal", "foobardoesexist", True), ("alt4", "foo|bar|baz|quux", False), ("run16", "[A-Za-z0-9_]{16,}", False), ("lit2", "qz", False), ("icase", "(?i)linus", False), ("lits8", "alpha|bravo|charlie|delta|echo|foxtrot|golf|hotel", False), ("digits", r"\\d{3}-\\d{4}", False), ("run4", "[0-9]{4,}", False), ("lits100", corpus.literals100(), False), ("literal2", "foobardoesexist", True), ("nomatch", "foobardoesnotexist", True)):
     p = G.Pattern(pat, literal=lit)
     ms = []
     for i in range(6):
