@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("GSCAN_LIB") or os.path.join(_HERE, "libgscan.so")  # 
 MODE_ALL, MODE_FIRST, MODE_LINE = 0, 1, 2
 LITERAL, STRICT_REF = 1, 2
 UNIT_DEVICE = 1
-ENGINE_FIXED, ENGINE_RUN, ENGINE_NONE = 1, 2, 3
+ENGINE_FIXED, ENGINE_RUN, ENGINE_NONE, ENGINE_VM = 1, 2, 3, 4
 
 
 class GscanError(RuntimeError):

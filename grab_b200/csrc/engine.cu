@@ -100,7 +100,8 @@ struct gscan_ctx {
 	std::vector<ResultBuf> results;
 	DevBuf<uint32_t> unit_start, unit_out, blk;
 	DevBuf<unsigned long long> cursor; // [0] cursor, then 2 x u32 totals behind it
-	DevBuf<uint8_t> pat_tables, hash_tables;
+	DevBuf<uint8_t> pat_tables, hash_tables, vm_tables;
+	const uint32_t *vm_code = nullptr, *vm_sets = nullptr;
 	uint64_t pat_id = 0;
 	FixedParams pat_fixed; // with this context's device pointers
 	HashParams pat_hash;
@@ -249,7 +250,7 @@ extern "C" int gscan_pattern_get_info(const gscan_pattern *p, gscan_pattern_info
 	o->minlen = p->prog.minlen;
 	o->maxlen = p->prog.maxlen;
 	o->captures = p->prog.captures;
-	o->engine = (int32_t)p->prog.kind;
+	o->engine = p->prog.use_vm ? GSCAN_ENGINE_VM : (int32_t)p->prog.kind;
 	o->n_sequences = (int32_t)p->prog.seqs.size();
 	o->n_filter_tests = p->prog.use_hash ? -(int32_t)p->prog.hash_slots : (int32_t)p->prog.tests.size();
 	o->filter_anchor = p->prog.anchor;
@@ -299,7 +300,7 @@ extern "C" void gscan_close(gscan_ctx *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->segs.release(); c->cand.release(); c->scratch.release(); c->ord.release(); c->out.release();
-	c->unit_start.release(); c->unit_out.release(); c->blk.release(); c->cursor.release(); c->pat_tables.release(); c->hash_tables.release();
+	c->unit_start.release(); c->unit_out.release(); c->blk.release(); c->cursor.release(); c->pat_tables.release(); c->hash_tables.release(); c->vm_tables.release();
 	c->probe_sum.release(); c->needle.release();
 	c->pool_arena.release(); c->pool_tiles.release(); c->pool_units.release();
 	c->readback.release(); c->stage[0].release(); c->stage[1].release();
@@ -515,6 +516,15 @@ static int ensure_pattern(gscan_ctx *ctx, const gscan_pattern *pat)
 			ctx->pat_hash.seq_pos = ctx->pat_fixed.seq_pos;
 			ctx->pat_hash.cls_bm = ctx->pat_fixed.cls_bm;
 		}
+		if (pat->prog.use_vm) {
+			const size_t nc = pat->prog.vm_code.size() * 4, nsb = pat->prog.vm_sets.size() * 4;
+			CK(ctx, ctx->vm_tables.ensure(nc + nsb + 64));
+			CK(ctx, cudaMemcpyAsync(ctx->vm_tables.p, pat->prog.vm_code.data(), nc, cudaMemcpyHostToDevice, ctx->stream));
+			CK(ctx, cudaMemcpyAsync(ctx->vm_tables.p + nc, pat->prog.vm_sets.data(), nsb, cudaMemcpyHostToDevice, ctx->stream));
+			CK(ctx, cudaStreamSynchronize(ctx->stream));
+			ctx->vm_code = reinterpret_cast<const uint32_t *>(ctx->vm_tables.p);
+			ctx->vm_sets = reinterpret_cast<const uint32_t *>(ctx->vm_tables.p + nc);
+		}
 	}
 	ctx->pat_id = pat->prog.id;
 	return 0;
@@ -569,7 +579,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	for (int attempt = 0;; attempt++) {
 		A.cand = ctx->cand.p;
 		A.cand_cap = (uint32_t)std::min<size_t>(ctx->cand.cap, 0xffffffffu);
-		CK(ctx, launch_fill_u32(reinterpret_cast<uint32_t *>(ctx->cursor.p), 4, 0u, ctx->stream));
+		CK(ctx, launch_fill_u32(reinterpret_cast<uint32_t *>(ctx->cursor.p), 8, 0u, ctx->stream));
 		CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
 		if (hashed) CK(ctx, launch_scan_hash(A, ctx->pat_hash, grid, ctx->stream));
 		else if (pat->prog.kind == ENGINE_FIXED) CK(ctx, launch_scan_fixed(A, ctx->pat_fixed, pat->prog.delta, geom, grid, ctx->stream));
@@ -617,7 +627,9 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		R.totals = reinterpret_cast<uint32_t *>(ctx->cursor.p + 1);
 		R.mode = mode;
 		R.minlen = (uint32_t)pat->prog.minlen;
-		R.engine = (uint32_t)pat->prog.kind;
+		R.engine = pat->prog.use_vm ? (uint32_t)GSCAN_ENGINE_VM : (uint32_t)pat->prog.kind;
+		R.vm_code = ctx->vm_code;
+		R.vm_sets = ctx->vm_sets;
 		R.run_min = (uint32_t)pat->prog.run_min;
 		for (int i = 0; i < 8; i++) R.bitmap[i] = pat->prog.run_class.w[i];
 		R.total_cand = (uint32_t)total_cand;
@@ -625,8 +637,9 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		CK(ctx, launch_resolve_count(R, ctx->stream, &nl));
 		S.total_launches += nl;
 		uint32_t *h_tot = reinterpret_cast<uint32_t *>((uint8_t *)ctx->readback.p + 16);
-		CK(ctx, cudaMemcpyAsync(h_tot, R.totals, 8, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaMemcpyAsync(h_tot, R.totals, 12, cudaMemcpyDeviceToHost, ctx->stream));
 		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		if (h_tot[2]) return fail(ctx, "gscan_batch_scan: the backtracking VM hit its stack or step limit on this input (PCRE would report a match-limit error); nothing is returned rather than a guess");
 		if (h_tot[0] != (uint32_t)total_cand) return fail(ctx, "gscan_batch_scan: internal: segment counts disagree with the cursor");
 		n = h_tot[1];
 		if (n) {
@@ -760,7 +773,7 @@ extern "C" int gscan_tma_probe(gscan_ctx *ctx, gscan_batch *b, int geom, float *
 	ScanArgs A;
 	A.tiles = b->d_tiles; A.n_tiles = b->n_tiles; A.cand = ctx->cand.p; A.cand_cap = (uint32_t)ctx->cand.cap;
 	A.cursor = ctx->cursor.p; A.segs = ctx->segs.p; A.scratch = ctx->scratch.p; A.extra_smem = 0; A.tag = ctx->seg_tag;
-	CK(ctx, launch_fill_u32(reinterpret_cast<uint32_t *>(ctx->cursor.p), 4, 0u, ctx->stream));
+	CK(ctx, launch_fill_u32(reinterpret_cast<uint32_t *>(ctx->cursor.p), 8, 0u, ctx->stream));
 	CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
 	CK(ctx, launch_scan_null(A, geom, (int)std::min<uint32_t>((uint32_t)ctx->num_sms, b->n_tiles), ctx->stream));
 	CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));

@@ -45,10 +45,12 @@ struct ResolveArgs {
 	uint32_t *unit_start; // [n_units + 1] first candidate of each unit in ord
 	uint32_t *unit_out;   // [n_units] matches per unit, then (exclusive scan) first output slot
 	uint32_t *blk;        // block-sum scratch
-	uint32_t *totals;     // [0] candidates, [1] matches
+	uint32_t *totals;     // [0] candidates, [1] matches, [2] VM limit flag
 	uint32_t mode, minlen, engine, run_min;
 	uint32_t bitmap[8];   // RUN class, for match-length extension
 	uint32_t total_cand;  // known on the host after the scan kernel
+	const uint32_t *vm_code; // general patterns: VM program (3 words per instruction) and byte classes (8 words each)
+	const uint32_t *vm_sets;
 };
 // count pass: segment scan, gather, per-unit replay that counts, slot scan; totals[1] = number of matches
 cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t *launches);

@@ -91,6 +91,7 @@ struct Node {
 	uint32_t rmin = 0, rmax = 0; // rmax == UINT32_MAX: unbounded
 	bool lazy = false, possessive = false;
 	bool capturing = false;
+	int akind = 0; // ASSERT: one of VM_A_*
 	explicit Node(Kind k) : kind(k) {}
 };
 
@@ -181,10 +182,15 @@ private:
 		}
 		case 'b':
 			if (in_class) { ch = 8; return 1; }
+			ch = VM_A_WORDB;
 			return 3;
-		case 'B': case 'A': case 'z': case 'Z': case 'G':
+		case 'B': case 'A': case 'z': case 'Z':
 			if (in_class) { fail("assertion escape inside a class"); return 0; }
+			ch = c == 'B' ? VM_A_NWORDB : c == 'A' ? VM_A_SOS : c == 'z' ? VM_A_EOS : VM_A_EOSNL;
 			return 3;
+		case 'G':
+			fail("\\G is not supported");
+			return 0;
 		default:
 			if (c >= '1' && c <= '9') { fail("back references are not supported"); return 0; }
 			if (is_alnum(c)) { fail("unsupported escape sequence"); return 0; }
@@ -356,7 +362,11 @@ private:
 			if (!f.dotall) n->set.w[0] &= ~(1u << 10);
 			return n;
 		}
-		case '^': case '$': return NodeP(new Node(Node::ASSERT));
+		case '^': case '$': {
+			NodeP n(new Node(Node::ASSERT));
+			n->akind = c == '^' ? (f.multiline ? VM_A_MBOL : VM_A_BOL) : (f.multiline ? VM_A_MEOL : VM_A_EOL);
+			return n;
+		}
 		case '\\': {
 			if (more() && *p_ == 'Q') {
 				p_++;
@@ -374,7 +384,9 @@ private:
 			if (k == 0) return nullptr;
 			if (k == 1) return make_char(ch, f);
 			if (k == 2) { NodeP n(new Node(Node::SET)); n->set = t; return n; }
-			return NodeP(new Node(Node::ASSERT));
+			NodeP n(new Node(Node::ASSERT));
+			n->akind = (int)ch;
+			return n;
 		}
 		case '*': case '+': case '?':
 			fail("quantifier does not follow a repeatable item");
@@ -476,6 +488,7 @@ struct Expander {
 	size_t budget_seqs = kMaxSequences;
 	size_t budget_bytes = 1u << 20;
 	bool overflow = false;
+	bool general = false; // the pattern is fine, it just is not a list of fixed-length sequences: use the VM
 	std::string why;
 
 	typedef std::vector<Sequence> List;
@@ -530,7 +543,7 @@ struct Expander {
 		if (overflow) return out;
 		switch (n->kind) {
 		case Node::EMPTY: out.push_back(Sequence()); return out;
-		case Node::ASSERT: overflow = true; why = "assertions (^ $ \\b ...) are not supported by the device engines"; return out;
+		case Node::ASSERT: overflow = true; general = true; return out;
 		case Node::SET:
 			if (n->set.empty()) return out; // can never match: contributes no alternative
 			out.push_back(Sequence(1, n->set));
@@ -552,16 +565,12 @@ struct Expander {
 			}
 			return out;
 		case Node::REP: {
-			if (n->rmax == kInf) {
-				overflow = true;
-				why = "unbounded repeat (* + {n,}) is only supported as a whole-pattern byte-class run like [a-z]{4,}";
-				return out;
-			}
+			if (n->rmax == kInf) { overflow = true; general = true; return out; }
 			List body = expand(n->kids[0].get());
 			if (overflow) return out;
 			// a possessive bounded repeat of single-byte bodies behaves like greedy without give-back;
 			// expanding it as greedy could add matches PCRE would not find, so refuse
-			if (n->possessive) { overflow = true; why = "possessive quantifier on a bounded repeat is not supported"; return out; }
+			if (n->possessive) { overflow = true; general = true; return out; }
 			return rest(body, 0, n->rmin, n->rmax, n->lazy);
 		}
 		}
@@ -602,6 +611,165 @@ bool can_overlap(const Sequence &a, const Sequence &b, size_t shift)
 	for (size_t i = 0; shift + i < a.size() && i < b.size(); i++)
 		if (!a[shift + i].intersects(b[i])) return false;
 	return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// general patterns: backtracking VM program + leading-byte prefixes
+// ------------------------------------------------------------------------------------------
+// Anything the FIXED / RUN programs cannot express (unbounded repeats inside a sequence, assertions, lazy
+// quantifiers, repeated groups) runs as: (1) a scan for the fixed-length leading byte sequences every match
+// must start with (same kernels as FIXED), (2) the backtracking VM below, executed on the device at each
+// candidate in position order by the resolve walk -- PCRE's own strategy (first-code-unit scan, then the
+// interpreter), with PCRE's preference order: alternatives in source order, greedy takes all and gives back.
+
+struct VmGen {
+	std::vector<uint32_t> code; // 3 words per instruction: op | kind << 8 | set << 16, a, b
+	std::vector<ByteSet> sets;
+	bool failed = false;
+	std::string why;
+
+	uint32_t emit(uint32_t op, uint32_t kind, uint32_t set, uint32_t a, uint32_t b)
+	{
+		if (code.size() / 3 >= 4096) { failed = true; why = "pattern too large for the device VM (more than 4096 instructions)"; return 0; }
+		code.push_back(op | (kind << 8) | (set << 16));
+		code.push_back(a);
+		code.push_back(b);
+		return (uint32_t)(code.size() / 3 - 1);
+	}
+	uint32_t set_id(const ByteSet &s)
+	{
+		for (size_t i = 0; i < sets.size(); i++) if (sets[i] == s) return (uint32_t)i;
+		sets.push_back(s);
+		return (uint32_t)sets.size() - 1;
+	}
+	void gen(const Node *n)
+	{
+		if (failed) return;
+		switch (n->kind) {
+		case Node::EMPTY: return;
+		case Node::SET: emit(VM_SET, 0, set_id(n->set), 0, 0); return;
+		case Node::ASSERT: emit(VM_ASSERT, (uint32_t)n->akind, 0, 0, 0); return;
+		case Node::GROUP: gen(n->kids[0].get()); return;
+		case Node::CAT: for (auto &k : n->kids) gen(k.get()); return;
+		case Node::ALT: {
+			std::vector<uint32_t> jmps;
+			for (size_t i = 0; i < n->kids.size() && !failed; i++) {
+				if (i + 1 < n->kids.size()) {
+					const uint32_t s = emit(VM_SPLIT, 0, 0, 0, 0);
+					gen(n->kids[i].get());
+					jmps.push_back(emit(VM_JMP, 0, 0, 0, 0));
+					if (failed) return;
+					code[3 * s + 1] = s + 1;
+					code[3 * s + 2] = (uint32_t)(code.size() / 3);
+				} else {
+					gen(n->kids[i].get());
+				}
+			}
+			for (uint32_t j : jmps) code[3 * j + 1] = (uint32_t)(code.size() / 3);
+			return;
+		}
+		case Node::REP: {
+			const Node *body = peel(n->kids[0].get());
+			const uint32_t kind = n->lazy ? VM_Q_LAZY : n->possessive ? VM_Q_POSSESSIVE : VM_Q_GREEDY;
+			if (body->kind == Node::SET) { emit(VM_REP, kind, set_id(body->set), n->rmin, n->rmax); return; }
+			if (n->possessive) { failed = true; why = "possessive quantifier on a group is not supported"; return; }
+			if (n->rmax == kInf && min_length(n->kids[0].get()) == 0) { failed = true; why = "unbounded repeat of an empty-matchable group is not supported"; return; }
+			if (n->rmin > 256 || (n->rmax != kInf && n->rmax > 256)) { failed = true; why = "group repeat count above 256 is not supported"; return; }
+			for (uint32_t i = 0; i < n->rmin && !failed; i++) gen(n->kids[0].get());
+			if (n->rmax == kInf) {
+				const uint32_t L = emit(VM_SPLIT, 0, 0, 0, 0);
+				gen(n->kids[0].get());
+				emit(VM_JMP, 0, 0, L, 0);
+				if (failed) return;
+				const uint32_t out = (uint32_t)(code.size() / 3);
+				code[3 * L + 1] = n->lazy ? out : L + 1;
+				code[3 * L + 2] = n->lazy ? L + 1 : out;
+			} else {
+				std::vector<uint32_t> splits;
+				for (uint32_t i = n->rmin; i < n->rmax && !failed; i++) {
+					splits.push_back(emit(VM_SPLIT, 0, 0, 0, 0));
+					gen(n->kids[0].get());
+				}
+				const uint32_t out = (uint32_t)(code.size() / 3);
+				for (uint32_t sp : splits) {
+					code[3 * sp + 1] = n->lazy ? out : sp + 1;
+					code[3 * sp + 2] = n->lazy ? sp + 1 : out;
+				}
+			}
+			return;
+		}
+		}
+	}
+};
+
+// byte-class sequences (length <= L) every match of `n` starts with; `done`: the node is consumed exactly by
+// the sequence, so what follows the node may extend it
+struct Pref { Sequence seq; bool done; };
+
+bool prefixes(const Node *n, size_t L, std::vector<Pref> &out)
+{
+	out.clear();
+	switch (n->kind) {
+	case Node::EMPTY: case Node::ASSERT: out.push_back(Pref{Sequence(), true}); return true;
+	case Node::SET:
+		if (n->set.empty()) return true; // can never match: no prefix at all
+		out.push_back(Pref{Sequence(1, n->set), true});
+		return true;
+	case Node::GROUP: return prefixes(n->kids[0].get(), L, out);
+	case Node::ALT:
+		for (auto &k : n->kids) {
+			std::vector<Pref> t;
+			if (!prefixes(k.get(), L, t)) return false;
+			out.insert(out.end(), t.begin(), t.end());
+			if (out.size() > 256) return false;
+		}
+		return true;
+	case Node::CAT: {
+		out.push_back(Pref{Sequence(), true});
+		for (auto &k : n->kids) {
+			bool any_open = false;
+			for (auto &p : out) any_open = any_open || (p.done && p.seq.size() < L);
+			if (!any_open) break;
+			std::vector<Pref> t, next;
+			if (!prefixes(k.get(), L, t)) return false;
+			for (auto &p : out) {
+				if (!p.done || p.seq.size() >= L) { next.push_back(Pref{p.seq, false}); continue; }
+				for (auto &q : t) {
+					Pref r{p.seq, q.done};
+					for (auto &cls : q.seq) {
+						if (r.seq.size() >= L) { r.done = false; break; }
+						r.seq.push_back(cls);
+					}
+					next.push_back(r);
+				}
+			}
+			if (next.size() > 256) return false;
+			out.swap(next);
+		}
+		return true;
+	}
+	case Node::REP: {
+		const Node *body = peel(n->kids[0].get());
+		if (n->rmax == 0) { out.push_back(Pref{Sequence(), true}); return true; }
+		if (body->kind == Node::SET && !body->set.empty()) {
+			// a class repeated: min copies are certain
+			const size_t take = std::min<size_t>(n->rmin, L);
+			if (n->rmin == 0) {
+				out.push_back(Pref{Sequence(), true});              // skipped: what follows starts the match
+				out.push_back(Pref{Sequence(1, body->set), false}); // or at least one
+			} else {
+				out.push_back(Pref{Sequence(take, body->set), n->rmin == n->rmax && n->rmin <= L});
+			}
+			return true;
+		}
+		std::vector<Pref> t;
+		if (!prefixes(n->kids[0].get(), L, t)) return false;
+		if (n->rmin == 0) out.push_back(Pref{Sequence(), true});
+		for (auto &p : t) out.push_back(Pref{p.seq, p.done && n->rmin == 1 && n->rmax == 1});
+		return true;
+	}
+	}
+	return false;
 }
 
 std::atomic<uint64_t> g_next_id{1};
@@ -708,10 +876,6 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 		out.maxlen = -1;
 		return true;
 	}
-	if (has_assert(root.get())) {
-		err = "assertions (^ $ \\b \\B \\A \\z \\Z) are not supported by the device engines";
-		return false;
-	}
 
 	// RUN: the whole pattern is one byte class repeated {n,}
 	const Node *core = peel(root.get());
@@ -739,8 +903,31 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 
 	// FIXED: expand into fixed-length sequences in backtracking (preference) order
 	Expander ex;
-	std::vector<Sequence> seqs = ex.expand(root.get());
-	if (ex.overflow) { err = ex.why; return false; }
+	std::vector<Sequence> seqs;
+	if (!has_assert(root.get())) seqs = ex.expand(root.get());
+	else { ex.overflow = true; ex.general = true; }
+	if (ex.overflow && !ex.general) { err = ex.why; return false; }
+	if (ex.overflow) {
+		// general pattern: VM program + leading-byte prefixes as the candidate filter
+		VmGen g;
+		g.gen(root.get());
+		g.emit(VM_MATCH, 0, 0, 0, 0);
+		if (g.failed) { err = g.why; return false; }
+		std::vector<Pref> pf;
+		if (!prefixes(root.get(), 4, pf) || pf.empty()) { err = "pattern has too many distinct leading byte sequences for the candidate filter"; return false; }
+		seqs.clear();
+		for (auto &p : pf) {
+			if (p.seq.empty()) {
+				err = "pattern can start with any byte (leading optional item or bare assertion): the device engines need at "
+				      "least one fixed leading byte class";
+				return false;
+			}
+			seqs.push_back(p.seq);
+		}
+		out.use_vm = true;
+		out.vm_code = g.code;
+		for (auto &s : g.sets) for (int i = 0; i < 8; i++) out.vm_sets.push_back(s.w[i]);
+	}
 	// drop exact duplicates (a later identical alternative can never win) and never-matching ones
 	std::vector<Sequence> uniq;
 	for (auto &s : seqs) {
@@ -760,7 +947,7 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 	out.seqs = uniq;
 	size_t mn = SIZE_MAX, mx = 0;
 	for (auto &s : out.seqs) { mn = std::min(mn, s.size()); mx = std::max(mx, s.size()); }
-	out.maxlen = (int)mx;
+	out.maxlen = out.use_vm ? -1 : (int)mx;
 	// (minlen from the tree equals mn unless shadowing removed the shortest: keep PCRE's figure)
 
 	// ---- choose the SWAR filter: anchor byte + second byte `delta` further on ----
@@ -831,6 +1018,11 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 		}
 	}
 
+	if (out.use_vm && best_p > 0.30) {
+		err = "the leading bytes of the pattern are too common for the candidate filter (every match attempt runs the "
+		      "backtracking VM on the device); anchor the pattern on a rarer leading byte";
+		return false;
+	}
 	// a 4 KiB slice has 8 rows of 512 bytes; once more than a few percent of the rows get flagged the slow path
 	// dominates, and three filter bytes (+2 ops per word) are cheaper than visiting it
 	out.pair_flag_prior = best_p;

@@ -53,6 +53,11 @@ struct FilterTest {
 
 enum EngineKind { ENGINE_FIXED = 1, ENGINE_RUN = 2, ENGINE_NONE = 3 };
 
+// device VM (resolve_kernels.cu) instruction set
+enum { VM_SET = 0, VM_SPLIT = 1, VM_JMP = 2, VM_REP = 3, VM_ASSERT = 4, VM_MATCH = 5 };
+enum { VM_Q_GREEDY = 0, VM_Q_LAZY = 1, VM_Q_POSSESSIVE = 2 };
+enum { VM_A_BOL = 0, VM_A_EOL = 1, VM_A_SOS = 2, VM_A_EOS = 3, VM_A_EOSNL = 4, VM_A_WORDB = 5, VM_A_NWORDB = 6, VM_A_MBOL = 7, VM_A_MEOL = 8 };
+
 constexpr int kMaxFilterTests = 8;
 constexpr int kMaxPatternLen = 1024;   // longest sequence the smem halo can verify
 constexpr int kMaxSequences = 4096;
@@ -88,6 +93,11 @@ struct Program {
 	ByteSet run_class;
 	int run_min = 0;
 	std::vector<ByteRange> ranges_low, ranges_high; // within 0x00-0x7F / 0x80-0xFF
+
+	// general patterns: seqs are the leading-byte prefixes (candidate filter), matches are decided by the VM
+	bool use_vm = false;
+	std::vector<uint32_t> vm_code; // 3 words per instruction
+	std::vector<uint32_t> vm_sets; // 8 words per byte class
 
 	uint64_t id = 0; // unique per compiled pattern (device-table cache key)
 };

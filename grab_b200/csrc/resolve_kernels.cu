@@ -14,6 +14,7 @@
 #include "../../include/gscan.h"
 #include "device_types.h"
 #include "kernels.h"
+#include "pattern.h"
 
 namespace gscan {
 
@@ -121,6 +122,111 @@ __global__ void k_gather(const ResolveArgs R)
 	}
 }
 
+// ---- device backtracking VM (general patterns) ----
+// PCRE's matching strategy restated for one anchored attempt: alternatives in source order, greedy repeats take
+// everything and give back one item at a time, lazy ones take one more on demand; explicit stack, no recursion.
+// `subj` is the subject as the reference's pcre_exec call sees it: it begins at the moving search start
+// (grab.cc:178), so ^, \A and \b at its first byte behave exactly as there.
+constexpr int kVmStack = 96;
+constexpr uint32_t kVmMaxSteps = 1u << 24;
+
+__device__ __forceinline__ bool vm_in_set(const ResolveArgs &R, uint32_t set, uint32_t b) { return (R.vm_sets[set * 8 + (b >> 5)] >> (b & 31)) & 1u; }
+__device__ __forceinline__ bool vm_is_word(uint32_t b) { return (b >= '0' && b <= '9') || (b >= 'A' && b <= 'Z') || (b >= 'a' && b <= 'z') || b == '_'; }
+
+__device__ bool vm_assert(uint32_t kind, const uint8_t *s, uint32_t len, uint32_t sp)
+{
+	switch (kind) {
+	case VM_A_BOL: case VM_A_SOS: return sp == 0;
+	case VM_A_MBOL: return sp == 0 || s[sp - 1] == '\n';
+	case VM_A_EOS: return sp == len;
+	case VM_A_EOL: case VM_A_EOSNL: return sp == len || (sp + 1 == len && s[sp] == '\n');
+	case VM_A_MEOL: return sp == len || s[sp] == '\n';
+	default: {
+		const bool before = sp > 0 && vm_is_word(s[sp - 1]);
+		const bool after = sp < len && vm_is_word(s[sp]);
+		return (before != after) == (kind == VM_A_WORDB);
+	}
+	}
+}
+
+// 1: match, *end set; 0: no match at `at`; -1: stack / step limit
+__device__ int vm_exec(const ResolveArgs &R, const uint8_t *s, uint32_t len, uint32_t at, uint32_t *end)
+{
+	uint32_t st_pc[kVmStack], st_sp[kVmStack], st_lo[kVmStack]; // st_pc: pc | kind << 16 (0 plain, 1 give-back, 2 take-more)
+	int top = 0;
+	uint32_t pc = 0, sp = at, steps = 0;
+	for (;;) {
+		if (++steps > kVmMaxSteps) return -1;
+		const uint32_t w0 = R.vm_code[3 * pc], a = R.vm_code[3 * pc + 1], b = R.vm_code[3 * pc + 2];
+		const uint32_t op = w0 & 0xffu, kind = (w0 >> 8) & 0xffu, set = w0 >> 16;
+		bool fail = false;
+		switch (op) {
+		case VM_MATCH: *end = sp; return 1;
+		case VM_SET:
+			if (sp < len && vm_in_set(R, set, s[sp])) { sp++; pc++; } else fail = true;
+			break;
+		case VM_ASSERT:
+			if (vm_assert(kind, s, len, sp)) pc++; else fail = true;
+			break;
+		case VM_JMP: pc = a; break;
+		case VM_SPLIT:
+			if (top == kVmStack) return -1;
+			st_pc[top] = b; st_sp[top] = sp; st_lo[top] = 0; top++;
+			pc = a;
+			break;
+		default: { // VM_REP: one byte class, a = min, b = max
+			const uint32_t avail = len - sp, mx = b == 0xffffffffu ? avail : (b < avail ? b : avail);
+			uint32_t k = 0;
+			if (kind == VM_Q_LAZY) {
+				while (k < a && k < avail && vm_in_set(R, set, s[sp + k])) k++;
+				if (k < a) { fail = true; break; }
+				if (b > a) { // may take more later: remember how many
+					if (top == kVmStack) return -1;
+					st_pc[top] = pc | (2u << 16); st_sp[top] = sp + k; st_lo[top] = b == 0xffffffffu ? 0xffffffffu : b - a; top++;
+				}
+				sp += k; pc++;
+			} else {
+				while (k < mx && vm_in_set(R, set, s[sp + k])) k++;
+				if (k < a) { fail = true; break; }
+				if (kind == VM_Q_GREEDY && k > a) {
+					if (top == kVmStack) return -1;
+					st_pc[top] = (pc + 1) | (1u << 16); st_sp[top] = sp + k; st_lo[top] = sp + a; top++;
+				}
+				sp += k; pc++;
+			}
+			break;
+		}
+		}
+		if (!fail) continue;
+		for (;;) { // backtrack
+			if (top == 0) return 0;
+			const uint32_t e = st_pc[top - 1], ek = e >> 16;
+			if (ek == 0) { pc = e; sp = st_sp[top - 1]; top--; break; }
+			if (ek == 1) { // greedy repeat gives one item back
+				if (st_sp[top - 1] > st_lo[top - 1]) {
+					sp = --st_sp[top - 1];
+					pc = e & 0xffffu;
+					if (st_sp[top - 1] == st_lo[top - 1]) top--;
+					break;
+				}
+				top--;
+				continue;
+			}
+			{ // lazy repeat takes one more item
+				const uint32_t rpc = e & 0xffffu, rset = R.vm_code[3 * rpc] >> 16;
+				if (st_lo[top - 1] > 0 && st_sp[top - 1] < len && vm_in_set(R, rset, s[st_sp[top - 1]])) {
+					sp = ++st_sp[top - 1];
+					if (st_lo[top - 1] != 0xffffffffu) st_lo[top - 1]--;
+					pc = rpc + 1;
+					if (st_lo[top - 1] == 0) top--;
+					break;
+				}
+				top--;
+			}
+		}
+	}
+}
+
 // ---- 3. per-unit replay of the reference loop ----
 // Pass 1 (WRITE=false) counts the matches of every unit, pass 2 writes them at the unit's slot of
 // the output (exclusive scan of the counts in between): the output can hold matches that are not
@@ -137,7 +243,39 @@ __global__ void k_walk(const ResolveArgs R)
 	const uint32_t end = R.unit_start[u + 1];
 	uint32_t n = 0;
 	FinalRec *o = WRITE ? R.out + R.unit_out[u] : nullptr;
-	if (i != end) {
+	if (i != end && R.engine == GSCAN_ENGINE_VM) {
+		// general patterns: every match starts at a candidate (a leading-byte prefix hit).  The count pass runs the
+		// VM and records the outcome in the candidate array, the write pass only copies.
+		const DevUnit du = R.units[u];
+		if (!WRITE) {
+			const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
+			const uint64_t ulen = du.len;
+			uint64_t start = 0;
+			for (; i < end; i++) {
+				if (!(start + R.minlen < ulen)) break;                                  // grab.cc:175
+				const uint32_t pos = R.ord[i].pos;
+				if (pos < start) continue;
+				uint32_t e = 0;
+				const int rc = vm_exec(R, data + start, (uint32_t)(ulen - start), (uint32_t)(pos - start), &e); // grab.cc:178
+				if (rc < 0) { atomicOr(R.totals + 2, 1u); break; }                      // limits: reported, never guessed
+				if (rc == 0) continue;                                                  // next start offset, like PCRE
+				uint64_t me = start + e;
+				R.ord[i].len = (uint32_t)(me - pos);
+				R.ord[i].pad = 1;
+				n++;
+				if (R.mode == GSCAN_MODE_FIRST) break;
+				if (R.mode == GSCAN_MODE_LINE) {
+					uint32_t a = 0;
+					while (me + a < ulen && a < 511 && data[me + a] != '\n') a++;
+					me += a;
+				}
+				start = me;                                                             // grab.cc:209
+			}
+		} else {
+			for (; i < end; i++)
+				if (R.ord[i].pad) { FinalRec r; r.start = du.base_off + R.ord[i].pos; r.file_id = du.file_id; r.len = R.ord[i].len; o[n++] = r; }
+		}
+	} else if (i != end) {
 		const DevUnit du = R.units[u];
 		const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
 		const uint64_t ulen = du.len;

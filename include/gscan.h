@@ -74,6 +74,7 @@ typedef struct gscan_pattern_info {
 #define GSCAN_ENGINE_FIXED 1 /* alternation of fixed-length byte-class sequences (literals, sets) */
 #define GSCAN_ENGINE_RUN 2   /* one byte class repeated {n,} (greedy) */
 #define GSCAN_ENGINE_NONE 3  /* can never print anything (STRICT_REF with a capturing group) */
+#define GSCAN_ENGINE_VM 4    /* general pattern: leading-byte scan + backtracking VM on the device */
 
 typedef struct gscan_stats {
 	uint64_t bytes_scanned;  /* sum of unit lengths == algorithmic HBM bytes */

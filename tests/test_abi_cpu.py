@@ -31,7 +31,7 @@ def test_struct_layouts():
     assert ctypes.sizeof(G.Match) == 16 and G.MATCH_DTYPE.itemsize == 16
 
 
-UNSUPPORTED_OK = ("not supported", "only supported", "empty string", "too many", "not built yet", "needs more than")
+UNSUPPORTED_OK = ("not supported", "only supported", "empty string", "too many", "too common", "any byte", "needs more than")
 
 
 @pytest.mark.parametrize("ent", MINLEN, ids=lambda e: e["pattern"][:24])
@@ -70,6 +70,10 @@ def test_engine_selection_and_filter():
     assert G.Pattern("a{2,4}").info["n_sequences"] == 3  # aaaa, aaa, aa (greedy order)
     assert G.Pattern("fo|foo|foobar").info["n_sequences"] == 1  # later alternatives are shadowed by fo
     assert G.Pattern("colou?r").info["n_sequences"] == 2
+    # general patterns: VM engine, candidates from the leading bytes
+    i = G.Pattern(r"foo\d+bar").info
+    assert i["engine"] == G.ENGINE_VM and i["minlen"] == 7 and i["maxlen"] == -1
+    assert G.Pattern("^foo").info["engine"] == G.ENGINE_VM and G.Pattern(r"\bfoo\b").info["minlen"] == 3
     # many alternatives: hashed engine (negative n_filter_tests = -(table slots))
     import corpus
     i = G.Pattern(corpus.literals100()).info
@@ -78,8 +82,7 @@ def test_engine_selection_and_filter():
 
 @pytest.mark.parametrize("pat,frag", [
     ("x*", "empty string"), ("", "empty string"), ("a|", "empty string"),
-    ("^foo", "not supported"), (r"\bfoo", "not supported"), ("foo$", "not supported"),
-    ("ab*c", "only supported"), ("<.+>", "only supported"), (r"foo\d+bar", "only supported"),
+    (".*foo", "too common"), (r"\w+@\w+", "too common"), ("a*", "empty string"), ("(?:a*)+b", "not supported"),
     ("(", "missing )"), ("[a-", "missing terminating ]"), (r"\1", "back references"), ("(?=a)b", "not supported"),
     ("a{3,2}", "quantifier"),
 ])

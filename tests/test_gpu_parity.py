@@ -86,7 +86,10 @@ DIFF_PATTERNS = ["ab", "aa", "aba", "abab", "a", "abc|bc|c", "ab|abc", "abc|ab",
                  "abcabc", "cab|abc|bca", "a{2,3}", "(?:ab){1,2}c", "b?ac", "[ab]c{0,2}a",
                  # > 4 distinct leading byte pairs => hashed engine (2- and 3-byte keys, shared prefixes, preference order)
                  "ab|ba|ca|cb|bc|ac", "aab|aba|abb|baa|bab|bba|cab|cba", "abc|ab|bca|bc|cab|ca|aab|bb", "(?i)ab|ba|ca|cb|bc",
-                 "a[ab]c|b[bc]a|c[ac]b|ab[ab]|ba[bc]", "abca|abcb|bcab|bcaa|cabc|caba|aabb|bbaa|ccaa"]
+                 "a[ab]c|b[bc]a|c[ac]b|ab[ab]|ba[bc]", "abca|abcb|bcab|bcaa|cabc|caba|aabb|bbaa|ccaa",
+                 # general patterns: leading-byte scan + backtracking VM on the device
+                 "ab*c", "a+b", "(?:ab)+c", "a.*b", "a.*?b", "^ab", "ab$", "\\bab", "ab\\b", "c[ab]+c[ab]*", "a(?:b|c)*a", "ab+?b", "(?:a|ab)(?:c|bcd)(?:d*)",
+                 "^a", "a$", "b\\Ba", "(?m)^ab", "(?m)ab$", "a{2,}b", "(?:ab|a)*c", "a[^\\n]*c", "ab??c", "(?s)a.b"]
 
 
 @pytest.mark.parametrize("pat", DIFF_PATTERNS)
