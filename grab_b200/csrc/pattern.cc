@@ -942,6 +942,28 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 			}
 		if (!dup) uniq.push_back(s);
 	}
+	// alternatives of equal length that differ in exactly one position are one alternative with the union class
+	// there: same start, same length, so which of them PCRE would have preferred does not show ("a|b|c" == "[abc]")
+	for (bool merged = true; merged;) {
+		merged = false;
+		for (size_t i = 0; i < uniq.size() && !merged; i++)
+			for (size_t j = i + 1; j < uniq.size() && !merged; j++) {
+				if (uniq[i].size() != uniq[j].size()) continue;
+				int diff = -1, ndiff = 0;
+				for (size_t k = 0; k < uniq[i].size(); k++)
+					if (!(uniq[i][k] == uniq[j][k])) { diff = (int)k; ndiff++; }
+				if (ndiff != 1) continue;
+				// only safe if nothing between them in preference order could win at a position where j matches:
+				// merging moves j's matches up to i's rank, which changes the result only if an alternative k in (i, j)
+				// of a DIFFERENT length also matches there -- so require all alternatives in between to have this length
+				bool ok = true;
+				for (size_t k = i + 1; k < j && ok; k++) ok = uniq[k].size() == uniq[i].size();
+				if (!ok) continue;
+				uniq[i][diff].unite(uniq[j][diff]);
+				uniq.erase(uniq.begin() + (long)j);
+				merged = true;
+			}
+	}
 	if (uniq.empty()) { err = "pattern can never match"; return false; }
 	out.kind = ENGINE_FIXED;
 	out.seqs = uniq;

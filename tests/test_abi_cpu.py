@@ -57,7 +57,7 @@ def test_engine_selection_and_filter():
     assert i["engine"] == G.ENGINE_FIXED and i["n_sequences"] == 1 and i["n_filter_tests"] == 1
     assert i["minlen"] == 18 and i["maxlen"] == 18 and i["filter_delta"] in (1, 2, 3, 4)
     i = G.Pattern("foo|bar|baz|quux").info
-    assert i["engine"] == G.ENGINE_FIXED and i["n_sequences"] == 4 and i["minlen"] == 3 and i["maxlen"] == 4
+    assert i["engine"] == G.ENGINE_FIXED and i["n_sequences"] == 3 and i["minlen"] == 3 and i["maxlen"] == 4  # bar|baz merge into ba[rz]
     assert 1 <= i["n_filter_tests"] <= 4
     i = G.Pattern("[A-Za-z0-9_]{16,}").info
     assert i["engine"] == G.ENGINE_RUN and i["minlen"] == 16 and i["maxlen"] == -1

@@ -1,0 +1,102 @@
+"""Seeded random differential: patterns drawn from a small PCRE grammar x random inputs, CUDA path vs the oracle
+port, all three modes.  Patterns either side rejects are skipped (the engine rejects loudly at compile)."""
+import random
+
+import pytest
+
+import grab_b200 as G
+import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+
+
+def gen_pattern(rnd, depth=0):
+    atoms = ["a", "b", "c", ".", "[ab]", "[^a]", "[a-c]", "\\w", "\\s", "x", " "]
+
+    def atom():
+        r = rnd.random()
+        if depth < 2 and r < 0.18:
+            return "(?:" + gen_pattern(rnd, depth + 1) + ")"
+        return rnd.choice(atoms)
+
+    def piece():
+        a = atom()
+        r = rnd.random()
+        if r < 0.50:
+            return a
+        q = rnd.choice(["*", "+", "?", "{2}", "{1,3}", "{2,}", "*?", "+?", "??"])
+        return a + q
+
+    def seq():
+        return "".join(piece() for _ in range(rnd.randint(1, 4)))
+
+    alts = [seq() for _ in range(rnd.choice([1, 1, 1, 2, 3]))]
+    p = "|".join(alts)
+    if depth == 0:
+        r = rnd.random()
+        if r < 0.08:
+            p = "^" + p
+        elif r < 0.16:
+            p = p + "$"
+        elif r < 0.22:
+            p = "\\b" + p
+        elif r < 0.27:
+            p = "(?i)" + p.upper() if p.isalpha() else p
+    return p
+
+
+def make_cases(n, seed):
+    rnd = random.Random(seed)
+    out, seen = [], set()
+    while len(out) < n:
+        p = gen_pattern(rnd)
+        if p in seen:
+            continue
+        seen.add(p)
+        out.append(p)
+    return out
+
+
+PATTERNS = make_cases(260, 424242)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = G.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def inputs():
+    rnd = random.Random(99)
+    bufs = []
+    for k in range(40):
+        alpha = [b"abc", b"abcx \n", b"ab", b"abc abc\n\n", b"aabbcc_x1 \t\n"][k % 5]
+        ln = rnd.choice([1, 2, 3, 7, 16, 17, 33, 64, 130, 511, 513, 1000, 2050, 4100, 9000])
+        bufs.append(bytes(rnd.choice(alpha) for _ in range(ln)))
+    return bufs
+
+
+@pytest.mark.parametrize("pat", PATTERNS)
+def test_random_pattern(ctx, inputs, pat):
+    try:
+        o = O.Regex(pat)
+    except O.OracleError:
+        pytest.skip("oracle does not model it")
+    if o.nullable:
+        with pytest.raises(G.GscanError):
+            G.Pattern(pat)
+        return
+    try:
+        p = G.Pattern(pat)
+    except G.GscanError as e:
+        pytest.skip("engine rejects: " + str(e)[:60])
+    assert p.minlen == o.minlen
+    for mode in (G.MODE_ALL, G.MODE_FIRST, G.MODE_LINE):
+        r = ctx.scan(p, inputs, mode=mode)
+        got = {}
+        for fid, s, l in zip(r["file_id"].tolist(), r["start"].tolist(), r["match_len"].tolist()):
+            got.setdefault(fid, []).append((s, l))
+        for i, b in enumerate(inputs):
+            assert got.get(i, []) == o.scan_window(b, mode=mode), (pat, mode, i, len(b))
