@@ -382,6 +382,7 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 	const uint8_t *run_src = nullptr;
 	uint8_t *run_dst = nullptr;
 	size_t run_len = 0;
+	const uint8_t *prev_pinned_end = nullptr;
 	bool staged[2] = {false, false};
 	cudaEvent_t sev[2] = {ctx->ev[2], ctx->ev[3]};
 	for (size_t i = 0; i < n_units; i++) {
@@ -393,9 +394,18 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 		} else {
 			uint8_t *dst = b->d_arena + arena_off[i];
 			dptr = dst;
-			cudaPointerAttributes attr;
-			bool pinned = cudaPointerGetAttributes(&attr, u.ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-			cudaGetLastError();
+			// pinned (page-locked) host memory can be copied from directly.  A unit that starts where the previous
+			// pinned unit ended is taken to be pinned too (one driver query per contiguous run, not per unit; a
+			// wrong guess only costs speed: cudaMemcpyAsync stages pageable memory itself)
+			bool pinned;
+			if (prev_pinned_end && u.ptr == prev_pinned_end) {
+				pinned = true;
+			} else {
+				cudaPointerAttributes attr;
+				pinned = cudaPointerGetAttributes(&attr, u.ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+				cudaGetLastError();
+			}
+			prev_pinned_end = pinned ? u.ptr + u.len : nullptr;
 			if (pinned) {
 				// host units that are contiguous in memory (and 256-byte multiples, so contiguous in the arena too) go as one copy
 				if (run_len && run_src + run_len == u.ptr && run_dst + run_len == dst && run_len < ((size_t)1 << 30)) {
@@ -591,7 +601,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
 		S.scan_kernel_ms += ms;
 		S.scan_launches++;
-		S.total_launches++;
+		S.total_launches += 2; // cursor fill + scan kernel
 		total_cand = *h_cursor;
 		if (total_cand <= A.cand_cap) break;
 		// candidate buffer too small: never truncate -- grow to what the kernel asked for and re-scan

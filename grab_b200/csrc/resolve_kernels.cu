@@ -127,7 +127,7 @@ __global__ void k_gather(const ResolveArgs R)
 // everything and give back one item at a time, lazy ones take one more on demand; explicit stack, no recursion.
 // `subj` is the subject as the reference's pcre_exec call sees it: it begins at the moving search start
 // (grab.cc:178), so ^, \A and \b at its first byte behave exactly as there.
-constexpr int kVmStack = 96;
+constexpr int kVmStack = 512; // entries of 12 bytes in thread-local memory; the VM walk runs in its own low-occupancy kernel
 constexpr uint32_t kVmMaxSteps = 1u << 24;
 
 __device__ __forceinline__ bool vm_in_set(const ResolveArgs &R, uint32_t set, uint32_t b) { return (R.vm_sets[set * 8 + (b >> 5)] >> (b & 31)) & 1u; }
@@ -243,39 +243,7 @@ __global__ void k_walk(const ResolveArgs R)
 	const uint32_t end = R.unit_start[u + 1];
 	uint32_t n = 0;
 	FinalRec *o = WRITE ? R.out + R.unit_out[u] : nullptr;
-	if (i != end && R.engine == GSCAN_ENGINE_VM) {
-		// general patterns: every match starts at a candidate (a leading-byte prefix hit).  The count pass runs the
-		// VM and records the outcome in the candidate array, the write pass only copies.
-		const DevUnit du = R.units[u];
-		if (!WRITE) {
-			const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
-			const uint64_t ulen = du.len;
-			uint64_t start = 0;
-			for (; i < end; i++) {
-				if (!(start + R.minlen < ulen)) break;                                  // grab.cc:175
-				const uint32_t pos = R.ord[i].pos;
-				if (pos < start) continue;
-				uint32_t e = 0;
-				const int rc = vm_exec(R, data + start, (uint32_t)(ulen - start), (uint32_t)(pos - start), &e); // grab.cc:178
-				if (rc < 0) { atomicOr(R.totals + 2, 1u); break; }                      // limits: reported, never guessed
-				if (rc == 0) continue;                                                  // next start offset, like PCRE
-				uint64_t me = start + e;
-				R.ord[i].len = (uint32_t)(me - pos);
-				R.ord[i].pad = 1;
-				n++;
-				if (R.mode == GSCAN_MODE_FIRST) break;
-				if (R.mode == GSCAN_MODE_LINE) {
-					uint32_t a = 0;
-					while (me + a < ulen && a < 511 && data[me + a] != '\n') a++;
-					me += a;
-				}
-				start = me;                                                             // grab.cc:209
-			}
-		} else {
-			for (; i < end; i++)
-				if (R.ord[i].pad) { FinalRec r; r.start = du.base_off + R.ord[i].pos; r.file_id = du.file_id; r.len = R.ord[i].len; o[n++] = r; }
-		}
-	} else if (i != end) {
+	if (i != end) {
 		const DevUnit du = R.units[u];
 		const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
 		const uint64_t ulen = du.len;
@@ -316,6 +284,52 @@ __global__ void k_walk(const ResolveArgs R)
 	if (!WRITE) R.unit_out[u] = n;
 }
 
+// general patterns: every match starts at a candidate (a leading-byte prefix hit).  The count pass runs the VM
+// and records the outcome in the candidate array, the write pass only copies.  Own kernel: the VM's backtrack
+// stack is thread-local memory, so occupancy is capped to keep the reservation small.
+template <bool WRITE>
+__global__ void __launch_bounds__(64, 4) k_walk_vm(const ResolveArgs R)
+{
+	const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= R.n_units) return;
+	uint32_t i = R.unit_start[u];
+	const uint32_t end = R.unit_start[u + 1];
+	uint32_t n = 0;
+	FinalRec *o = WRITE ? R.out + R.unit_out[u] : nullptr;
+	if (i != end) {
+		const DevUnit du = R.units[u];
+		if (!WRITE) {
+			const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
+			const uint64_t ulen = du.len;
+			uint64_t start = 0;
+			for (; i < end; i++) {
+				if (!(start + R.minlen < ulen)) break;                                  // grab.cc:175
+				const uint32_t pos = R.ord[i].pos;
+				if (pos < start) continue;
+				uint32_t e = 0;
+				const int rc = vm_exec(R, data + start, (uint32_t)(ulen - start), (uint32_t)(pos - start), &e); // grab.cc:178
+				if (rc < 0) { atomicOr(R.totals + 2, 1u); break; }                      // limits: reported, never guessed
+				if (rc == 0) continue;                                                  // next start offset, like PCRE
+				uint64_t me = start + e;
+				R.ord[i].len = (uint32_t)(me - pos);
+				R.ord[i].pad = 1;
+				n++;
+				if (R.mode == GSCAN_MODE_FIRST) break;
+				if (R.mode == GSCAN_MODE_LINE) {
+					uint32_t a = 0;
+					while (me + a < ulen && a < 511 && data[me + a] != '\n') a++;
+					me += a;
+				}
+				start = me;                                                             // grab.cc:209
+			}
+		} else {
+			for (; i < end; i++)
+				if (R.ord[i].pad) { FinalRec r; r.start = du.base_off + R.ord[i].pos; r.file_id = du.file_id; r.len = R.ord[i].len; o[n++] = r; }
+		}
+	}
+	if (!WRITE) R.unit_out[u] = n;
+}
+
 // ---- 4. generic u32 block sums / exclusive scan (per-unit match counts -> output slots) ----
 __global__ void k_u32_sums(const uint32_t *v, uint32_t n, uint32_t *blk)
 {
@@ -350,7 +364,9 @@ cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t
 	k_seg_sums<<<nb_seg, kScanBlock, 0, st>>>(R.segs, R.n_segs, R.tag, R.blk); nl++;
 	k_scan_blk<<<1, kScanBlock, 0, st>>>(R.blk, nb_seg, R.totals, R.unit_start + R.n_units); nl++;
 	k_gather<<<nb_seg, kScanBlock, 0, st>>>(R); nl++;
-	k_walk<false><<<(R.n_units + 127) / 128, 128, 0, st>>>(R); nl++;
+	if (R.engine == GSCAN_ENGINE_VM) k_walk_vm<false><<<(R.n_units + 63) / 64, 64, 0, st>>>(R);
+	else k_walk<false><<<(R.n_units + 127) / 128, 128, 0, st>>>(R);
+	nl++;
 	const uint32_t nb_u = (R.n_units + kPerBlock - 1) / kPerBlock;
 	uint32_t *blk2 = R.blk + nb_seg + 1; // block sums of the per-unit counts live behind the segment block sums
 	k_u32_sums<<<nb_u, kScanBlock, 0, st>>>(R.unit_out, R.n_units, blk2); nl++;
@@ -362,7 +378,8 @@ cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t
 
 cudaError_t launch_resolve_write(const ResolveArgs &R, cudaStream_t st, uint32_t *launches)
 {
-	k_walk<true><<<(R.n_units + 127) / 128, 128, 0, st>>>(R);
+	if (R.engine == GSCAN_ENGINE_VM) k_walk_vm<true><<<(R.n_units + 63) / 64, 64, 0, st>>>(R);
+	else k_walk<true><<<(R.n_units + 127) / 128, 128, 0, st>>>(R);
 	if (launches) *launches = 1;
 	return cudaGetLastError();
 }
