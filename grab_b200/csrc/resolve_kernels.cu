@@ -249,6 +249,12 @@ __global__ void k_walk(const ResolveArgs R)
 		const uint64_t ulen = du.len;
 		const bool run = R.engine == GSCAN_ENGINE_RUN;
 		uint64_t start = 0;
+		if (!WRITE && run && R.mode == GSCAN_MODE_ALL) {
+			// runs never touch each other (a non-class byte separates them), so in ALL mode every candidate is a
+			// match and the loop guard (grab.cc:175) can only bite before the first search: count without measuring
+			// the runs -- their lengths are only needed by the write pass
+			n = (R.minlen < ulen) ? end - i : 0u;
+		} else
 		for (;;) {
 			if (!(start + R.minlen < ulen)) break;                 // grab.cc:175 (strict '<': Q1)
 			uint64_t pos = 0, e = 0;
