@@ -12,6 +12,7 @@ One JSON line on stdout (rank 0).  Contract notes:
   cpu_baseline  the unmodified reference (oracle/_ref/grab_ref) timed on this box's host cores on a bounded sample
 """
 import argparse
+import ctypes
 import json
 import os
 import shutil
@@ -30,6 +31,10 @@ NEEDLE_EVERY = 64
 SEED = 2
 FILE_LEN = 1 << 20
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "grab_ref")
+
+
+def ctypes_memmove(dst, src, n):
+    ctypes.memmove(ctypes.c_void_p(dst), ctypes.c_void_p(src), n)
 
 
 def log(*a):
@@ -323,6 +328,20 @@ def main():
             line["parity"] = "MISMATCH(e2e)"
         line["e2e"] = {"value": e_files * FILE_LEN / e_dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(e_files * FILE_LEN + e_files * 32),
                        "d2h_bytes_per_step": int(len(re2e) * 16 + 24), "sample": "%d files x 1 MiB in pinned host memory" % e_files}
+        # the same call on PAGEABLE host memory (what the CLI's mmap windows are): staged by the engine's helper lanes
+        pag = np.empty(e_files * FILE_LEN, dtype=np.uint8)
+        ctypes_memmove(pag.ctypes.data, hptr, e_files * FILE_LEN)
+        punits = hunits.copy()
+        punits["ptr"] = pag.ctypes.data + np.arange(e_files, dtype=np.uint64) * np.uint64(FILE_LEN)
+        ctx.scan_units(pat, punits)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            rp = ctx.scan_units(pat, punits)
+        p_dt = (time.perf_counter() - t0) / 5
+        if rp.tobytes() != re2e.tobytes():
+            line["parity"] = "MISMATCH(e2e pageable)"
+        line["e2e"]["pageable_host_value"] = e_files * FILE_LEN / p_dt / 1e9
+        del pag
         G.lib().gscan_host_free(hptr)
 
         # ---- cpu baseline: the unmodified reference on this box's host cores ----

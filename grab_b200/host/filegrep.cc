@@ -9,6 +9,7 @@
 
 #include <cerrno>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 
@@ -180,6 +181,12 @@ int FileGrep::flush()
 	size_t n = 0;
 	int rc = gscan_scan_batch(d_ctx, d_pat, units.data(), units.size(), mode, &matches, &n);
 	if (rc < 0) d_err = std::string("FileGrep::find::scan: ") + gscan_why(d_ctx);
+	if (getenv("GRAB_B200_TRACE")) { // side channel on stderr only: stdout is the parity surface
+		gscan_stats st;
+		gscan_last_stats(d_ctx, &st);
+		fprintf(stderr, "[grab-b200] batch: %zu windows, %.1f MiB, staging+h2d %.2f ms, scan kernel %.3f ms, resolve %.3f ms, call %.2f ms, %zu matches\n",
+		        units.size(), (double)st.bytes_scanned / 1048576.0, st.h2d_ms, st.scan_kernel_ms, st.resolve_ms, st.total_ms, n);
+	}
 
 	// per window, in queue order: format, then flush under the lock (grab.cc:217-234)
 	std::vector<gscan_match_view> view;

@@ -97,6 +97,8 @@ int main(int argc, char **argv)
 			return -1;
 		}
 		chunk_size >>= 2; // main.cc:172-173
+		// every thread stages its own batches: keep the engine's helper lanes from oversubscribing the host
+		if (!getenv("GSCAN_STAGE_THREADS")) setenv("GSCAN_STAGE_THREADS", cores >= 8 ? "1" : "2", 1);
 		config["chunk_size"] = chunk_size;
 		files.reserve(1 << 20);
 		stats.reserve(1 << 20);
