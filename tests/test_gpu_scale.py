@@ -64,3 +64,46 @@ def test_sampled_files_match_oracle(env, pat):
     # linearity over units: scanning the sampled files as a separate device batch gives the same records
     stats = ctx.stats()
     assert stats["bytes_scanned"] == N_FILES * FILE_LEN
+
+
+def test_maximum_window_one_gib():
+    """One unit of the reference's largest window (1 GiB, grab.h:48): matches at the very start, across every 64 KiB tile
+    border region, and in the last bytes; Q1 at the window end."""
+    ctx = G.Context(0)
+    n = 1 << 30
+    a = np.full(n, ord("."), dtype=np.uint8)
+    a[79::80] = 10
+    nd = np.frombuffer(b"NEEDLE", dtype=np.uint8)
+    pos = [0, 65533, 65536, (1 << 20) - 3, (1 << 29) - 1, (1 << 30) - 4096 + 100, n - 12, n - 6]
+    for p in pos:
+        a[p:p + 6] = nd
+    d = ctx.device_alloc(n)
+    try:
+        ctx.h2d(d, a)
+        r = ctx.scan_units(G.Pattern("NEEDLE"), G.Context.device_units(d, 1, n))
+        # the needle that exactly fills the tail is found here because the search did not START there (Q1 needs start == n-6)
+        assert r["start"].tolist() == pos and set(r["match_len"].tolist()) == {6}
+        want = O.Regex("NEEDLE").scan_window(a.tobytes())
+        assert [(int(s), int(l)) for s, l in zip(r["start"], r["match_len"])] == want
+        r = ctx.scan_units(G.Pattern("[A-Z]{6,}"), G.Context.device_units(d, 1, n))
+        assert r["start"].tolist() == pos
+    finally:
+        ctx.device_free(d)
+        ctx.close()
+
+
+def test_oversized_unit_is_rejected_loudly():
+    ctx = G.Context(0)
+    u = np.zeros(1, dtype=G.UNIT_DTYPE)
+    u["ptr"] = 0x10000
+    u["len"] = (1 << 31) + 16
+    u["flags"] = G.UNIT_DEVICE
+    with pytest.raises(G.GscanError) as ei:
+        ctx.scan_units(G.Pattern("abc"), u)
+    assert "2 GiB" in str(ei.value)
+    u["len"] = 64
+    u["ptr"] = 0x10008  # misaligned device pointer
+    with pytest.raises(G.GscanError) as ei:
+        ctx.scan_units(G.Pattern("abc"), u)
+    assert "aligned" in str(ei.value)
+    ctx.close()
