@@ -74,7 +74,7 @@ def test_maximum_window_one_gib():
     a = np.full(n, ord("."), dtype=np.uint8)
     a[79::80] = 10
     nd = np.frombuffer(b"NEEDLE", dtype=np.uint8)
-    pos = [0, 65533, 65536, (1 << 20) - 3, (1 << 29) - 1, (1 << 30) - 4096 + 100, n - 12, n - 6]
+    pos = [0, 65531, 65600, (1 << 20) - 3, (1 << 29) - 1, (1 << 30) - 4096 + 100, n - 12, n - 6]
     for p in pos:
         a[p:p + 6] = nd
     d = ctx.device_alloc(n)
