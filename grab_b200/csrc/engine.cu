@@ -107,7 +107,7 @@ struct gscan_ctx {
 	uint64_t pat_id = 0;
 	FixedParams pat_fixed; // with this context's device pointers
 	HashParams pat_hash;
-	PinnedBuf readback, stage[2];
+	PinnedBuf readback;
 	DevBuf<unsigned long long> probe_sum;
 	DevBuf<uint8_t> needle;
 	// staging of pageable host memory (the reference's mmap windows): helper threads, each with its own stream,
@@ -309,7 +309,7 @@ extern "C" void gscan_close(gscan_ctx *c)
 	c->unit_start.release(); c->unit_out.release(); c->blk.release(); c->cursor.release(); c->pat_tables.release(); c->hash_tables.release(); c->vm_tables.release();
 	c->probe_sum.release(); c->needle.release();
 	c->pool_arena.release(); c->pool_tiles.release(); c->pool_units.release();
-	c->readback.release(); c->stage[0].release(); c->stage[1].release();
+	c->readback.release();
 	for (auto &rb : c->results) if (rb.p) cudaFreeHost(rb.p);
 	for (auto &l : c->lanes) {
 		for (int i = 0; i < 2; i++) { if (l.buf[i]) cudaFreeHost(l.buf[i]); if (l.ev[i]) cudaEventDestroy(l.ev[i]); }
@@ -580,6 +580,8 @@ static int ensure_pattern(gscan_ctx *ctx, const gscan_pattern *pat)
 			ctx->pat_hash.seq_pos = ctx->pat_fixed.seq_pos;
 			ctx->pat_hash.cls_bm = ctx->pat_fixed.cls_bm;
 		}
+	}
+	{
 		if (pat->prog.use_vm) {
 			const size_t nc = pat->prog.vm_code.size() * 4, nsb = pat->prog.vm_sets.size() * 4;
 			CK(ctx, ctx->vm_tables.ensure(nc + nsb + 64));
@@ -694,6 +696,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		R.engine = pat->prog.use_vm ? (uint32_t)GSCAN_ENGINE_VM : (uint32_t)pat->prog.kind;
 		R.vm_code = ctx->vm_code;
 		R.vm_sets = ctx->vm_sets;
+		R.vm_runstart = pat->prog.vm_runstart ? 1u : 0u;
 		R.run_min = (uint32_t)pat->prog.run_min;
 		for (int i = 0; i < 8; i++) R.bitmap[i] = pat->prog.run_class.w[i];
 		R.total_cand = (uint32_t)total_cand;

@@ -51,6 +51,7 @@ struct ResolveArgs {
 	uint32_t total_cand;  // known on the host after the scan kernel
 	const uint32_t *vm_code; // general patterns: VM program (3 words per instruction) and byte classes (8 words each)
 	const uint32_t *vm_sets;
+	uint32_t vm_runstart; // candidates are run starts of `bitmap`: also try the search start itself when it lies inside a run
 };
 // count pass: segment scan, gather, per-unit replay that counts, slot scan; totals[1] = number of matches
 cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t *launches);

@@ -913,6 +913,38 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 		g.gen(root.get());
 		g.emit(VM_MATCH, 0, 0, 0, 0);
 		if (g.failed) { err = g.why; return false; }
+		// a pattern that begins with a greedy/lazy/possessive byte-class repeat C{n,}: if an attempt succeeds anywhere
+		// inside a run of C it also succeeds at the run's first byte (C{n,} simply takes the bytes in between), so
+		// PCRE's leftmost match starts at a run start -- or at the search start itself when that lies inside a run.
+		// Candidates are then the run starts (RUN scan kernel), far fewer than "every byte of the class".
+		{
+			const Node *top = peel(root.get());
+			if (top->kind == Node::CAT && top->kids.size() >= 2) {
+				const Node *lead = top->kids[0].get();
+				while (lead->kind == Node::GROUP) lead = lead->kids[0].get();
+				const Node *body = lead->kind == Node::REP ? peel(lead->kids[0].get()) : nullptr;
+				if (body && body->kind == Node::SET && !body->set.empty() && lead->rmin >= 1 && lead->rmax == kInf && lead->rmin <= (uint32_t)kMaxPatternLen) {
+					std::vector<ByteRange> lo, hi;
+					for (auto r : to_ranges(body->set)) {
+						if (r.lo < 0x80) lo.push_back(ByteRange{r.lo, (uint8_t)std::min<int>(r.hi, 0x7f)});
+						if (r.hi >= 0x80) hi.push_back(ByteRange{(uint8_t)std::max<int>(r.lo, 0x80), r.hi});
+					}
+					if ((int)lo.size() <= kMaxRunRangesLow && (int)hi.size() <= kMaxRunRangesHigh) {
+						out.kind = ENGINE_RUN;
+						out.run_class = body->set;
+						out.run_min = (int)lead->rmin;
+						out.ranges_low = lo;
+						out.ranges_high = hi;
+						out.maxlen = -1;
+						out.use_vm = true;
+						out.vm_runstart = true;
+						out.vm_code = g.code;
+						for (auto &s : g.sets) for (int i = 0; i < 8; i++) out.vm_sets.push_back(s.w[i]);
+						return true;
+					}
+				}
+			}
+		}
 		std::vector<Pref> pf;
 		if (!prefixes(root.get(), 4, pf) || pf.empty()) { err = "pattern has too many distinct leading byte sequences for the candidate filter"; return false; }
 		seqs.clear();

@@ -96,6 +96,7 @@ struct Program {
 
 	// general patterns: seqs are the leading-byte prefixes (candidate filter), matches are decided by the VM
 	bool use_vm = false;
+	bool vm_runstart = false;      // candidates are the starts of runs of run_class (pattern begins with C{n,})
 	std::vector<uint32_t> vm_code; // 3 words per instruction
 	std::vector<uint32_t> vm_sets; // 8 words per byte class
 

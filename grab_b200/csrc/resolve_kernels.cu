@@ -302,7 +302,44 @@ __global__ void __launch_bounds__(64, 4) k_walk_vm(const ResolveArgs R)
 	const uint32_t end = R.unit_start[u + 1];
 	uint32_t n = 0;
 	FinalRec *o = WRITE ? R.out + R.unit_out[u] : nullptr;
-	if (i != end) {
+	if (i != end && R.vm_runstart) {
+		// candidates are run starts; a match may also begin at the search start when that lies inside a run, so the
+		// outcome cannot be recorded in the candidate array: both passes replay the loop (the VM runs twice)
+		const DevUnit du = R.units[u];
+		const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
+		const uint64_t ulen = du.len;
+		uint64_t start = 0;
+		for (;;) {
+			if (!(start + R.minlen < ulen)) break;                                      // grab.cc:175
+			uint64_t pos = 0;
+			uint32_t e = 0;
+			bool found = false;
+			if (start > 0 && in_class(R, data[start - 1]) && in_class(R, data[start])) {
+				const int rc = vm_exec(R, data + start, (uint32_t)(ulen - start), 0u, &e);
+				if (rc < 0) { atomicOr(R.totals + 2, 1u); break; }
+				if (rc == 1) { pos = start; found = true; }
+			}
+			while (!found) {
+				while (i < end && R.ord[i].pos < start) i++;
+				if (i == end) break;
+				pos = R.ord[i++].pos;
+				const int rc = vm_exec(R, data + start, (uint32_t)(ulen - start), (uint32_t)(pos - start), &e); // grab.cc:178
+				if (rc < 0) { atomicOr(R.totals + 2, 1u); i = end; break; }
+				found = rc == 1;
+			}
+			if (!found) break;
+			uint64_t me = start + e;
+			if (WRITE) { FinalRec r; r.start = du.base_off + pos; r.file_id = du.file_id; r.len = (uint32_t)(me - pos); o[n] = r; }
+			n++;
+			if (R.mode == GSCAN_MODE_FIRST) break;
+			if (R.mode == GSCAN_MODE_LINE) {
+				uint32_t a = 0;
+				while (me + a < ulen && a < 511 && data[me + a] != '\n') a++;
+				me += a;
+			}
+			start = me;                                                                 // grab.cc:209
+		}
+	} else 	if (i != end) {
 		const DevUnit du = R.units[u];
 		if (!WRITE) {
 			const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);

@@ -89,7 +89,9 @@ DIFF_PATTERNS = ["ab", "aa", "aba", "abab", "a", "abc|bc|c", "ab|abc", "abc|ab",
                  "a[ab]c|b[bc]a|c[ac]b|ab[ab]|ba[bc]", "abca|abcb|bcab|bcaa|cabc|caba|aabb|bbaa|ccaa",
                  # general patterns: leading-byte scan + backtracking VM on the device
                  "ab*c", "a+b", "(?:ab)+c", "a.*b", "a.*?b", "^ab", "ab$", "\\bab", "ab\\b", "c[ab]+c[ab]*", "a(?:b|c)*a", "ab+?b", "(?:a|ab)(?:c|bcd)(?:d*)",
-                 "^a", "a$", "b\\Ba", "(?m)^ab", "(?m)ab$", "a{2,}b", "(?:ab|a)*c", "a[^\\n]*c", "ab??c", "(?s)a.b"]
+                 "^a", "a$", "b\\Ba", "(?m)^ab", "(?m)ab$", "a{2,}b", "(?:ab|a)*c", "a[^\\n]*c", "ab??c", "(?s)a.b",
+                 # patterns that begin with a byte-class run: candidates are run starts (+ the search start inside a run)
+                 "[ab]+c", "a+?b", "[ab]{2,}c+", "b+(?:a|c)", "[a-c]+ [a-c]+", "a++b", "[ab]+b", "[^c\\n]+c", "a+a", "[ab]+?[bc]{2}"]
 
 
 @pytest.mark.parametrize("pat", DIFF_PATTERNS)
