@@ -626,9 +626,9 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	CK(ctx, ctx->scratch.ensure((size_t)ctx->num_sms * geom.warps * geom.slice));
 	CK(ctx, ctx->cursor.ensure(2));
 	CK(ctx, ctx->readback.ensure(64));
-	if (ctx->cand.cap == 0) {
-		size_t want = std::min<size_t>(std::max<size_t>(b->bytes / 2048, 1u << 20), 64u << 20);
-		CK(ctx, ctx->cand.ensure(want));
+	{ // candidate buffer: sized to the batch (1 per 2 KiB, 1 Mi .. 64 Mi entries); grown on demand by the retry loop below
+		const size_t want = std::min<size_t>(std::max<size_t>(b->bytes / 2048, 1u << 20), 64u << 20);
+		if (ctx->cand.cap < want) CK(ctx, ctx->cand.ensure(want));
 	}
 
 	ScanArgs A;

@@ -3,6 +3,9 @@ import ctypes
 import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if not os.path.exists(os.path.join(ROOT, "oracle", "libgrab_oracle.so")):  # test infrastructure: gcc, <1 s
+    import subprocess
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=True, stdout=subprocess.DEVNULL)
 _lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "libgrab_oracle.so"))
 _libc = ctypes.CDLL(None)
 
