@@ -90,6 +90,7 @@ struct RunParams {
 	uint32_t nlo, nhi;
 	uint32_t add_ge_lo[8], add_gt_lo[8]; // (0x80-lo)*0x01010101, (0x7f-hi)*0x01010101 for ranges in 0x00-0x7f
 	uint32_t add_ge_hi[2], add_gt_hi[2]; // same for ranges in 0x80-0xff (after clearing bit 7)
+	uint32_t nfold, add_ge_fold, add_gt_fold; // one pair of ranges that differ only in bit 5, tested once on x | 0x20
 	uint32_t run_min;
 	uint32_t sh[5];      // w &= w >> sh[i], i = 0..4: leaves the bits where min(run_min, 17) ones start (0 = no-op)
 	uint32_t bitmap[8];

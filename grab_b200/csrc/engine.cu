@@ -220,11 +220,26 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 	} else if (pr.kind == ENGINE_RUN) {
 		RunParams &R = p->run;
 		R.one = 1;
-		R.nlo = (uint32_t)pr.ranges_low.size();
+		// two low ranges [a,b] and [a+0x20,b+0x20] inside one 64-byte block with bit 5 clear / set throughout
+		// ([A-Z] and [a-z]) collapse into one test of x | 0x20 against the upper range: exact, one range cheaper
+		std::vector<ByteRange> low = pr.ranges_low;
+		R.nfold = 0;
+		for (size_t i = 0; i < low.size() && !R.nfold; i++)
+			for (size_t j = 0; j < low.size() && !R.nfold; j++) {
+				const ByteRange a = low[i], b = low[j];
+				if (i != j && b.lo == a.lo + 0x20 && b.hi == a.hi + 0x20 && !(a.lo & 0x20) && !(a.hi & 0x20) && (a.lo >> 6) == (a.hi >> 6)) {
+					R.nfold = 1;
+					R.add_ge_fold = rep4((uint8_t)(0x80 - b.lo));
+					R.add_gt_fold = rep4((uint8_t)(0x7f - b.hi));
+					low.erase(low.begin() + (long)std::max(i, j));
+					low.erase(low.begin() + (long)std::min(i, j));
+				}
+			}
+		R.nlo = (uint32_t)low.size();
 		R.nhi = (uint32_t)pr.ranges_high.size();
-		for (size_t i = 0; i < pr.ranges_low.size(); i++) {
-			R.add_ge_lo[i] = rep4((uint8_t)(0x80 - pr.ranges_low[i].lo));
-			R.add_gt_lo[i] = rep4((uint8_t)(0x7f - pr.ranges_low[i].hi));
+		for (size_t i = 0; i < low.size(); i++) {
+			R.add_ge_lo[i] = rep4((uint8_t)(0x80 - low[i].lo));
+			R.add_gt_lo[i] = rep4((uint8_t)(0x7f - low[i].hi));
 		}
 		for (size_t i = 0; i < pr.ranges_high.size(); i++) {
 			R.add_ge_hi[i] = rep4((uint8_t)(0x80 - (pr.ranges_high[i].lo - 0x80)));

@@ -509,7 +509,7 @@ struct HashEngine {
 // ------------------------------------------------------------------------------------------
 // RUN engine: one byte class repeated {n,}: one candidate per maximal run of >= n class bytes
 // ------------------------------------------------------------------------------------------
-template <int NLO, int NHI>
+template <int NLO, int NHI, int NFO>
 struct RunEngine {
 	typedef RunParams Params;
 	static constexpr bool kLookBehind = true, kLookAhead = true;
@@ -526,6 +526,11 @@ struct RunEngine {
 			const uint32_t ge = r == 0 ? x7 + P.add_ge_lo[r] : x7 * P.one + P.add_ge_lo[r];
 			const uint32_t gt = x7 * P.one + P.add_gt_lo[r];
 			lo |= ge & ~gt;
+		}
+		if (NFO) {
+			// one range test serves two ranges that differ only in bit 5 ([A-Z] and [a-z]): test x | 0x20 against the upper one
+			const uint32_t y = x7 | 0x20202020u;
+			lo |= (y * P.one + P.add_ge_fold) & ~(y * P.one + P.add_gt_fold);
 		}
 #pragma unroll
 		for (int r = 0; r < NHI; r++) hi |= (x7 * P.one + P.add_ge_hi[r]) & ~(x7 * P.one + P.add_gt_hi[r]);
@@ -874,25 +879,32 @@ cudaError_t launch_scan_fixed(const ScanArgs &A, const FixedParams &P, int delta
 	}
 }
 
-template <int NHI>
-static cudaError_t launch_run_h(const ScanArgs &A, const RunParams &P, const ScanGeom &g, int grid, cudaStream_t st)
+template <int NHI, int NFO>
+static cudaError_t launch_run_hf(const ScanArgs &A, const RunParams &P, const ScanGeom &g, int grid, cudaStream_t st)
 {
 	switch (P.nlo) {
-	case 0: case 1: return launch<RunEngine<1, NHI>, false>(A, P, g, grid, st);
-	case 2: return launch<RunEngine<2, NHI>, false>(A, P, g, grid, st);
-	case 3: return launch<RunEngine<3, NHI>, false>(A, P, g, grid, st);
-	case 4: return launch<RunEngine<4, NHI>, false>(A, P, g, grid, st);
-	case 5: case 6: return launch<RunEngine<6, NHI>, false>(A, P, g, grid, st);
-	default: return launch<RunEngine<8, NHI>, false>(A, P, g, grid, st);
+	case 0: case 1: return launch<RunEngine<1, NHI, NFO>, false>(A, P, g, grid, st);
+	case 2: return launch<RunEngine<2, NHI, NFO>, false>(A, P, g, grid, st);
+	case 3: return launch<RunEngine<3, NHI, NFO>, false>(A, P, g, grid, st);
+	case 4: return launch<RunEngine<4, NHI, NFO>, false>(A, P, g, grid, st);
+	case 5: case 6: return launch<RunEngine<6, NHI, NFO>, false>(A, P, g, grid, st);
+	default: return launch<RunEngine<8, NHI, NFO>, false>(A, P, g, grid, st);
 	}
 }
 
 cudaError_t launch_scan_run(const ScanArgs &A, const RunParams &P, const ScanGeom &g, int grid, cudaStream_t st)
 {
+	if (P.nfold) {
+		switch (P.nhi) {
+		case 0: return launch_run_hf<0, 1>(A, P, g, grid, st);
+		case 1: return launch_run_hf<1, 1>(A, P, g, grid, st);
+		default: return launch_run_hf<2, 1>(A, P, g, grid, st);
+		}
+	}
 	switch (P.nhi) {
-	case 0: return launch_run_h<0>(A, P, g, grid, st);
-	case 1: return launch_run_h<1>(A, P, g, grid, st);
-	default: return launch_run_h<2>(A, P, g, grid, st);
+	case 0: return launch_run_hf<0, 0>(A, P, g, grid, st);
+	case 1: return launch_run_hf<1, 0>(A, P, g, grid, st);
+	default: return launch_run_hf<2, 0>(A, P, g, grid, st);
 	}
 }
 
