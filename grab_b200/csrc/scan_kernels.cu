@@ -29,6 +29,10 @@
 #include "swar.h"
 #include "kernels.h"
 
+#ifndef GS_RUN_STREAM
+#define GS_RUN_STREAM 0
+#endif
+
 namespace gscan {
 
 // ------------------------------------------------------------------------------------------
@@ -824,7 +828,7 @@ static cudaError_t launch(const ScanArgs &A, const typename Eng::Params &P, cons
 ScanGeom scan_geom(int engine, uint32_t n_tests_or_ranges)
 {
 	if (engine == 4 /*FIXED, hashed*/) return ScanGeom{GeomHash::kWarps, GeomHash::kRing, GeomHash::kSlice};
-	if (engine == 1 /*FIXED*/) return ScanGeom{GeomStream::kWarps, GeomStream::kRing, GeomStream::kSlice};
+	if (engine == 1 /*FIXED*/ || (engine == 2 && GS_RUN_STREAM)) return ScanGeom{GeomStream::kWarps, GeomStream::kRing, GeomStream::kSlice};
 	return ScanGeom{GeomBalanced::kWarps, GeomBalanced::kRing, GeomBalanced::kSlice};
 }
 
@@ -879,16 +883,21 @@ cudaError_t launch_scan_fixed(const ScanArgs &A, const FixedParams &P, int delta
 	}
 }
 
+#ifndef GS_RUN_STREAM
+#define GS_RUN_STREAM 0
+#endif
+constexpr bool kRunStream = GS_RUN_STREAM != 0; // RUN on the 4 KiB-slice geometry (tuning switch)
+
 template <int NHI, int NFO>
 static cudaError_t launch_run_hf(const ScanArgs &A, const RunParams &P, const ScanGeom &g, int grid, cudaStream_t st)
 {
 	switch (P.nlo) {
-	case 0: case 1: return launch<RunEngine<1, NHI, NFO>, false>(A, P, g, grid, st);
-	case 2: return launch<RunEngine<2, NHI, NFO>, false>(A, P, g, grid, st);
-	case 3: return launch<RunEngine<3, NHI, NFO>, false>(A, P, g, grid, st);
-	case 4: return launch<RunEngine<4, NHI, NFO>, false>(A, P, g, grid, st);
-	case 5: case 6: return launch<RunEngine<6, NHI, NFO>, false>(A, P, g, grid, st);
-	default: return launch<RunEngine<8, NHI, NFO>, false>(A, P, g, grid, st);
+	case 0: case 1: return launch<RunEngine<1, NHI, NFO>, kRunStream>(A, P, g, grid, st);
+	case 2: return launch<RunEngine<2, NHI, NFO>, kRunStream>(A, P, g, grid, st);
+	case 3: return launch<RunEngine<3, NHI, NFO>, kRunStream>(A, P, g, grid, st);
+	case 4: return launch<RunEngine<4, NHI, NFO>, kRunStream>(A, P, g, grid, st);
+	case 5: case 6: return launch<RunEngine<6, NHI, NFO>, kRunStream>(A, P, g, grid, st);
+	default: return launch<RunEngine<8, NHI, NFO>, kRunStream>(A, P, g, grid, st);
 	}
 }
 
