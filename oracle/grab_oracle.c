@@ -755,12 +755,18 @@ static int check_assert(int kind, const uint8_t *s, size_t len, size_t sp)
 }
 
 /* one anchored attempt at offset `at`; returns 1 and *e on success, 0 on failure, -1 on limit */
+/* PCRE bounds its search (match limit, 10 million by default); so does the oracle, or a pathological pattern
+ * would keep a test busy for hours.  Hitting the limit is reported (-1), never turned into an answer. */
+#define GO_MATCH_LIMIT 20000000ul
+
 static int attempt(const go_regex *re, const uint8_t *s, size_t len, size_t at, size_t *e, btstack *st)
 {
 	uint32_t pc = 0;
 	size_t sp = at;
+	unsigned long steps = 0;
 	st->n = 0;
 	for (;;) {
+		if (++steps > GO_MATCH_LIMIT) return -1;
 		const inst *in = &re->prog[pc];
 		int fail = 0;
 		switch (in->op) {
@@ -889,6 +895,7 @@ int go_scan_window(const go_regex *re, const uint8_t *w, size_t clen, uint64_t b
 	while (start + minlen < clen) {                         /* grab.cc:175  (strict <  => Q1) */
 		size_t s = 0, e = 0;
 		int rc = go_exec(re, w + start, clen - start, &s, &e); /* grab.cc:178 */
+		if (rc < 0) return -1;                                /* oracle's own match limit: report, do not guess */
 		if (rc == 1 && strict_q2 && re->ncapture > 0) rc = 0; /* ovecsize 3 too small => rc 0 */
 		if (rc <= 0) break;                                   /* grab.cc:179 */
 		if (push_match(out, base_off + start + s, (uint32_t)(e - s), unit) < 0) return -1;
@@ -920,6 +927,7 @@ int go_grab_buffer(const go_regex *re, const go_opts *o, const uint8_t *file, si
 		while (start + minlen < clen) {                       /* grab.cc:175 */
 			size_t s = 0, e = 0;
 			int rc = go_exec(re, w + start, clen - start, &s, &e);
+			if (rc < 0) return -1;
 			if (rc == 1 && o->strict_q2 && re->ncapture > 0) rc = 0;
 			if (rc <= 0) break;
 			if (o->path_prefix) { fputs(o->path_prefix, out); fputc(':', out); } /* :182-183 */
