@@ -18,6 +18,11 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
+    # a pathological random pattern must fail its test, not hold the suite (pytest-timeout is installed in this image)
+    if config.pluginmanager.hasplugin("timeout"):
+        for it in items:
+            if not any(m.name == "timeout" for m in it.iter_markers()):
+                it.add_marker(pytest.mark.timeout(600))
     try:
         import torch
         has_gpu = torch.cuda.is_available()
