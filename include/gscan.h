@@ -116,7 +116,8 @@ const char *gscan_why(const gscan_ctx *ctx);
  * loop emits, including the tail off-by-one (Q1) and, since every unit is scanned statelessly,
  * the chunk-overlap duplicates/phantoms (Q3).  Host buffers are fully consumed before the call
  * returns (the reference munmap()s right after the loop, grab.cc:215).
- * *out is owned by the context until gscan_free_matches().  Returns 0 / -1 (gscan_why). */
+ * *out points into a pinned result buffer owned by the context: valid until gscan_free_matches() or gscan_close(),
+ * whichever comes first (a second scan before freeing gets a different buffer).  Returns 0 / -1 (gscan_why). */
 int gscan_scan_batch(gscan_ctx *ctx, const gscan_pattern *pat, const gscan_unit *units, size_t n_units,
                      uint32_t mode, gscan_match **out, size_t *n_out);
 void gscan_free_matches(gscan_ctx *ctx, gscan_match *m);
