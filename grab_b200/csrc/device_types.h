@@ -73,8 +73,6 @@ struct HashParams {
 	uint32_t slot_mask;  // (slots - 1) << 2
 	uint32_t key_mask;   // 0xffff or 0xffffff
 	uint32_t nslots;
-	uint32_t replicated; // shared-memory table holds 32 copies, entry of (slot, lane) at (slot * 32 + lane) * 4: every lane
-	                     // reads its own bank, no conflicts (tables of <= 512 slots)
 	const uint32_t *table;      // [nslots] key or 0xffffffff (copied to shared memory at kernel start)
 	const uint32_t *slot_first; // [nslots] first index into slot_seqs
 	const uint32_t *slot_count; // [nslots]

@@ -212,7 +212,6 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 			HashParams &H = p->hash;
 			H.mul = pr.hash_mul;
 			H.nslots = pr.hash_slots;
-			H.replicated = pr.hash_slots <= 512 ? 1u : 0u;
 			H.slot_mask = (pr.hash_slots - 1) << 2;
 			H.key_mask = pr.hash_len == 2 ? 0xffffu : 0xffffffu;
 			H.uniform_len = F.uniform_len;
@@ -653,7 +652,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	A.cursor = ctx->cursor.p;
 	A.segs = ctx->segs.p;
 	A.scratch = ctx->scratch.p;
-	A.extra_smem = hashed ? pat->prog.hash_slots * 4u * (pat->hash.replicated ? 32u : 1u) : 0u;
+	A.extra_smem = hashed ? pat->prog.hash_slots * 4u : 0u;
 	A.tag = ctx->seg_tag;
 
 	unsigned long long *h_cursor = reinterpret_cast<unsigned long long *>(ctx->readback.p);

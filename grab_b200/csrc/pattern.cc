@@ -806,9 +806,7 @@ bool build_hash(Program &out, int L)
 	while (slots < 2 * distinct.size()) slots <<= 1;
 	uint64_t rng = 0x9E3779B97F4A7C15ull ^ (distinct.size() * 0xD1B54A32D192ED03ull);
 	for (; slots <= 8192; slots <<= 1) {
-		// small tables can be replicated per shared-memory bank (conflict-free lookups): worth a long search
-		const int tries = slots <= 512 ? 400000 : 4000;
-		for (int attempt = 0; attempt < tries; attempt++) {
+		for (int attempt = 0; attempt < 4000; attempt++) {
 			rng = rng * 6364136223846793005ull + 1442695040888963407ull;
 			const uint32_t mul = (uint32_t)(rng >> 32) | 1u;
 			std::vector<uint32_t> table(slots, 0xffffffffu);

@@ -414,8 +414,7 @@ struct HashEngine {
 	static __device__ __forceinline__ void prologue(const HashParams &P, uint8_t *extra)
 	{
 		uint32_t *t = reinterpret_cast<uint32_t *>(extra);
-		if (P.replicated) for (uint32_t i = threadIdx.x; i < P.nslots * 32u; i += blockDim.x) t[i] = P.table[i >> 5];
-		else for (uint32_t i = threadIdx.x; i < P.nslots; i += blockDim.x) t[i] = P.table[i];
+		for (uint32_t i = threadIdx.x; i < P.nslots; i += blockDim.x) t[i] = P.table[i];
 		__syncthreads();
 	}
 
@@ -449,15 +448,8 @@ struct HashEngine {
 		return (k ? __funnelshift_r(lo, hi, 8 * k) : lo) & P.key_mask;
 	}
 
-	// table entry for key y.  lane_off = lane * 4 when the table is replicated per bank (entry of (slot, lane) at
-	// (slot * 32 + lane) * 4: the multiply-add is an IMAD on the FMA pipe), 0 and scale 1 otherwise.
-	static __device__ __forceinline__ uint32_t lookup(const HashParams &P, const uint8_t *tbl, uint32_t y, uint32_t scale, uint32_t lane_off)
-	{
-		return *reinterpret_cast<const uint32_t *>(tbl + (__umulhi(y, P.mul) & P.slot_mask) * scale + lane_off);
-	}
-
 	// min over the 16 positions of (table[slot(key)] ^ key): zero <=> some position holds a key of the set
-	static __device__ __forceinline__ uint32_t row_min(const HashParams &P, const uint8_t *tbl, const uint32_t (&w)[5], uint32_t scale, uint32_t lane_off)
+	static __device__ __forceinline__ uint32_t row_min(const HashParams &P, const uint8_t *tbl, const uint32_t (&w)[5])
 	{
 		uint32_t mn = 0xffffffffu;
 #pragma unroll
@@ -465,7 +457,8 @@ struct HashEngine {
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
 				const uint32_t y = key_at(P, w[j], w[j + 1], k);
-				mn = min(mn, lookup(P, tbl, y, scale, lane_off) ^ y);
+				const uint32_t e = *reinterpret_cast<const uint32_t *>(tbl + (__umulhi(y, P.mul) & P.slot_mask));
+				mn = min(mn, e ^ y);
 			}
 		}
 		return mn;
@@ -476,13 +469,13 @@ struct HashEngine {
 	                                                 uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4)
 	{
 		const uint32_t w[5] = {w0, w1, w2, w3, w4};
-		const uint32_t scale = P.replicated ? 32u : 1u, lane_off = P.replicated ? lane * 4u : 0u;
 		uint32_t mm = 0;
 		uint32_t hits = 0; // positions whose leading bytes are a key of the set (unrolled: straight-line, no divergence yet)
 #pragma unroll
 		for (int b = 0; b < 16; b++) {
 			const uint32_t y = key_at(P, w[b >> 2], w[(b >> 2) + 1], b & 3);
-			hits |= (lookup(P, tbl, y, scale, lane_off) == y ? 1u : 0u) << b;
+			const uint32_t e = *reinterpret_cast<const uint32_t *>(tbl + (__umulhi(y, P.mul) & P.slot_mask));
+			hits |= (e == y ? 1u : 0u) << b;
 		}
 		while (hits) { // verify() is out of line: one copy, the kernel stays instruction-cache resident
 			const int b = __ffs(hits) - 1;
@@ -504,14 +497,13 @@ struct HashEngine {
 	{
 		const uint8_t *tbl = S.extra;
 		const uint32_t base = S.begin + lane * 16;
-		const uint32_t scale = P.replicated ? 32u : 1u, lane_off = P.replicated ? lane * 4u : 0u;
 		for (uint32_t it = 0; it < S.niter; it++) {
 			const uint32_t c0 = base + it * 512;
 			uint32_t w[5];
 			const uint4 a = *reinterpret_cast<const uint4 *>(S.tile + c0);
 			w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
 			w[4] = *reinterpret_cast<const uint32_t *>(S.tile + c0 + 16);
-			const uint32_t mn = row_min(P, tbl, w, scale, lane_off);
+			const uint32_t mn = row_min(P, tbl, w);
 			if (__any_sync(0xffffffffu, mn == 0))
 				E.n += slow_row(P, tbl, S.gtile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, c0, w[0], w[1], w[2], w[3], w[4]);
 		}
