@@ -596,16 +596,14 @@ static int ensure_pattern(gscan_ctx *ctx, const gscan_pattern *pat)
 			ctx->pat_hash.cls_bm = ctx->pat_fixed.cls_bm;
 		}
 	}
-	{
-		if (pat->prog.use_vm) {
-			const size_t nc = pat->prog.vm_code.size() * 4, nsb = pat->prog.vm_sets.size() * 4;
-			CK(ctx, ctx->vm_tables.ensure(nc + nsb + 64));
-			CK(ctx, cudaMemcpyAsync(ctx->vm_tables.p, pat->prog.vm_code.data(), nc, cudaMemcpyHostToDevice, ctx->stream));
-			CK(ctx, cudaMemcpyAsync(ctx->vm_tables.p + nc, pat->prog.vm_sets.data(), nsb, cudaMemcpyHostToDevice, ctx->stream));
-			CK(ctx, cudaStreamSynchronize(ctx->stream));
-			ctx->vm_code = reinterpret_cast<const uint32_t *>(ctx->vm_tables.p);
-			ctx->vm_sets = reinterpret_cast<const uint32_t *>(ctx->vm_tables.p + nc);
-		}
+	if (pat->prog.use_vm) { // general patterns (either scan engine): VM program and byte classes
+		const size_t nc = pat->prog.vm_code.size() * 4, nsb = pat->prog.vm_sets.size() * 4;
+		CK(ctx, ctx->vm_tables.ensure(nc + nsb + 64));
+		CK(ctx, cudaMemcpyAsync(ctx->vm_tables.p, pat->prog.vm_code.data(), nc, cudaMemcpyHostToDevice, ctx->stream));
+		CK(ctx, cudaMemcpyAsync(ctx->vm_tables.p + nc, pat->prog.vm_sets.data(), nsb, cudaMemcpyHostToDevice, ctx->stream));
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		ctx->vm_code = reinterpret_cast<const uint32_t *>(ctx->vm_tables.p);
+		ctx->vm_sets = reinterpret_cast<const uint32_t *>(ctx->vm_tables.p + nc);
 	}
 	ctx->pat_id = pat->prog.id;
 	return 0;
