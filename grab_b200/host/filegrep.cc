@@ -8,10 +8,14 @@
 #include <unistd.h>
 
 #include <cerrno>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <iostream>
+#include <mutex>
+#include <thread>
 
 #include "../../include/gscan.h"
 
@@ -22,6 +26,28 @@ static pthread_mutex_t g_stdout_lock = PTHREAD_MUTEX_INITIALIZER;
 
 static const char kStartInv[] = "\33[7m", kStopInv[] = "\33[27m"; // grab.cc:66-67
 
+// One batch of queued windows on its way through a lane.
+struct FileGrep::Batch {
+	uint64_t seq = 0;
+	std::vector<Window> windows;
+};
+
+// Job queue + output sequencer shared by the walking thread and the lanes of one FileGrep.
+struct FileGrep::Pipeline {
+	std::mutex mu;
+	std::condition_variable cv_job, cv_space, cv_turn, cv_idle;
+	std::deque<Batch *> jobs;
+	uint64_t next_seq = 0, next_out = 0; // next batch number to submit / to print
+	size_t inflight = 0;                 // submitted and not yet printed
+	bool stop = false, failed = false;
+	std::string err;
+	// -s: once a window of a file has printed, the rest of that file prints nothing (grab.cc:232-233); owned by
+	// whoever holds the output turn
+	bool have_done = false;
+	uint32_t done_seq = 0;
+	std::vector<std::thread> lanes;
+};
+
 FileGrep::FileGrep() : FileGrep(0) {}
 
 FileGrep::FileGrep(int device) : d_device(device) { d_my_uid = geteuid(); }
@@ -29,8 +55,15 @@ FileGrep::FileGrep(int device) : d_device(device) { d_my_uid = geteuid(); }
 FileGrep::~FileGrep()
 {
 	flush();
+	if (d_pipe) {
+		{
+			std::lock_guard<std::mutex> g(d_pipe->mu);
+			d_pipe->stop = true;
+		}
+		d_pipe->cv_job.notify_all();
+		for (auto &t : d_pipe->lanes) t.join();
+	}
 	if (d_pat) gscan_free_pattern(d_pat);
-	if (d_ctx) gscan_close(d_ctx);
 }
 
 void FileGrep::config(const std::map<std::string, size_t> &config)
@@ -46,6 +79,12 @@ void FileGrep::config(const std::map<std::string, size_t> &config)
 	if (it != config.end()) d_chunk_size = it->second;
 	it = config.find("device");
 	if (it != config.end()) d_device = (int)it->second;
+	it = config.find("batch_bytes");
+	if (it != config.end() && it->second >= 1) d_batch_bytes = it->second;
+	it = config.find("ndev");
+	if (it != config.end() && it->second >= 1) d_ndev = (int)it->second;
+	it = config.find("lanes");
+	if (it != config.end() && it->second >= 1) d_lanes_per_dev = (int)it->second;
 }
 
 int FileGrep::prepare(const std::string &regex)
@@ -58,17 +97,6 @@ int FileGrep::prepare(const std::string &regex)
 		return -1;
 	}
 	d_minlen = gscan_minlen(d_pat);
-	return 0;
-}
-
-int FileGrep::ensure_ctx()
-{
-	if (d_ctx) return 0;
-	d_ctx = gscan_open(d_device);
-	if (!d_ctx) {
-		d_err = std::string("FileGrep::find::gscan_open: ") + gscan_last_error();
-		return -1;
-	}
 	return 0;
 }
 
@@ -111,7 +139,7 @@ int FileGrep::find(const char *path, const struct stat *st, int)
 		w.file_seq = seq;
 		d_queue.push_back(std::move(w));
 		d_queued_bytes += clen;
-		if (d_queued_bytes >= d_batch_bytes && flush() < 0) { close(fd); return -1; }
+		if (d_queued_bytes >= d_batch_bytes && submit() < 0) { close(fd); return -1; }
 	}
 	close(fd);
 	return 0;
@@ -156,68 +184,149 @@ void FileGrep::format_window(const Window &w, const gscan_match_view *m, size_t 
 	}
 }
 
-int FileGrep::flush()
+// Moves the queued windows into a batch for the lanes.  Returns -1 when an earlier batch failed (why() has the
+// first failure); the queue is empty afterwards either way.
+int FileGrep::submit()
 {
 	if (d_queue.empty()) return 0;
-	if (ensure_ctx() < 0) {
-		for (auto &w : d_queue) release(w);
-		d_queue.clear();
-		d_queued_bytes = 0;
+	if (!d_pipe) d_pipe.reset(new Pipeline);
+	Pipeline &p = *d_pipe;
+	Batch *b = new Batch;
+	b->windows.swap(d_queue);
+	d_queued_bytes = 0;
+	std::unique_lock<std::mutex> lk(p.mu);
+	if (p.lanes.empty()) {
+		const int n = d_ndev * d_lanes_per_dev;
+		for (int i = 0; i < n; i++) p.lanes.emplace_back(&FileGrep::lane_main, this, i);
+	}
+	// bounded look-ahead: at most one waiting batch per lane keeps the mapped-but-unscanned windows small
+	p.cv_space.wait(lk, [&] { return p.jobs.size() < p.lanes.size(); });
+	if (p.failed) {
+		d_err = p.err;
+		lk.unlock();
+		for (auto &w : b->windows) release(w);
+		delete b;
 		return -1;
 	}
-	std::vector<gscan_unit> units(d_queue.size());
-	for (size_t i = 0; i < d_queue.size(); i++) {
-		units[i].ptr = d_queue[i].map;
-		units[i].len = d_queue[i].clen;
-		units[i].base_off = d_queue[i].off;
-		units[i].file_id = (uint32_t)i; // index of the window in this batch
-		units[i].flags = 0;
-	}
-	uint32_t mode = GSCAN_MODE_ALL;
-	if (d_print_line) mode = GSCAN_MODE_LINE;                 // resume after the printed line (grab.cc:188-209)
-	else if (!d_print_offset) mode = GSCAN_MODE_FIRST;        // "matches" once per window (grab.cc:204-207)
-	if (d_single_match) mode = GSCAN_MODE_FIRST;              // grab.cc:211-212
-	gscan_match *matches = nullptr;
-	size_t n = 0;
-	int rc = gscan_scan_batch(d_ctx, d_pat, units.data(), units.size(), mode, &matches, &n);
-	if (rc < 0) d_err = std::string("FileGrep::find::scan: ") + gscan_why(d_ctx);
-	if (getenv("GRAB_B200_TRACE")) { // side channel on stderr only: stdout is the parity surface
-		gscan_stats st;
-		gscan_last_stats(d_ctx, &st);
-		fprintf(stderr, "[grab-b200] batch: %zu windows, %.1f MiB, staging+h2d %.2f ms, scan kernel %.3f ms, resolve %.3f ms, call %.2f ms, %zu matches\n",
-		        units.size(), (double)st.bytes_scanned / 1048576.0, st.h2d_ms, st.scan_kernel_ms, st.resolve_ms, st.total_ms, n);
-	}
+	b->seq = p.next_seq++;
+	p.inflight++;
+	p.jobs.push_back(b);
+	lk.unlock();
+	p.cv_job.notify_one();
+	return 0;
+}
 
-	// per window, in queue order: format, then flush under the lock (grab.cc:217-234)
-	std::vector<gscan_match_view> view;
-	std::string out;
-	size_t k = 0;
-	bool have_done = false;
-	uint32_t done_seq = 0;
-	for (size_t i = 0; i < d_queue.size() && rc == 0; i++) {
-		view.clear();
-		while (k < n && matches[k].file_id == (uint32_t)i) {
-			view.push_back(gscan_match_view{matches[k].start, matches[k].match_len});
-			k++;
-		}
-		// -s: once a window of a file printed something, the rest of the file is skipped (grab.cc:232-233)
-		if (d_single_match && have_done && done_seq == d_queue[i].file_seq) continue;
-		if (view.empty()) continue;
-		out.clear();
-		format_window(d_queue[i], view.data(), view.size(), out);
-		if (!out.empty()) {
-			pthread_mutex_lock(&g_stdout_lock);
-			std::cout << out;
-			pthread_mutex_unlock(&g_stdout_lock);
-			if (d_single_match) { have_done = true; done_seq = d_queue[i].file_seq; }
-		}
+// Submits what is queued and waits until every batch has been printed.
+int FileGrep::flush()
+{
+	int rc = submit();
+	if (!d_pipe) return rc;
+	Pipeline &p = *d_pipe;
+	std::unique_lock<std::mutex> lk(p.mu);
+	p.cv_idle.wait(lk, [&] { return p.inflight == 0; });
+	if (p.failed) {
+		d_err = p.err;
+		p.failed = false; // reported once, like a failing find() of the reference
+		rc = -1;
 	}
-	std::cout.flush();
-	if (matches) gscan_free_matches(d_ctx, matches);
-	for (auto &w : d_queue) release(w);
-	d_queue.clear();
-	d_queued_bytes = 0;
 	return rc;
+}
+
+// One lane: its own engine context on device d_device + lane % d_ndev; takes batches in submission order, scans
+// and formats them concurrently with the other lanes, prints when it is the batch's turn.
+void FileGrep::lane_main(int lane)
+{
+	Pipeline &p = *d_pipe;
+	const int device = d_device + lane % d_ndev;
+	gscan_ctx *ctx = nullptr;
+	std::vector<gscan_unit> units;
+	std::vector<gscan_match_view> view;
+	std::vector<std::pair<uint32_t, std::string>> outs; // (file_seq, text of one window)
+	const bool trace = getenv("GRAB_B200_TRACE") != nullptr;
+	for (;;) {
+		Batch *b = nullptr;
+		{
+			std::unique_lock<std::mutex> lk(p.mu);
+			p.cv_job.wait(lk, [&] { return p.stop || !p.jobs.empty(); });
+			if (p.jobs.empty()) break;
+			b = p.jobs.front();
+			p.jobs.pop_front();
+		}
+		p.cv_space.notify_one();
+
+		std::string err;
+		int rc = 0;
+		if (!ctx && !(ctx = gscan_open(device))) {
+			err = std::string("FileGrep::find::gscan_open: ") + gscan_last_error();
+			rc = -1;
+		}
+		outs.clear();
+		if (rc == 0) {
+			units.resize(b->windows.size());
+			for (size_t i = 0; i < units.size(); i++) {
+				units[i].ptr = b->windows[i].map;
+				units[i].len = b->windows[i].clen;
+				units[i].base_off = b->windows[i].off;
+				units[i].file_id = (uint32_t)i; // index of the window in this batch
+				units[i].flags = 0;
+			}
+			uint32_t mode = GSCAN_MODE_ALL;
+			if (d_print_line) mode = GSCAN_MODE_LINE;                 // resume after the printed line (grab.cc:188-209)
+			else if (!d_print_offset) mode = GSCAN_MODE_FIRST;        // "matches" once per window (grab.cc:204-207)
+			if (d_single_match) mode = GSCAN_MODE_FIRST;              // grab.cc:211-212
+			gscan_match *matches = nullptr;
+			size_t n = 0;
+			rc = gscan_scan_batch(ctx, d_pat, units.data(), units.size(), mode, &matches, &n);
+			if (rc < 0) err = std::string("FileGrep::find::scan: ") + gscan_why(ctx);
+			if (trace) { // side channel on stderr only: stdout is the parity surface
+				gscan_stats st;
+				gscan_last_stats(ctx, &st);
+				fprintf(stderr, "[grab-b200] lane %d gpu %d batch %llu: %zu windows, %.1f MiB, staging+h2d %.2f ms, scan kernel %.3f ms, resolve %.3f ms, call %.2f ms, %zu matches\n",
+				        lane, device, (unsigned long long)b->seq, units.size(), (double)st.bytes_scanned / 1048576.0, st.h2d_ms,
+				        st.scan_kernel_ms, st.resolve_ms, st.total_ms, n);
+			}
+			// per window, in queue order: the text the reference would have flushed for it (grab.cc:175-213)
+			size_t k = 0;
+			for (size_t i = 0; i < b->windows.size() && rc == 0; i++) {
+				view.clear();
+				while (k < n && matches[k].file_id == (uint32_t)i) {
+					view.push_back(gscan_match_view{matches[k].start, matches[k].match_len});
+					k++;
+				}
+				if (view.empty()) continue;
+				outs.emplace_back(b->windows[i].file_seq, std::string());
+				format_window(b->windows[i], view.data(), view.size(), outs.back().second);
+			}
+			if (matches) gscan_free_matches(ctx, matches);
+		}
+		for (auto &w : b->windows) release(w); // grab.cc:215
+
+		{
+			std::unique_lock<std::mutex> lk(p.mu);
+			p.cv_turn.wait(lk, [&] { return p.next_out == b->seq; });
+			// flush window by window under the stdout lock (grab.cc:217-234)
+			for (auto &o : outs) {
+				if (d_single_match && p.have_done && p.done_seq == o.first) continue; // grab.cc:232-233
+				if (o.second.empty()) continue;
+				pthread_mutex_lock(&g_stdout_lock);
+				std::cout << o.second;
+				pthread_mutex_unlock(&g_stdout_lock);
+				if (d_single_match) { p.have_done = true; p.done_seq = o.first; }
+			}
+			if (!outs.empty()) {
+				pthread_mutex_lock(&g_stdout_lock);
+				std::cout.flush();
+				pthread_mutex_unlock(&g_stdout_lock);
+			}
+			if (rc < 0 && !p.failed) { p.failed = true; p.err = err; }
+			p.next_out++;
+			p.inflight--;
+		}
+		p.cv_turn.notify_all();
+		p.cv_idle.notify_all();
+		delete b;
+	}
+	if (ctx) gscan_close(ctx);
 }
 
 int FileGrep::find(const std::string &path)

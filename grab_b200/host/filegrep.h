@@ -9,6 +9,12 @@
 // in batches (one kernel launch per ~256 MiB instead of one pcre_exec per match); matches come
 // back sorted by (window, offset), so the bytes written to stdout are the reference's, in the
 // reference's order.
+//
+// Batches are scanned by "lanes": worker threads that each own one engine context on one GPU
+// (SURVEY.md 8(f) f1/f4).  The walking thread keeps stat/open/mmap-ing while the lanes stage, scan
+// and format; a sequencer prints the batches in submission order, so stdout does not depend on the
+// number of lanes or GPUs.  Since the batches of one huge file are the reference's own windows
+// (grab.cc:151-159, 4 KiB overlap), spreading them over several GPUs reproduces Q3 exactly.
 #pragma once
 
 #include <sys/stat.h>
@@ -16,6 +22,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -45,6 +52,8 @@ public:
 	void literal(bool b) { d_literal = b; }        // -S
 	void strict_reference(bool b) { d_strict = b; } // Q2 on/off (default on: bit-identical output)
 	void batch_bytes(size_t n) { d_batch_bytes = n; }
+	void devices(int first, int count) { d_device = first; d_ndev = count < 1 ? 1 : count; } // lanes go to first..first+count-1
+	void lanes_per_device(int n) { d_lanes_per_dev = n < 1 ? 1 : n; }
 	int minlen() const { return d_minlen; }
 
 private:
@@ -56,9 +65,13 @@ private:
 		uint32_t file_seq = 0;    // which find() call the window belongs to (for -s early exit)
 	};
 
-	int ensure_ctx();
+	struct Batch;
+	struct Pipeline;
+	friend struct Pipeline;
+	int submit();                      // hand the queued windows to the lanes (blocks only when they are all busy)
+	void lane_main(int lane);
 	void format_window(const Window &w, const struct gscan_match_view *m, size_t n, std::string &out) const;
-	void release(Window &w);
+	static void release(Window &w);
 
 	std::string d_err;
 	int d_minlen = 1;
@@ -66,9 +79,9 @@ private:
 	     d_single_match = false, d_low_mem = false, d_literal = false, d_strict = true;
 	size_t d_chunk_size = (size_t)1 << 30;   // grab.h:48
 	uid_t d_my_uid = 0;
-	int d_device = 0;
-	gscan_ctx *d_ctx = nullptr;
+	int d_device = 0, d_ndev = 1, d_lanes_per_dev = 1;
 	gscan_pattern *d_pat = nullptr;
+	std::unique_ptr<Pipeline> d_pipe;
 	std::vector<Window> d_queue;
 	size_t d_queued_bytes = 0;
 	size_t d_batch_bytes = (size_t)256 << 20;

@@ -2,7 +2,10 @@
 // of the CUDA scan engine.  Same getopt string "Rrn:IOlsL", same config-map keys, same exit codes;
 // additionally accepts -2 -H (aliases: same PCRE match semantics) and -S (literal pattern) from the
 // reference's README.md:16-31.  GPU knobs are environment variables so the short-flag surface
-// stays identical: GRAB_B200_DEVICE=<n>, GRAB_B200_LENIENT=1 (do not reproduce quirk Q2).
+// stays identical: GRAB_B200_DEVICE=<n> (first GPU), GRAB_B200_NDEV=<k> (GPUs to spread over: threads under -n,
+// batches of windows otherwise -- also the windows of ONE huge file), GRAB_B200_LANES=<k> (scan lanes per GPU),
+// GRAB_B200_BATCH_BYTES=<n> (bytes of windows per engine call, default 256 MiB), GRAB_B200_LENIENT=1 (do not
+// reproduce quirk Q2).
 #include <ftw.h>
 #include <pthread.h>
 #include <sched.h>
@@ -85,6 +88,8 @@ int main(int argc, char **argv)
 	int device = getenv("GRAB_B200_DEVICE") ? atoi(getenv("GRAB_B200_DEVICE")) : 0;
 	int ndev = getenv("GRAB_B200_NDEV") ? atoi(getenv("GRAB_B200_NDEV")) : 1;
 	if (ndev < 1) ndev = 1;
+	if (getenv("GRAB_B200_BATCH_BYTES") && atoll(getenv("GRAB_B200_BATCH_BYTES")) > 0) config["batch_bytes"] = (size_t)atoll(getenv("GRAB_B200_BATCH_BYTES"));
+	if (getenv("GRAB_B200_LANES") && atoi(getenv("GRAB_B200_LANES")) > 0) config["lanes"] = (size_t)atoi(getenv("GRAB_B200_LANES"));
 
 	if (argc < optind + 2) usage(argv[0]);
 	string regex = argv[optind++];
@@ -141,6 +146,7 @@ int main(int argc, char **argv)
 	}
 
 	config["device"] = (size_t)device;
+	config["ndev"] = (size_t)ndev; // batches of windows go round the GPUs; stdout order does not depend on it
 	FileGrep *grep = new (nothrow) FileGrep;
 	if (!grep) { cerr << "Out of memory.\n"; return -1; }
 	grep->config(config);

@@ -114,3 +114,56 @@ def test_cli_literal_flag(tmp_path):
     assert rc == 0 and so == b""
     rc, so, se = run(["-O", "-l", "(a.c)", str(fn)], env={"GRAB_B200_LENIENT": "1"})
     assert rc == 0 and so == b"Match at offset 0\nMatch at offset 4\nMatch at offset 8\n"
+
+
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [["-O", "-l"], ["-s", "-O", "-l"], ["-O"], ["-l"]], ids=lambda f: "".join(f))
+def test_cli_one_file_over_lanes_and_gpus(flags, tmp_path):
+    """f4: the 32 MiB windows of one file as separate batches over 2 lanes (and over 2 GPUs when the box has them):
+    stdout byte-identical to the single-lane run and to the oracle's FileGrep::find restatement (Q3 duplicates, -s
+    stopping the file after the first printing window)."""
+    import numpy as np
+    import oracle_py as O
+    C = 1 << 25
+    size = 3 * C + 12345
+    a = np.full(size, ord("."), dtype=np.uint8)
+    a[63::64] = 10
+    for off in (1000, C - 4096 + 100, C - 3, 2 * (C - 4096) + 77, size - 6, size - 400):
+        a[off:off + 6] = np.frombuffer(b"NEEDLE", dtype=np.uint8)
+    fn = str(tmp_path / "big.bin")
+    a.tofile(fn)
+    want = O.Regex("NEEDLE").grab(a.tobytes(), offsets="-O" in flags, line="-l" not in flags, single="-s" in flags, chunk_size=C)
+    args = ["-L"] * 5 + flags + ["NEEDLE", fn]
+    rc, one, se = run(args)
+    assert rc == 0 and one == want, se
+    envs = [dict(GRAB_B200_LANES="2", GRAB_B200_BATCH_BYTES="1")]
+    if _gpu_count() >= 2:
+        envs.append(dict(GRAB_B200_NDEV="2", GRAB_B200_BATCH_BYTES="1"))
+        envs.append(dict(GRAB_B200_NDEV=str(_gpu_count()), GRAB_B200_LANES="2", GRAB_B200_BATCH_BYTES="1"))
+    for env in envs:
+        rc, so, se = run(args, env=env)
+        assert rc == 0 and so == want, (env, se)
+
+
+@pytest.mark.gpu
+def test_cli_lanes_keep_submission_order(tmp_path):
+    import numpy as np
+    rng = np.random.default_rng(5)
+    words = [b"foo", b"bar", b"baz", b"quux", b"lorem", b"ipsum", b"dolor", b"\n", b" ", b"sit", b"\n"]
+    for i in range(200):
+        sub = tmp_path / "tree" / ("d%d" % (i % 7))
+        sub.mkdir(parents=True, exist_ok=True)
+        (sub / ("f%03d.txt" % i)).write_bytes(b"".join(words[j] for j in rng.integers(0, len(words), int(rng.integers(0, 400)))))
+    for flags in (["-r", "-O", "-l"], ["-r"], ["-r", "-s"]):
+        rc, one, se = run(flags + ["foo|bar|baz|quux", "tree"], cwd=str(tmp_path))
+        assert rc == 0, se
+        env = dict(GRAB_B200_LANES="3", GRAB_B200_BATCH_BYTES="3000")
+        if _gpu_count() >= 2:
+            env["GRAB_B200_NDEV"] = "2"
+        rc, many, se = run(flags + ["foo|bar|baz|quux", "tree"], cwd=str(tmp_path), env=env)
+        assert rc == 0 and many == one, se
