@@ -25,6 +25,24 @@ def files_of_rank(n_files, rank, world, mode="stride"):
     return np.arange(lo, lo + per + (1 if rank < extra else 0), dtype=np.int64)
 
 
+def file_windows(size, chunk_size=1 << 30, overlap=0x1000):
+    """(off, clen) of the windows the reference cuts one file into (grab.cc:151-159): clen = min(chunk, size - off),
+    off += chunk - 4096.  They are independent scan units (every window is searched statelessly, quirk Q3), which
+    makes them the partition for scanning ONE huge file on several GPUs."""
+    out, off = [], 0
+    while off < size:
+        out.append((off, min(chunk_size, size - off)))
+        off += chunk_size - overlap
+    return out
+
+
+def windows_of_rank(n_windows, rank, world):
+    """Window indices of one file scanned by `rank`: round-robin, like the files (main.cc:94).  Scan them as units
+    with file_id = window index and base_off = off; gather_matches() then restores the reference's output order
+    (window by window, ascending inside a window -- duplicates in the overlaps included)."""
+    return np.arange(rank, n_windows, world, dtype=np.int64)
+
+
 def _device(group=None):
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
 
