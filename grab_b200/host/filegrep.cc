@@ -8,6 +8,7 @@
 #include <unistd.h>
 
 #include <cerrno>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -23,6 +24,17 @@ namespace grab_b200 {
 
 // one lock around stdout, like stdout_lock of grab.cc:56,219-225
 static pthread_mutex_t g_stdout_lock = PTHREAD_MUTEX_INITIALIZER;
+
+// GRAB_B200_TRACE=1: milestones with milliseconds since the process was loaded, on stderr (stdout is the parity surface)
+static const std::chrono::steady_clock::time_point g_t0 = std::chrono::steady_clock::now();
+static const bool g_trace = getenv("GRAB_B200_TRACE") != nullptr;
+static void trace_ts(const char *what, int lane = -1)
+{
+	if (!g_trace) return;
+	const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_t0).count();
+	if (lane >= 0) fprintf(stderr, "[grab-b200] %9.2f ms  lane %d: %s\n", ms, lane, what);
+	else fprintf(stderr, "[grab-b200] %9.2f ms  %s\n", ms, what);
+}
 
 static const char kStartInv[] = "\33[7m", kStopInv[] = "\33[27m"; // grab.cc:66-67
 
@@ -97,6 +109,7 @@ int FileGrep::prepare(const std::string &regex)
 		return -1;
 	}
 	d_minlen = gscan_minlen(d_pat);
+	trace_ts("pattern compiled");
 	return 0;
 }
 
@@ -196,6 +209,7 @@ int FileGrep::submit()
 	d_queued_bytes = 0;
 	std::unique_lock<std::mutex> lk(p.mu);
 	if (p.lanes.empty()) {
+		trace_ts("first batch submitted");
 		const int n = d_ndev * d_lanes_per_dev;
 		for (int i = 0; i < n; i++) p.lanes.emplace_back(&FileGrep::lane_main, this, i);
 	}
@@ -224,6 +238,7 @@ int FileGrep::flush()
 	Pipeline &p = *d_pipe;
 	std::unique_lock<std::mutex> lk(p.mu);
 	p.cv_idle.wait(lk, [&] { return p.inflight == 0; });
+	trace_ts("all batches printed");
 	if (p.failed) {
 		d_err = p.err;
 		p.failed = false; // reported once, like a failing find() of the reference
@@ -242,7 +257,7 @@ void FileGrep::lane_main(int lane)
 	std::vector<gscan_unit> units;
 	std::vector<gscan_match_view> view;
 	std::vector<std::pair<uint32_t, std::string>> outs; // (file_seq, text of one window)
-	const bool trace = getenv("GRAB_B200_TRACE") != nullptr;
+	const bool trace = g_trace;
 	for (;;) {
 		Batch *b = nullptr;
 		{
@@ -256,9 +271,12 @@ void FileGrep::lane_main(int lane)
 
 		std::string err;
 		int rc = 0;
-		if (!ctx && !(ctx = gscan_open(device))) {
-			err = std::string("FileGrep::find::gscan_open: ") + gscan_last_error();
-			rc = -1;
+		if (!ctx) {
+			if (!(ctx = gscan_open(device))) {
+				err = std::string("FileGrep::find::gscan_open: ") + gscan_last_error();
+				rc = -1;
+			}
+			trace_ts("engine context open", lane);
 		}
 		outs.clear();
 		if (rc == 0) {
@@ -278,12 +296,14 @@ void FileGrep::lane_main(int lane)
 			size_t n = 0;
 			rc = gscan_scan_batch(ctx, d_pat, units.data(), units.size(), mode, &matches, &n);
 			if (rc < 0) err = std::string("FileGrep::find::scan: ") + gscan_why(ctx);
-			if (trace) { // side channel on stderr only: stdout is the parity surface
+			if (trace) {
 				gscan_stats st;
 				gscan_last_stats(ctx, &st);
-				fprintf(stderr, "[grab-b200] lane %d gpu %d batch %llu: %zu windows, %.1f MiB, staging+h2d %.2f ms, scan kernel %.3f ms, resolve %.3f ms, call %.2f ms, %zu matches\n",
-				        lane, device, (unsigned long long)b->seq, units.size(), (double)st.bytes_scanned / 1048576.0, st.h2d_ms,
-				        st.scan_kernel_ms, st.resolve_ms, st.total_ms, n);
+				char line[256];
+				snprintf(line, sizeof line, "gpu %d batch %llu: %zu windows, %.1f MiB, staging+h2d %.2f ms, scan kernel %.3f ms, resolve %.3f ms, call %.2f ms, %zu matches",
+				         device, (unsigned long long)b->seq, units.size(), (double)st.bytes_scanned / 1048576.0, st.h2d_ms,
+				         st.scan_kernel_ms, st.resolve_ms, st.total_ms, n);
+				trace_ts(line, lane);
 			}
 			// per window, in queue order: the text the reference would have flushed for it (grab.cc:175-213)
 			size_t k = 0;
@@ -300,6 +320,7 @@ void FileGrep::lane_main(int lane)
 			if (matches) gscan_free_matches(ctx, matches);
 		}
 		for (auto &w : b->windows) release(w); // grab.cc:215
+		if (trace) trace_ts("windows unmapped", lane);
 
 		{
 			std::unique_lock<std::mutex> lk(p.mu);
@@ -327,6 +348,7 @@ void FileGrep::lane_main(int lane)
 		delete b;
 	}
 	if (ctx) gscan_close(ctx);
+	trace_ts("engine context closed", lane);
 }
 
 int FileGrep::find(const std::string &path)

@@ -1,13 +1,19 @@
-python - <<'PY'
+# Where the command line's wall time goes: timestamped milestones (GRAB_B200_TRACE=1) on a tmpfs tree.
+# Usage: bash tools/cli_trace.sh [n_files]      (run from the repository root on a GPU box)
+N=${1:-8192}
+python - <<PY
 import sys,os
 sys.path.insert(0,os.getcwd())
 import bench
-d=bench.materialise_sample(2048)
-print(d)
+d=bench.materialise_sample($N)
 open('/tmp/cli_dir','w').write(d)
 PY
 D=$(cat /tmp/cli_dir)
-echo "--- one file"; time grab_b200/bin/grab-b200 -O -l foobardoesexist $D/f000032 
-echo "--- 2 GiB tree, 1 thread"; time GRAB_B200_TRACE=1 grab_b200/bin/grab-b200 -r -O -l foobardoesexist $D > /dev/null
-echo "--- 2 GiB tree, -n 8"; time GRAB_B200_TRACE=1 grab_b200/bin/grab-b200 -n 8 -r -O -l foobardoesexist $D 2>&1 >/dev/null | tail -12
-rm -rf $D
+B=grab_b200/bin/grab-b200
+echo "--- one 1 MiB file"; time GRAB_B200_TRACE=1 $B -O -l foobardoesexist $D/f000032
+echo "--- $N x 1 MiB tree, 1 lane"; time GRAB_B200_TRACE=1 $B -r -O -l foobardoesexist $D 2>/tmp/tr.txt >/dev/null; head -8 /tmp/tr.txt; echo ...; tail -8 /tmp/tr.txt
+echo "--- same, 2 lanes"; time GRAB_B200_LANES=2 GRAB_B200_TRACE=1 $B -r -O -l foobardoesexist $D 2>/tmp/tr.txt >/dev/null; head -8 /tmp/tr.txt; echo ...; tail -8 /tmp/tr.txt
+cat $D/f* > /dev/shm/gscan_big.bin
+echo "--- one file of $N MiB"; time GRAB_B200_TRACE=1 $B -O -l foobardoesexist /dev/shm/gscan_big.bin 2>/tmp/tr.txt >/dev/null; cat /tmp/tr.txt | head -40
+echo "--- same, batches of 256 MiB windows (-L -L), 2 lanes"; time GRAB_B200_LANES=2 GRAB_B200_TRACE=1 $B -L -L -O -l foobardoesexist /dev/shm/gscan_big.bin 2>/tmp/tr.txt >/dev/null; head -12 /tmp/tr.txt; echo ...; tail -6 /tmp/tr.txt
+rm -rf $D /dev/shm/gscan_big.bin
