@@ -21,7 +21,9 @@ struct Geom {
 };
 typedef Geom<16, 3, 4096> GeomStream;  // memory-bound: single-test literal filter
 typedef Geom<24, 4, 2048> GeomBalanced;
-typedef Geom<16, 4, 2048> GeomHash;     // leaves 32 KiB of shared memory for the hash table
+// hashed engine: issue-bound, wants warps (20 = 5 per scheduler measured best; 16, 18 and 22 were 8-10 % slower) and
+// long slices (fewer ring refills per byte): 2 x 4 KiB per warp, which leaves 32 KiB for the table
+typedef Geom<20, 2, 4096> GeomHash;
 
 struct ScanGeom { int warps, ring, slice; }; // host-side mirror of the chosen Geom
 
@@ -69,10 +71,10 @@ struct FixedParams {
 // FIXED, hashed: exact membership of the 2 or 3 bytes at every position in a perfect-hash table held in
 // shared memory; hits are verified against the alternatives sharing the key
 struct HashParams {
-	uint32_t mul;        // slot byte offset = umulhi(key, mul) & slot_mask
-	uint32_t slot_mask;  // (slots - 1) << 2
-	uint32_t key_mask;   // 0xffff or 0xffffff
+	uint32_t mul;        // slot = umulhi(key * mul, nslots): two IMADs, nothing on the ALU pipe
 	uint32_t nslots;
+	uint32_t key_mask;   // 0xffff or 0xffffff
+	uint32_t stride;     // bytes between slots in shared memory: 4, or 128 when the table is replicated per bank
 	const uint32_t *table;      // [nslots] key or 0xffffffff (copied to shared memory at kernel start)
 	const uint32_t *slot_first; // [nslots] first index into slot_seqs
 	const uint32_t *slot_count; // [nslots]
@@ -84,6 +86,11 @@ struct HashParams {
 	const uint32_t *cls_bm;
 };
 constexpr int kHashMaxSlots = 8192;
+// copies of the table in shared memory (slot s, copy c at word s * copies + c; lane l reads copy l % copies): 32 copies
+// put every lane of a warp on its own bank (one wavefront per lookup instead of ~3.4 for random slots), 16 copies
+// two lanes per bank; the table then still fits in 32 KiB beside the 20-warp ring
+constexpr uint32_t kHashReplicatedSlots = 512;
+static inline uint32_t hash_table_copies(uint32_t nslots) { return nslots <= 256 ? 32u : (nslots <= kHashReplicatedSlots ? 16u : 1u); }
 
 struct RunParams {
 	uint32_t one;         // == 1, opaque (see FixedParams)

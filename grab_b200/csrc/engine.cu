@@ -212,7 +212,7 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 			HashParams &H = p->hash;
 			H.mul = pr.hash_mul;
 			H.nslots = pr.hash_slots;
-			H.slot_mask = (pr.hash_slots - 1) << 2;
+			H.stride = hash_table_copies(pr.hash_slots) * 4u;
 			H.key_mask = pr.hash_len == 2 ? 0xffffu : 0xffffffu;
 			H.uniform_len = F.uniform_len;
 			H.maxlen = F.maxlen;
@@ -631,6 +631,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	if (ensure_pattern(ctx, pat) < 0) return -1;
 
 	const bool hashed = pat->prog.kind == ENGINE_FIXED && pat->prog.use_hash;
+	const uint32_t table_bytes = hashed ? pat->prog.hash_slots * 4u * hash_table_copies(pat->prog.hash_slots) : 0u;
 	const ScanGeom geom = scan_geom(hashed ? 4 : (int)pat->prog.kind, pat->prog.kind == ENGINE_FIXED ? (uint32_t)pat->prog.tests.size() : 99u);
 	const uint32_t spt = (uint32_t)(kTileBytes / geom.slice);
 	const uint32_t n_segs = b->n_tiles * spt;
@@ -650,7 +651,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	A.cursor = ctx->cursor.p;
 	A.segs = ctx->segs.p;
 	A.scratch = ctx->scratch.p;
-	A.extra_smem = hashed ? pat->prog.hash_slots * 4u : 0u;
+	A.extra_smem = table_bytes;
 	A.tag = ctx->seg_tag;
 
 	unsigned long long *h_cursor = reinterpret_cast<unsigned long long *>(ctx->readback.p);

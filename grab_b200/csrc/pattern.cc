@@ -802,38 +802,51 @@ bool build_hash(Program &out, int L)
 	for (auto &e : kv) distinct.push_back(e.first);
 	std::sort(distinct.begin(), distinct.end());
 	distinct.erase(std::unique(distinct.begin(), distinct.end()), distinct.end());
-	uint32_t slots = 256;
-	while (slots < 2 * distinct.size()) slots <<= 1;
 	uint64_t rng = 0x9E3779B97F4A7C15ull ^ (distinct.size() * 0xD1B54A32D192ED03ull);
-	for (; slots <= 8192; slots <<= 1) {
-		for (int attempt = 0; attempt < 4000; attempt++) {
+	const uint32_t kEmpty = 0xffffffffu; // never a key: keys are at most 3 bytes
+	// slot = umulhi(key * mul mod 2^32, slots): multiplicative hashing on the LOW product word (every key bit reaches
+	// its top bits; text keys differ mostly in their low bits) and a multiply-high range reduction, so the kernel
+	// computes the slot with two IMADs and no ALU-pipe instruction, and `slots` need not be a power of two.
+	std::vector<uint32_t> table;
+	auto search = [&](uint32_t ns, int attempts) -> bool {
+		for (int attempt = 0; attempt < attempts; attempt++) {
 			rng = rng * 6364136223846793005ull + 1442695040888963407ull;
 			const uint32_t mul = (uint32_t)(rng >> 32) | 1u;
-			std::vector<uint32_t> table(slots, 0xffffffffu);
+			table.assign(ns, kEmpty);
 			bool ok = true;
 			for (uint32_t k : distinct) {
-				const uint32_t sl = (umulhi32(k, mul) >> 2) & (slots - 1);
-				if (table[sl] != 0xffffffffu) { ok = false; break; }
+				const uint32_t sl = umulhi32(k * mul, ns);
+				if (table[sl] != kEmpty) { ok = false; break; }
 				table[sl] = k;
 			}
 			if (!ok) continue;
 			out.use_hash = true;
 			out.hash_len = L;
 			out.hash_mul = mul;
-			out.hash_slots = slots;
+			out.hash_slots = ns;
 			out.hash_table = table;
-			out.slot_first.assign(slots, 0);
-			out.slot_count.assign(slots, 0);
+			out.slot_first.assign(ns, 0);
+			out.slot_count.assign(ns, 0);
 			out.slot_seqs.clear();
-			for (uint32_t sl = 0; sl < slots; sl++) {
-				if (table[sl] == 0xffffffffu) continue;
+			for (uint32_t sl = 0; sl < ns; sl++) {
+				if (table[sl] == kEmpty) continue;
 				out.slot_first[sl] = (uint32_t)out.slot_seqs.size();
 				for (auto &e : kv) // kv is in preference order of the alternatives
 					if (e.first == table[sl]) { out.slot_seqs.push_back(e.second); out.slot_count[sl]++; }
 			}
 			return true;
 		}
-	}
+		return false;
+	};
+	// tables of up to kHashReplicatedSlots (512) slots are replicated once per shared-memory bank by the kernel
+	// (conflict-free lookups; with random slots the shared-memory data pipe is the bottleneck: 3.4 wavefronts per
+	// lookup measured), so a small table is worth a long search: P(no collision) ~ exp(-n^2 / 2 slots) per try
+	const size_t n = distinct.size();
+	if (n + n / 8 <= 256 && search(256, 20000)) return true;
+	if (n + n / 8 <= 384 && search(384, 100000)) return true;
+	if (n + n / 8 <= 512 && search(512, 400000)) return true;
+	for (uint32_t ns = 1024; ns <= 8192; ns <<= 1)
+		if (search(ns, 4000)) return true;
 	return false;
 }
 

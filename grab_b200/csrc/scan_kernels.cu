@@ -406,6 +406,11 @@ struct Fixed3Engine {
 // are looked up in a perfect-hash table in shared memory -- exact membership, one multiply (FMA pipe),
 // one LDS and four ALU ops per position, independent of how many alternatives there are.  Only true
 // key hits are verified, against the alternatives that share the key, in preference order.
+//
+// Small tables are replicated across the shared-memory banks: 32 copies (stride 128 B, lane l reads bank l: one
+// wavefront per lookup) up to 256 slots, 16 copies (two lanes per bank: two wavefronts) up to 512.  With a single
+// copy the 32 random slots of a warp cost ~3.4 wavefronts and the shared-memory data pipe is the bottleneck (95 %
+// busy, profiles/r01_scan_v5_lits8_ncu.txt).
 // ------------------------------------------------------------------------------------------
 struct HashEngine {
 	typedef HashParams Params;
@@ -414,7 +419,8 @@ struct HashEngine {
 	static __device__ __forceinline__ void prologue(const HashParams &P, uint8_t *extra)
 	{
 		uint32_t *t = reinterpret_cast<uint32_t *>(extra);
-		for (uint32_t i = threadIdx.x; i < P.nslots; i += blockDim.x) t[i] = P.table[i];
+		const uint32_t copies = P.stride >> 2; // 32, 16 or 1 (power of two): slot s, copy c at word s * copies + c
+		for (uint32_t i = threadIdx.x; i < P.nslots * copies; i += blockDim.x) t[i] = P.table[i / copies];
 		__syncthreads();
 	}
 
@@ -447,19 +453,23 @@ struct HashEngine {
 	{
 		return (k ? __funnelshift_r(lo, hi, 8 * k) : lo) & P.key_mask;
 	}
+	static __device__ __forceinline__ uint32_t slot_of(const HashParams &P, uint32_t y) { return __umulhi(y * P.mul, P.nslots); }
+	// tbl: the table in shared memory, for a replicated table already advanced to this lane's bank (+ lane * 4).
+	// Slot and address are three IMADs (FMA pipe); zero <=> the position holds a key of the set.
+	static __device__ __forceinline__ uint32_t probe(const HashParams &P, const uint8_t *tbl, uint32_t y)
+	{
+		return *reinterpret_cast<const uint32_t *>(tbl + slot_of(P, y) * P.stride) ^ y;
+	}
 
-	// min over the 16 positions of (table[slot(key)] ^ key): zero <=> some position holds a key of the set
+	// min over the 16 positions of (table[slot(key)] ^ key), two positions per 3-input minimum
 	static __device__ __forceinline__ uint32_t row_min(const HashParams &P, const uint8_t *tbl, const uint32_t (&w)[5])
 	{
 		uint32_t mn = 0xffffffffu;
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
 #pragma unroll
-			for (int k = 0; k < 4; k++) {
-				const uint32_t y = key_at(P, w[j], w[j + 1], k);
-				const uint32_t e = *reinterpret_cast<const uint32_t *>(tbl + (__umulhi(y, P.mul) & P.slot_mask));
-				mn = min(mn, e ^ y);
-			}
+			for (int k = 0; k < 4; k += 2)
+				mn = __vimin3_u32(mn, probe(P, tbl, key_at(P, w[j], w[j + 1], k)), probe(P, tbl, key_at(P, w[j], w[j + 1], k + 1)));
 		}
 		return mn;
 	}
@@ -472,30 +482,26 @@ struct HashEngine {
 		uint32_t mm = 0;
 		uint32_t hits = 0; // positions whose leading bytes are a key of the set (unrolled: straight-line, no divergence yet)
 #pragma unroll
-		for (int b = 0; b < 16; b++) {
-			const uint32_t y = key_at(P, w[b >> 2], w[(b >> 2) + 1], b & 3);
-			const uint32_t e = *reinterpret_cast<const uint32_t *>(tbl + (__umulhi(y, P.mul) & P.slot_mask));
-			hits |= (e == y ? 1u : 0u) << b;
-		}
+		for (int b = 0; b < 16; b++)
+			hits |= (probe(P, tbl, key_at(P, w[b >> 2], w[(b >> 2) + 1], b & 3)) == 0u ? 1u : 0u) << b;
+		// the key at position b for a run-time b (rolled loops below: the slow path stays small)
+		auto key_rt = [&](int b) -> uint32_t { return __funnelshift_r(w[b >> 2], w[(b >> 2) + 1], 8 * (b & 3)) & P.key_mask; };
 		while (hits) { // verify() is out of line: one copy, the kernel stays instruction-cache resident
 			const int b = __ffs(hits) - 1;
 			hits &= hits - 1;
-			const uint32_t y = __funnelshift_r(w[b >> 2], w[(b >> 2) + 1], 8 * (b & 3)) & P.key_mask;
 			const int p = (int)c0 + b;
-			if (p < (int)tile_len && verify(P, gtile, off, ulen, p, (__umulhi(y, P.mul) & P.slot_mask) >> 2)) mm |= 1u << b;
+			if (p < (int)tile_len && verify(P, gtile, off, ulen, p, slot_of(P, key_rt(b)))) mm |= 1u << b;
 		}
 		return Emitter::emit_at(dst, mm, off + c0, [&](uint32_t b) -> uint32_t {
 			if (P.uniform_len) return P.uniform_len;
-			const int j = (int)b >> 2, k = (int)b & 3;
-			const uint32_t y = __funnelshift_r(w[j], w[j + 1], 8 * k) & P.key_mask;
-			return verify(P, gtile, off, ulen, (int)(c0 + b), (__umulhi(y, P.mul) & P.slot_mask) >> 2);
+			return verify(P, gtile, off, ulen, (int)(c0 + b), slot_of(P, key_rt((int)b)));
 		}, lane);
 	}
 
 	template <class G>
 	static __device__ __forceinline__ void run(const HashParams &P, const Slice &S, Emitter &E, uint32_t lane)
 	{
-		const uint8_t *tbl = S.extra;
+		const uint8_t *tbl = S.extra + ((lane * 4u) & (P.stride - 1u)); // this lane's copy of the table
 		const uint32_t base = S.begin + lane * 16;
 		for (uint32_t it = 0; it < S.niter; it++) {
 			const uint32_t c0 = base + it * 512;

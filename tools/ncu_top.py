@@ -18,7 +18,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__thread_inst_executed_per_inst_executed.ratio"]
 for i, h in enumerate(hdr):
-    if h in want or ("issue_stalled" in h and "per_issue_active" in h and float(vals[i] or 0) > 0.15):
+    if h in want or "wavefronts_mem_shared" in h or h in ("sm__cycles_elapsed.avg", "sm__cycles_active.avg", "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed") or ("issue_stalled" in h and "per_issue_active" in h and float(vals[i] or 0) > 0.15):
         print("%-88s %-12s %s" % (h, units[i], vals[i]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
 rows = list(csv.reader(io.StringIO(src)))
