@@ -20,7 +20,12 @@ struct Geom {
 	static constexpr int kThreads = W * 32;
 };
 typedef Geom<16, 3, 4096> GeomStream;  // memory-bound: single-test literal filter
-typedef Geom<24, 4, 2048> GeomBalanced;
+#ifndef GS_BAL_W
+#define GS_BAL_W 24
+#define GS_BAL_R 2
+#define GS_BAL_S 4096
+#endif
+typedef Geom<GS_BAL_W, GS_BAL_R, GS_BAL_S> GeomBalanced;
 // hashed engine: issue-bound, wants warps (20 = 5 per scheduler measured best; 16, 18 and 22 were 8-10 % slower) and
 // long slices (fewer ring refills per byte): 2 x 4 KiB per warp, which leaves 32 KiB for the table
 typedef Geom<20, 2, 4096> GeomHash;
