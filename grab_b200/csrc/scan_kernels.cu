@@ -410,7 +410,7 @@ struct Fixed3Engine {
 // Small tables are replicated across the shared-memory banks: 32 copies (stride 128 B, lane l reads bank l: one
 // wavefront per lookup) up to 256 slots, 16 copies (two lanes per bank: two wavefronts) up to 512.  With a single
 // copy the 32 random slots of a warp cost ~3.4 wavefronts and the shared-memory data pipe is the bottleneck (95 %
-// busy, profiles/r01_scan_v5_lits8_ncu.txt).
+// busy, profiles/r01_scan_v5_lits8_single_table_ncu.txt).
 // ------------------------------------------------------------------------------------------
 struct HashEngine {
 	typedef HashParams Params;
