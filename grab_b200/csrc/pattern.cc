@@ -989,7 +989,8 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 	}
 	// alternatives of equal length that differ in exactly one position are one alternative with the union class
 	// there: same start, same length, so which of them PCRE would have preferred does not show ("a|b|c" == "[abc]")
-	for (bool merged = true; merged;) {
+	// (an optimisation only, quadratic per merge: skipped for sets far beyond what the engines serve anyway)
+	for (bool merged = uniq.size() <= 512; merged;) {
 		merged = false;
 		for (size_t i = 0; i < uniq.size() && !merged; i++)
 			for (size_t j = i + 1; j < uniq.size() && !merged; j++) {
