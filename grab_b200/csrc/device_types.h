@@ -19,7 +19,9 @@ struct Geom {
 	static constexpr int kSlicesPerTile = kTileBytes / S;
 	static constexpr int kThreads = W * 32;
 };
-typedef Geom<16, 3, 4096> GeomStream;  // memory-bound: single-test literal filter
+typedef Geom<16, 3, 4096> GeomStream;  // memory-bound: the FIXED filters
+// RUN (class runs): ALU/issue-bound, 24 warps; 4 KiB slices with a 2-deep ring do half the ring work per byte of the
+// earlier <24, 4, 2048> (+18-22 % measured).  GS_BAL_* : tuning override (make NAME=x DEFS=-DGS_BAL_W=...)
 #ifndef GS_BAL_W
 #define GS_BAL_W 24
 #define GS_BAL_R 2
