@@ -226,15 +226,27 @@ def main():
             torch.cuda.synchronize()
 
     from grab_b200 import shard
-    state = {"counts": None}
+    state = {"counts": None, "pending": None}
 
     def step():
+        # the one collective of the path: an NCCL all-gather of the per-rank match counts, once per step.  It is
+        # enqueued right after the scan and collected one step later (the last one before the timed region ends), so
+        # its launch/completion latency and the rank skew it exposes overlap the next scan instead of adding to it
         r = ctx.batch_scan(pat, batch, G.MODE_ALL)
-        state["counts"] = shard.gather_counts(len(r))  # the one collective of the path (NCCL all-gather of match counts)
+        h = shard.gather_counts_start(len(r))
+        if state["pending"] is not None:
+            state["counts"] = state["pending"].finish()
+        state["pending"] = h
         return r
+
+    def drain():
+        if state["pending"] is not None:
+            state["counts"] = state["pending"].finish()
+            state["pending"] = None
 
     for _ in range(a.warmup):
         r = step()
+    drain()
     # ---- parity gate (outside the timed region): planted needles + oracle on regenerated files ----
     import corpus
     import oracle_py as O
@@ -263,6 +275,7 @@ def main():
         st = ctx.stats()
         kernel_ms.append(st["scan_kernel_ms"])
         launches += st["total_launches"]
+    drain()  # every step's all-gather has completed inside the timed region
     sync_all()
     dt = time.perf_counter() - t0
     sampler.stop()

@@ -58,6 +58,31 @@ def gather_counts(n_local, group=None):
     return out.cpu().numpy()
 
 
+class PendingCounts:
+    """An all-gather of match counts in flight (gather_counts_start): finish() returns the per-rank counts.  Lets the
+    next scan overlap the collective's launch and completion latency -- the counts are only needed at the end."""
+
+    def __init__(self, out, work, n_local):
+        self._out, self._work, self._n = out, work, n_local
+
+    def finish(self):
+        if self._work is None:
+            return np.array([self._n], dtype=np.int64) if self._out is None else self._out.cpu().numpy()
+        self._work.wait()
+        return self._out.cpu().numpy()
+
+
+def gather_counts_start(n_local, group=None):
+    """Asynchronous gather_counts(): enqueues the all-gather and returns a PendingCounts."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return PendingCounts(None, None, int(n_local))
+    dev = _device(group)
+    mine = torch.tensor([int(n_local)], dtype=torch.int64).to(dev, non_blocking=True)
+    out = torch.zeros(dist.get_world_size(group), dtype=torch.int64, device=dev)
+    work = dist.all_gather_into_tensor(out, mine, group=group, async_op=True)
+    return PendingCounts(out, work, int(n_local))
+
+
 def gather_matches(local, dst=0, group=None):
     """Gathers MATCH_DTYPE records of all ranks on `dst`, merged by (file_id, start); others get None.
     Counts first (all-gather), then one padded all-gather of the raw record bytes."""

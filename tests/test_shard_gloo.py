@@ -33,6 +33,8 @@ def _worker(rank, world, port, mode, q):
     ids = shard.files_of_rank(N_FILES, rank, world, mode)
     local = _scan_files(ids)
     counts = shard.gather_counts(len(local))
+    pend = shard.gather_counts_start(len(local))  # asynchronous flavour: same answer
+    assert pend.finish().tolist() == counts.tolist()
     merged = shard.gather_matches(local, dst=0)
     q.put((rank, ids.tolist(), counts.tolist(), None if merged is None else merged.tobytes()))
     dist.barrier()
@@ -72,6 +74,7 @@ def test_two_rank_shard_and_gather(mode):
 def test_single_rank_passthrough():
     local = _scan_files(range(3))
     assert shard.gather_counts(len(local)).tolist() == [len(local)]
+    assert shard.gather_counts_start(len(local)).finish().tolist() == [len(local)]
     assert shard.gather_matches(local).tobytes() == np.sort(local, order=["file_id", "start"], kind="stable").tobytes()
 
 
