@@ -1,0 +1,38 @@
+"""What the pattern compiler hands to the device, interpreted on the CPU and compared with the oracle (no GPU):
+tests/model_check.cc runs the compiled Program the way the resolve kernels do -- with the device VM's own source,
+extracted verbatim from grab_b200/csrc/resolve_kernels.cu and compiled for the host -- inside the reference's loop."""
+import os
+import subprocess
+
+import test_gpu_random_patterns as R
+import test_gpu_parity as P
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+BEGIN = "// ---- device backtracking VM (general patterns) ----"
+END = "// ---- 3. per-unit replay of the reference loop ----"
+
+
+def test_compiled_programs_match_the_oracle(tmp_path):
+    src = open(os.path.join(ROOT, "grab_b200", "csrc", "resolve_kernels.cu")).read()
+    assert BEGIN in src and END in src
+    snippet = src[src.index(BEGIN):src.index(END)]
+    assert "vm_exec" in snippet and "__global__" not in snippet
+    (tmp_path / "vm_snippet.inc").write_text(snippet)
+    pats = list(R.PATTERNS) + R.make_cases(400, 777) + list(P.DIFF_PATTERNS) + [
+        "foo|bar|baz|quux", "[A-Za-z0-9_]{16,}", "[0-9]{2,}", "(?i)ab|ba", "a.c", "ab?c", "a{2,4}", "\\d{2}-\\d{2}", "<[a-z]+>", "qz\\w+;",
+        "a+b+", "(?:a|b)+c", "^a.*c$", "\\bab\\b", "a.*?c", "[ab]+?c", "x*ab", "(?:ab)*c", "ab|abc|a", "a(?:b|bc)c"]
+    (tmp_path / "patterns.txt").write_text("\n".join(p for p in pats if "\n" not in p) + "\n")
+    exe = str(tmp_path / "model_check")
+    subprocess.run(["gcc", "-O2", "-c", os.path.join(ROOT, "oracle", "grab_oracle.c"), "-o", str(tmp_path / "oracle.o")], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", str(tmp_path), os.path.join(HERE, "model_check.cc"),
+                    os.path.join(ROOT, "grab_b200", "csrc", "pattern.cc"), str(tmp_path / "oracle.o"), "-I", os.path.join(ROOT, "include"),
+                    "-o", exe], check=True)
+    p = subprocess.run([exe, str(tmp_path / "patterns.txt")], stdout=subprocess.PIPE, timeout=900)
+    out = p.stdout.decode()
+    assert p.returncode == 0 and "model ok" in out, out[-3000:]
+    # the sample must actually exercise the engines
+    tail = out.strip().splitlines()[-2]
+    served = int(tail.split("served ")[1].split(" ")[0])
+    vm = int(tail.split("(")[1].split(" ")[0])
+    assert served > 300 and vm > 100, tail
