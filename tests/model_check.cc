@@ -3,7 +3,8 @@
 // first sequence in preference order at the leftmost position; RUN: greedy class run of at least run_min; general
 // patterns: the device VM, whose source is extracted verbatim from resolve_kernels.cu by tests/test_model.py
 // (vm_snippet.inc) and compiled here for the host -- inside the reference's loop (moving search start, strict '<'
-// guard, grab.cc:175-213).  Also checks that the candidate filter of general patterns (leading-byte sequences / run
+// guard, grab.cc:175-213).  Then the same with the device's own per-unit walk kernels (k_walk / k_walk_vm, same
+// extraction) fed with the candidates the scan kernels deliver by contract, in all three modes (ALL / FIRST / LINE).  Also checks that the candidate filter of general patterns (leading-byte sequences / run
 // starts) never rejects a position where the VM matches.
 // Usage: model_check PATTERN_FILE   (one pattern per line)
 #include <cstdio>
@@ -13,16 +14,34 @@
 #include <string>
 #include <vector>
 
+#include "../include/gscan.h"
 #include "../grab_b200/csrc/pattern.h"
+#include "../grab_b200/csrc/kernels.h" // ResolveArgs, DevUnit, FinalRec, OutRec (host-includable: PODs + launcher prototypes)
 extern "C" {
 #include "../oracle/grab_oracle.h"
 }
 
-namespace gscan {
-struct ResolveArgs { const uint32_t *vm_code; const uint32_t *vm_sets; };
+// the extracted device source (VM + the per-unit walk kernels of resolve_kernels.cu) compiled for the host: CUDA's
+// qualifiers vanish, the thread index is a global we set to the unit under test, atomicOr is a plain OR
+#undef __device__
+#undef __global__
+#undef __forceinline__
+#undef __launch_bounds__
 #define __device__
+#define __global__
 #define __forceinline__ inline
+#define __launch_bounds__(...)
+namespace gscan {
+struct ModelIdx { uint32_t x; };
+static ModelIdx model_blockIdx{0}, model_blockDim{1}, model_threadIdx{0};
+#define blockIdx model_blockIdx
+#define blockDim model_blockDim
+#define threadIdx model_threadIdx
+static inline uint32_t atomicOr(uint32_t *p, uint32_t v) { const uint32_t o = *p; *p |= v; return o; }
 #include "vm_snippet.inc"
+#undef blockIdx
+#undef blockDim
+#undef threadIdx
 } // namespace gscan
 
 using namespace gscan;
@@ -42,7 +61,10 @@ static bool seq_at(const Sequence &q, const uint8_t *s, size_t len, size_t pos)
 // 0 ok, -1 VM limit, -2 filter soundness violated
 static int emulate(const Program &p, const uint8_t *s, size_t len, std::vector<M> &out, std::string &why)
 {
-	ResolveArgs R{p.vm_code.data(), p.vm_sets.data()};
+	ResolveArgs R;
+	memset(&R, 0, sizeof R);
+	R.vm_code = p.vm_code.data();
+	R.vm_sets = p.vm_sets.data();
 	size_t start = 0;
 	while (start + (size_t)p.minlen < len) { // grab.cc:175
 		bool found = false;
@@ -77,6 +99,66 @@ static int emulate(const Program &p, const uint8_t *s, size_t len, std::vector<M
 	return 0;
 }
 
+// What the scan kernels deliver for one unit, by contract (scan_kernels.cu): FIXED -- every position where an
+// alternative (for general patterns: a leading-byte prefix) lies entirely inside the unit, with the length of the first
+// one in preference order; RUN (and general patterns that begin with a class repeat) -- the first byte of every maximal
+// class run of at least run_min bytes.  Position order.
+static void candidates(const Program &p, const uint8_t *s, size_t len, std::vector<OutRec> &ord)
+{
+	const bool runs = p.kind == ENGINE_RUN || (p.use_vm && p.vm_runstart);
+	for (size_t pos = 0; pos < len; pos++) {
+		if (runs) {
+			if (!p.run_class.has(s[pos]) || (pos > 0 && p.run_class.has(s[pos - 1]))) continue;
+			size_t k = 0;
+			while (pos + k < len && p.run_class.has(s[pos + k])) k++;
+			if (k >= (size_t)p.run_min) ord.push_back(OutRec{0, (uint32_t)pos, 0, 0});
+		} else {
+			for (auto &q : p.seqs)
+				if (seq_at(q, s, len, pos)) { ord.push_back(OutRec{0, (uint32_t)pos, (uint32_t)q.size(), 0}); break; }
+		}
+	}
+}
+
+// count pass, slot scan (one unit: slot 0), write pass -- the device code of resolve_kernels.cu, on the host.
+// 0 ok, -1 VM limit
+static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, std::vector<M> &out)
+{
+	std::vector<OutRec> ord;
+	candidates(p, s, len, ord);
+	DevUnit du;
+	memset(&du, 0, sizeof du);
+	du.ptr = (uint64_t)(uintptr_t)s;
+	du.len = (uint32_t)len;
+	uint32_t unit_start[2] = {0, (uint32_t)ord.size()}, unit_out[1] = {0}, totals[4] = {0, 0, 0, 0};
+	ResolveArgs R;
+	memset(&R, 0, sizeof R);
+	R.units = &du;
+	R.n_units = 1;
+	R.ord = ord.empty() ? nullptr : ord.data();
+	R.unit_start = unit_start;
+	R.unit_out = unit_out;
+	R.totals = totals;
+	R.mode = mode;
+	R.minlen = (uint32_t)p.minlen;
+	R.engine = p.use_vm ? (uint32_t)GSCAN_ENGINE_VM : (uint32_t)p.kind;
+	R.run_min = (uint32_t)p.run_min;
+	for (int i = 0; i < 8; i++) R.bitmap[i] = p.run_class.w[i];
+	R.vm_code = p.vm_code.data();
+	R.vm_sets = p.vm_sets.data();
+	R.vm_runstart = p.vm_runstart ? 1u : 0u;
+	model_threadIdx.x = 0;
+	if (p.use_vm) k_walk_vm<false>(R); else k_walk<false>(R);
+	if (totals[2]) return -1;
+	std::vector<FinalRec> fin(unit_out[0] + 1);
+	const uint32_t n = unit_out[0];
+	unit_out[0] = 0;
+	R.out = fin.data();
+	if (p.use_vm) k_walk_vm<true>(R); else k_walk<true>(R);
+	if (totals[2]) return -1;
+	for (uint32_t i = 0; i < n; i++) out.push_back(M{fin[i].start, fin[i].len});
+	return 0;
+}
+
 int main(int argc, char **argv)
 {
 	if (argc < 2) return 2;
@@ -92,7 +174,7 @@ int main(int argc, char **argv)
 		for (auto &c : b) c = (uint8_t)al[rnd() % na];
 		subjects.push_back(b);
 	}
-	int n_pat = 0, n_served = 0, n_vm = 0, n_cmp = 0, n_limit = 0, bad = 0;
+	int n_pat = 0, n_served = 0, n_vm = 0, n_cmp = 0, n_walk = 0, n_limit = 0, bad = 0;
 	while (std::getline(f, pat)) {
 		if (pat.empty()) continue;
 		n_pat++;
@@ -124,10 +206,30 @@ int main(int argc, char **argv)
 				if (bad > 20) { go_matches_free(&want); go_free(re); return 1; }
 			}
 			go_matches_free(&want);
+			// the device's own walk code in all three modes
+			const int modes[3] = {GO_MODE_ALL, GO_MODE_FIRST, GO_MODE_LINE};
+			const uint32_t dmodes[3] = {GSCAN_MODE_ALL, GSCAN_MODE_FIRST, GSCAN_MODE_LINE};
+			for (int m = 0; m < 3; m++) {
+				go_matches w2 = {0, 0, 0};
+				if (go_scan_window(re, sb.data(), sb.size(), 0, 0, modes[m], 0, &w2) != 0) { go_matches_free(&w2); continue; }
+				std::vector<M> g2;
+				if (walk(p, sb.data(), sb.size(), dmodes[m], g2) != 0) { go_matches_free(&w2); n_limit++; continue; }
+				bool ok = g2.size() == w2.n;
+				for (size_t i = 0; ok && i < g2.size(); i++) ok = g2[i].pos == w2.v[i].start && g2[i].len == w2.v[i].len;
+				n_walk++;
+				if (!ok) {
+					bad++;
+					printf("WALK MISMATCH %s mode %d (engine %d vm %d runstart %d) on \"", pat.c_str(), m, (int)p.kind, (int)p.use_vm, (int)p.vm_runstart);
+					for (uint8_t c : sb) printf(c == '\n' ? "\\n" : c == '\t' ? "\\t" : "%c", c);
+					printf("\": got %zu want %zu\n", g2.size(), w2.n);
+					if (bad > 20) { go_matches_free(&w2); go_free(re); return 1; }
+				}
+				go_matches_free(&w2);
+			}
 		}
 		go_free(re);
 	}
-	printf("patterns %d, served %d (%d through the VM), comparisons %d, limit skips %d, mismatches %d\n", n_pat, n_served, n_vm, n_cmp, n_limit, bad);
+	printf("patterns %d, served %d (%d through the VM), comparisons %d + %d through the walk kernels, limit skips %d, mismatches %d\n", n_pat, n_served, n_vm, n_cmp, n_walk, n_limit, bad);
 	if (bad == 0) printf("model ok\n");
 	return bad ? 1 : 0;
 }
