@@ -97,7 +97,7 @@ struct Node {
 
 constexpr uint32_t kInf = UINT32_MAX;
 
-struct Flags { bool icase = false, dotall = false, multiline = false; };
+struct Flags { bool icase = false, dotall = false, multiline = false, ungreedy = false, extended = false; };
 
 class Parser {
 public:
@@ -323,7 +323,13 @@ private:
 					while (more() && *p_ != close) p_++;
 					if (!more()) { fail("unterminated group name"); return nullptr; }
 					p_++;
-				} else if (strchr("=!<>|#R(&C+0123456789", (int)*p_)) {
+				} else if (*p_ == '#') { // (?#comment): up to the next ')'
+					while (more() && *p_ != ')') p_++;
+					if (!more()) { fail("missing ) after comment"); return nullptr; }
+					p_++;
+					flag_only = true;
+					return nullptr;
+				} else if (strchr("=!<>|R(&C+0123456789", (int)*p_)) {
 					fail("lookaround / atomic / recursive / conditional groups are not supported by the device engines");
 					return nullptr;
 				} else {
@@ -336,6 +342,8 @@ private:
 						if (o == 'i') { nf.icase = on; continue; }
 						if (o == 's') { nf.dotall = on; continue; }
 						if (o == 'm') { nf.multiline = on; continue; }
+						if (o == 'U') { nf.ungreedy = on; continue; } // PCRE_UNGREEDY: greedy <-> lazy
+						if (o == 'x') { nf.extended = on; continue; } // PCRE_EXTENDED: white space and #-comments ignored
 						if (o == ')') { f = nf; flag_only = true; return nullptr; }
 						if (o == ':') { inner = nf; capturing = false; break; }
 						fail("unsupported inline option");
@@ -395,15 +403,38 @@ private:
 		}
 	}
 
+	// (?x): outside character classes white space is ignored and # starts a comment that ends at the next newline
+	// (?#...) comments vanish wherever they stand, also between an item and its quantifier ("a(?#x)+" is "a+")
+	void skip_extended(const Flags &f)
+	{
+		while (more()) {
+			const unsigned c = *p_;
+			if (c == '(' && p_ + 2 < end_ && p_[1] == '?' && p_[2] == '#') {
+				const uint8_t *q = p_ + 3;
+				while (q < end_ && *q != ')') q++;
+				if (q >= end_) return; // unterminated: atom() reports it
+				p_ = q + 1;
+				continue;
+			}
+			if (!f.extended) break;
+			if (c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v') { p_++; continue; }
+			if (c == '#') { while (more() && *p_ != '\n') p_++; continue; }
+			break;
+		}
+	}
+
 	NodeP concatenation(Flags &f)
 	{
 		NodeP cat(new Node(Node::CAT));
-		while (ok_ && more() && *p_ != '|' && *p_ != ')') {
+		for (;;) {
+			skip_extended(f);
+			if (!(ok_ && more() && *p_ != '|' && *p_ != ')')) break;
 			bool flag_only = false;
 			NodeP a = atom(f, flag_only);
 			if (!ok_) break;
 			if (flag_only) continue;
 			if (!a) break;
+			skip_extended(f);
 			if (more()) {
 				uint32_t mn = 0, mx = 0;
 				bool q = false;
@@ -419,8 +450,9 @@ private:
 					NodeP r(new Node(Node::REP));
 					r->rmin = mn;
 					r->rmax = mx;
-					if (more() && *p_ == '?') { r->lazy = true; p_++; }
-					else if (more() && *p_ == '+') { r->possessive = true; p_++; }
+					r->lazy = f.ungreedy;
+					if (more() && *p_ == '?') { r->lazy = !f.ungreedy; p_++; }
+					else if (more() && *p_ == '+') { r->possessive = true; r->lazy = false; p_++; }
 					if (a->kind == Node::ASSERT) { fail("quantified assertion"); break; }
 					r->kids.push_back(std::move(a));
 					a = std::move(r);

@@ -124,7 +124,7 @@ static void nfree(node *n)
 	free(n);
 }
 
-typedef struct { int icase, dotall, multiline; } pflags;
+typedef struct { int icase, dotall, multiline, ungreedy, extended; } pflags;
 
 static node *parse_alt(parser *P, pflags f);
 
@@ -348,8 +348,14 @@ static node *parse_atom(parser *P, pflags *f, int *is_flag_change)
 				while (P->p < P->end && *P->p != close) P->p++;
 				if (P->p >= P->end) { perr(P, "bad named group"); return NULL; }
 				P->p++;
+			} else if (*P->p == '#') { /* (?#comment): up to the next ')' */
+				while (P->p < P->end && *P->p != ')') P->p++;
+				if (P->p >= P->end) { perr(P, "missing ) after comment"); return NULL; }
+				P->p++;
+				*is_flag_change = 1;
+				return NULL;
 			} else if (*P->p == '=' || *P->p == '!' || *P->p == '<' || *P->p == '>' || *P->p == '|' ||
-			           *P->p == '#' || *P->p == 'R' || *P->p == '(' || c_isdigit(*P->p) || *P->p == '&' ||
+			           *P->p == 'R' || *P->p == '(' || c_isdigit(*P->p) || *P->p == '&' ||
 			           *P->p == 'C' || *P->p == '+') {
 				perr(P, "group construct not modelled (lookaround/atomic/recursion/conditional)");
 				return NULL;
@@ -364,6 +370,8 @@ static node *parse_atom(parser *P, pflags *f, int *is_flag_change)
 					if (o == 'i') { nf.icase = on; continue; }
 					if (o == 's') { nf.dotall = on; continue; }
 					if (o == 'm') { nf.multiline = on; continue; }
+					if (o == 'U') { nf.ungreedy = on; continue; } /* PCRE_UNGREEDY: greedy <-> lazy */
+					if (o == 'x') { nf.extended = on; continue; } /* PCRE_EXTENDED: white space and #-comments ignored */
 					if (o == ')') { *f = nf; *is_flag_change = 1; return NULL; }
 					if (o == ':') { inner = nf; capturing = 0; break; }
 					perr(P, "inline option not modelled");
@@ -420,10 +428,32 @@ static node *parse_atom(parser *P, pflags *f, int *is_flag_change)
 	}
 }
 
+/* (?x): outside character classes white space is ignored and # starts a comment that ends at the next newline */
+/* (?#...) comments vanish wherever they stand, also between an item and its quantifier ("a(?#x)+" is "a+") */
+static void skip_extended(parser *P, const pflags *f)
+{
+	while (P->p < P->end) {
+		unsigned c = *P->p;
+		if (c == '(' && P->p + 2 < P->end && P->p[1] == '?' && P->p[2] == '#') {
+			const uint8_t *q = P->p + 3;
+			while (q < P->end && *q != ')') q++;
+			if (q >= P->end) return; /* unterminated: parse_atom reports it */
+			P->p = q + 1;
+			continue;
+		}
+		if (!f->extended) break;
+		if (c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v') { P->p++; continue; }
+		if (c == '#') { while (P->p < P->end && *P->p != '\n') P->p++; continue; }
+		break;
+	}
+}
+
 static node *parse_concat(parser *P, pflags *f)
 {
 	node *cat = nnew(N_CAT);
-	while (!P->failed && P->p < P->end && *P->p != '|' && *P->p != ')') {
+	for (;;) {
+		skip_extended(P, f);
+		if (P->failed || P->p >= P->end || *P->p == '|' || *P->p == ')') break;
 		int flagchange = 0;
 		node *a = parse_atom(P, f, &flagchange);
 		if (P->failed) { nfree(a); break; }
@@ -431,6 +461,7 @@ static node *parse_concat(parser *P, pflags *f)
 		if (!a) break;
 		/* quantifier */
 		for (;;) {
+			skip_extended(P, f);
 			if (P->p >= P->end) break;
 			uint32_t mn = 0, mx = 0;
 			unsigned q = *P->p;
@@ -444,8 +475,8 @@ static node *parse_concat(parser *P, pflags *f)
 				isq = r;
 			}
 			if (!isq) break;
-			int kind = Q_GREEDY;
-			if (P->p < P->end && *P->p == '?') { kind = Q_LAZY; P->p++; }
+			int kind = f->ungreedy ? Q_LAZY : Q_GREEDY;
+			if (P->p < P->end && *P->p == '?') { kind = f->ungreedy ? Q_GREEDY : Q_LAZY; P->p++; }
 			else if (P->p < P->end && *P->p == '+') { kind = Q_POSSESSIVE; P->p++; }
 			if (a->type == N_ASSERT) { perr(P, "quantified assertion not modelled"); nfree(a); a = NULL; break; }
 			node *r = nnew(N_REP);
@@ -670,7 +701,7 @@ go_regex *go_compile(const char *pattern, size_t len, unsigned flags, char *err,
 	P.errlen = errlen;
 	if (err && errlen) err[0] = 0;
 	node *root;
-	pflags f0 = {0, 0, 0};
+	pflags f0 = {0, 0, 0, 0, 0};
 	if (flags & GO_LITERAL) {
 		root = nnew(N_CAT);
 		for (size_t i = 0; i < len; i++) nadd(root, mkset_char((uint8_t)pattern[i], f0));

@@ -21,6 +21,8 @@ def test_compiled_programs_match_the_oracle(tmp_path):
     (tmp_path / "vm_snippet.inc").write_text(snippet)
     pats = list(R.PATTERNS) + R.make_cases(400, 777) + list(P.DIFF_PATTERNS) + [
         "foo|bar|baz|quux", "[A-Za-z0-9_]{16,}", "[0-9]{2,}", "(?i)ab|ba", "a.c", "ab?c", "a{2,4}", "\\d{2}-\\d{2}", "<[a-z]+>", "qz\\w+;",
+        "(?U)a+b", "(?U)a+?b", "(?U)a{2,}", "(?U)\\w+ ", "(?U:a+)b", "(?U)a*b", "(?U)(?:ab)+c", "a(?U)b+c?", "(?x) a b c", "(?x)a +b",
+        "(?xi)A B", "(?x)a b | b c", "a(?x) b c", "(?x)a{2} b", "(?x) [ab] {2} c", "a(?#hello)b", "(?#c)a|b(?#d)c", "a(?#x)+b",
         "a+b+", "(?:a|b)+c", "^a.*c$", "\\bab\\b", "a.*?c", "[ab]+?c", "x*ab", "(?:ab)*c", "ab|abc|a", "a(?:b|bc)c"]
     (tmp_path / "patterns.txt").write_text("\n".join(p for p in pats if "\n" not in p) + "\n")
     exe = str(tmp_path / "model_check")

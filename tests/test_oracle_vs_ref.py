@@ -60,6 +60,31 @@ def test_random_patterns_stdout_identical(tmp_path):
     assert checked >= 60
 
 
+OPTION_PATTERNS = [r"(?U)a+b", r"(?U)a+?b", r"(?U)a{2,}", r"(?U)\w+ ", r"(?U:a+)b", r"(?U)a*b", r"(?U)(?:ab)+c", r"a(?U)b+c?", r"(?U)a++b",
+                   r"(?x) a b c", "(?x)a b # comment\n c", r"(?x)a\ b", r"(?x)a[ ]b", r"(?x)a +b", r"(?xi)A B", r"(?x)a b | b c", r"a(?x) b c",
+                   r"(?x)a{2} b", r"(?x: a b ) c", r"(?x) [ab] {2} c", "(?x)# only a comment\nab",
+                   r"a(?#hello)b", r"(?#c)a|b(?#d)c", r"a(?#x)+b"]
+
+
+@needs_ref
+def test_inline_options_ungreedy_extended_comment(tmp_path):
+    """(?U), (?x) and (?#...) as the reference's PCRE build treats them: identical stdout in all three output modes."""
+    rnd = random.Random(5)
+    inputs = random_inputs(rnd, 15) + [b"aaab ab\nfoo  bar # x\nabcabc aXb a\nb\n", b"a b c abc a  b\n", b"aab aaab abbc abc\n"]
+    checked = 0
+    for pat in OPTION_PATTERNS:
+        o = O.Regex(pat)
+        if o.nullable:
+            continue
+        for i, data in enumerate(inputs):
+            path = tmp_path / ("in%d" % i)
+            path.write_bytes(data)
+            for flags, kw in ((("-O", "-l"), dict(offsets=True, line=False)), ((), dict()), (("-s", "-O"), dict(offsets=True, single=True))):
+                assert o.grab(data, **kw) == ref_offsets(pat, str(path), flags), (pat, flags, data)
+        checked += 1
+    assert checked >= 20
+
+
 @needs_ref
 def test_minlen_quirk_q1_against_reference(tmp_path):
     # the strict '<' of grab.cc:175 for every length around minlen
