@@ -177,6 +177,35 @@ def run_reference(a, rank, world):
     print(json.dumps(line))
 
 
+def e2e_all_ranks(scan, want_bytes, steps, world, rank, torch, dist, device, sync_all):
+    """The timed end-to-end region at N > 1: every rank runs `scan()` (one gscan_scan_batch over its host sample) `steps`
+    times between barriers.  Returns (seconds per step of the slowest rank, records per step on this rank, results equal
+    `want_bytes` on every rank), or None when any rank could not run it (scan is None there, or it raised): every rank
+    reaches every collective whatever happens on the others, so a local failure can drop the number but never hang the job."""
+    failed, bad, n_rec = (1.0 if scan is None else 0.0), 0.0, 0
+    sync_all()
+    t0 = time.perf_counter()
+    try:
+        if not failed:
+            out = None
+            for _ in range(steps):
+                out = scan()
+            n_rec = len(out)
+            bad = 0.0 if out.tobytes() == want_bytes else 1.0
+    except Exception as ex:  # noqa: BLE001
+        failed = 1.0
+        sys.stderr.write("bench: e2e leg failed on rank %d: %r\n" % (rank, ex))
+    if device == "cuda":
+        torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    sync_all()
+    t = torch.tensor([dt, bad, failed], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if float(t[2].item()) != 0.0:
+        return None
+    return float(t[0].item()), n_rec, float(t[1].item()) == 0.0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -374,6 +403,38 @@ def main():
                 shutil.rmtree(d, ignore_errors=True)
         else:
             line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/grab_ref missing"}
+
+    if world > 1 and not a.quick:
+        # ---- e2e at N GPUs: every rank feeds its own GPU from its own pinned host sample over its own PCIe link,
+        # same call and same timed region as at N = 1; aggregate = N x bytes / slowest rank
+        e_files = int(min(a.e2e_gib * GiB, corpus_bytes) // FILE_LEN)
+        hptr, scan = None, None
+        try:
+            hptr = G.lib().gscan_host_alloc(e_files * FILE_LEN)
+            if not hptr:
+                raise RuntimeError("pinned allocation failed")
+            G.lib().gscan_memcpy_d2h(ctx._h, hptr, dptr, e_files * FILE_LEN)
+            hunits = np.zeros(e_files, dtype=G.UNIT_DTYPE)
+            hunits["ptr"] = hptr + np.arange(e_files, dtype=np.uint64) * np.uint64(FILE_LEN)
+            hunits["len"] = FILE_LEN
+            hunits["file_id"] = first_id + np.arange(e_files, dtype=np.uint32)
+            for _ in range(2):
+                ctx.scan_units(pat, hunits)
+            scan = lambda: ctx.scan_units(pat, hunits)  # noqa: E731
+        except Exception as ex:  # noqa: BLE001
+            sys.stderr.write("bench: e2e leg at %d GPUs failed on rank %d: %r\n" % (world, rank, ex))
+        want = r[r["file_id"] < first_id + e_files].tobytes()
+        res = e2e_all_ranks(scan, want, a.steps, world, rank, torch, dist, "cuda", sync_all)
+        if res is not None:
+            e_dt, n_rec, ok = res
+            if not ok:
+                line["parity"] = "MISMATCH(e2e)"
+            line["e2e"] = {"value": world * e_files * FILE_LEN / e_dt / 1e9, "unit": "GB/s",
+                           "h2d_bytes_per_step": int(world * (e_files * FILE_LEN + e_files * 32)),
+                           "d2h_bytes_per_step": int(world * (n_rec * 16 + 24)),
+                           "sample": "%d files x 1 MiB in pinned host memory per rank, %d ranks, slowest rank" % (e_files, world)}
+        if hptr:
+            G.lib().gscan_host_free(hptr)
 
     batch.free()
     ctx.device_free(dptr)
