@@ -136,6 +136,12 @@ int FileGrep::find(const char *path, const struct stat *st, int)
 	const off_t overlap = 0x1000; // grab.cc:151
 	const uint32_t seq = d_file_seq++;
 	for (off_t off = 0; off < st->st_size; off += ((off_t)d_chunk_size - overlap)) { // grab.cc:154
+		// -s: the reference stops reading a file once one of its windows printed (grab.cc:232-233).  The sequencer
+		// suppresses later windows anyway; not queueing them only saves the work when an earlier batch is already out
+		if (d_single_match && d_pipe) {
+			std::lock_guard<std::mutex> g(d_pipe->mu);
+			if (d_pipe->have_done && d_pipe->done_seq == seq) break;
+		}
 		clen = (st->st_size - off < (off_t)d_chunk_size) ? (size_t)(st->st_size - off) : d_chunk_size;
 		void *m = mmap(nullptr, clen, PROT_READ, MAP_PRIVATE | MAP_NORESERVE, fd, off); // grab.cc:126-128,161
 		if (m == MAP_FAILED) {
