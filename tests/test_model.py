@@ -24,6 +24,9 @@ def test_compiled_programs_match_the_oracle(tmp_path):
         "(?U)a+b", "(?U)a+?b", "(?U)a{2,}", "(?U)\\w+ ", "(?U:a+)b", "(?U)a*b", "(?U)(?:ab)+c", "a(?U)b+c?", "(?x) a b c", "(?x)a +b",
         "(?xi)A B", "(?x)a b | b c", "a(?x) b c", "(?x)a{2} b", "(?x) [ab] {2} c", "a(?#hello)b", "(?#c)a|b(?#d)c", "a(?#x)+b",
         "a+b+", "(?:a|b)+c", "^a.*c$", "\\bab\\b", "a.*?c", "[ab]+?c", "x*ab", "(?:ab)*c", "ab|abc|a", "a(?:b|bc)c"]
+    import json
+    kat = json.load(open(os.path.join(HERE, "golden", "kat.json")))
+    pats += sorted({c["pattern"] for c in kat["cases"]})  # the reference's recorded cases
     (tmp_path / "patterns.txt").write_text("\n".join(p for p in pats if "\n" not in p) + "\n")
     exe = str(tmp_path / "model_check")
     subprocess.run(["gcc", "-O2", "-c", os.path.join(ROOT, "oracle", "grab_oracle.c"), "-o", str(tmp_path / "oracle.o")], check=True)
