@@ -178,3 +178,33 @@ def test_host_lane_failure_is_loud(tmp_path):
     assert b"injected failure on device 1" in se
     rc, so, se = run(["-O", "-l", "foo", "tree/d0/f000.txt"], cwd=str(tmp_path), env=dict(GRAB_B200_DEVICE="9"))
     assert rc == 255 and b"no such device" in se and so == b""
+
+
+@pytest.mark.parametrize("san", ["address,undefined", "thread"], ids=["asan_ubsan", "tsan"])
+def test_host_pipeline_under_sanitizers(san, tmp_path):
+    """The host side built with ASan+UBSan / TSan (engine double included): 6 lanes on 3 'GPUs', tiny batches, jitter,
+    also under -n 4 -- no report, and the same stdout as the plain build."""
+    tag = san.split(",")[0]
+    exe = str(tmp_path / ("hc_" + tag))
+    objs = []
+    for src in (os.path.join(HERE, "hostcheck", "gscan_double.c"), os.path.join(ROOT, "oracle", "grab_oracle.c")):
+        o = str(tmp_path / (os.path.basename(src) + ".o"))
+        subprocess.run(["gcc", "-O1", "-g", "-fsanitize=" + san, "-c", src, "-o", o], check=True)
+        objs.append(o)
+    subprocess.run(["g++", "-O1", "-g", "-fsanitize=" + san, "-std=c++17", os.path.join(ROOT, "grab_b200", "host", "filegrep.cc"),
+                    os.path.join(ROOT, "grab_b200", "host", "main.cc")] + objs + ["-pthread", "-o", exe], check=True)
+    _tree(tmp_path, n_files=200, seed=11)
+    env = dict(GRAB_B200_NDEV="3", GRAB_B200_LANES="2", GRAB_B200_BATCH_BYTES="2000", GSCAN_DOUBLE_JITTER="1",
+               TSAN_OPTIONS="halt_on_error=1 exitcode=66", ASAN_OPTIONS="detect_leaks=0 exitcode=66", UBSAN_OPTIONS="halt_on_error=1 exitcode=66")
+    variants = [["-r", "-O", "-l"], ["-r"], ["-r", "-s"]]
+    if (os.cpu_count() or 1) >= 4:
+        variants.append(["-r", "-n", "4", "-O", "-l"])
+    for flags in variants:
+        rc, so, se = run(flags + ["foo|bar|baz|quux", "tree"], cwd=str(tmp_path), env=env, binary=exe)
+        assert rc == 0 and b"Sanitizer" not in se, (flags, se.decode()[-2000:])
+        rc0, plain, _ = run(flags + ["foo|bar|baz|quux", "tree"], cwd=str(tmp_path))
+        assert rc0 == 0
+        if "-n" in flags:
+            assert sorted(so.split(b"\n")) == sorted(plain.split(b"\n"))
+        else:
+            assert so == plain
