@@ -68,6 +68,7 @@ _PROTOS = {
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
     "gscan_batch_free": (None, [ctypes.c_void_p, ctypes.c_void_p]),
     "gscan_last_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Stats)]),
+    "gscan_last_device_matches": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
     "gscan_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "gscan_host_free": (None, [ctypes.c_void_p]),
     "gscan_device_alloc": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_size_t]),
@@ -230,6 +231,12 @@ class Context:
         out, n = ctypes.c_void_p(), ctypes.c_size_t()
         self._check(lib().gscan_batch_scan(self._h, pattern._h, batch._h, mode, ctypes.byref(out), ctypes.byref(n)))
         return self._take(out, n)
+
+    def last_device_matches(self):
+        """(device pointer, count) of the last scan's records in HBM (valid until the next scan on this context)."""
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        self._check(lib().gscan_last_device_matches(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return (p.value or 0), n.value
 
     def stats(self):
         s = Stats()

@@ -4,11 +4,14 @@
 
 namespace gscan {
 
-// Geometry.  A tile (the planning unit, one 32-byte descriptor) is always 64 KiB of one unit; the
-// scan kernel cuts it into slices, the amount one warp scans per step.  Geometry is a template
-// parameter of the kernel, chosen per engine (memory-bound filters want big slices and a deep
-// ring, instruction-bound ones want as many warps as fit).
-constexpr int kTileBytes = 65536;
+// Geometry.  A tile (the planning unit, one 32-byte descriptor) is up to 2^tile_shift bytes of one unit --
+// 64 KiB for batches of big units, down to 4 KiB for batches of many small files (the batch planner picks
+// the power of two next to the average unit length, so a 16 KiB file is four full 4 KiB slices and not a
+// sixteenth of a 64 KiB tile each); the scan kernel cuts a tile into slices of Geom::kSlice bytes, the
+// amount one warp scans per step.  Geometry is a template parameter of the kernel, chosen per engine
+// (memory-bound filters want a deep ring, instruction-bound ones want as many warps as fit).
+constexpr int kTileBytes = 65536;     // largest tile
+constexpr int kMinTileShift = 12, kMaxTileShift = 16;
 constexpr int kSmemBudget = 227 * 1024;
 
 template <int W, int R, int S>
@@ -16,7 +19,7 @@ struct Geom {
 	static constexpr int kWarps = W;          // warps per CTA, every one an independent scanner
 	static constexpr int kRing = R;           // slices in flight per warp
 	static constexpr int kSlice = S;          // bytes one warp scans per step (rows of 512)
-	static constexpr int kSlicesPerTile = kTileBytes / S;
+	static_assert(S >= 512 && S <= (1 << kMinTileShift) && (S & (S - 1)) == 0, "a slice is a power of two that divides the smallest tile");
 	static constexpr int kThreads = W * 32;
 };
 typedef Geom<16, 3, 4096> GeomStream;  // memory-bound: the FIXED filters
@@ -31,6 +34,12 @@ typedef Geom<GS_BAL_W, GS_BAL_R, GS_BAL_S> GeomBalanced;
 // hashed engine: issue-bound, wants warps (20 = 5 per scheduler measured best; 16, 18 and 22 were 8-10 % slower) and
 // long slices (fewer ring refills per byte): 2 x 4 KiB per warp, which leaves 32 KiB for the table
 typedef Geom<20, 2, 4096> GeomHash;
+// balanced pair filter (FixedBEngine): issue-bound like the hashed engine
+#ifndef GS_PAIR_W
+#define GS_PAIR_W 20
+#define GS_PAIR_R 2
+#endif
+typedef Geom<GS_PAIR_W, GS_PAIR_R, 4096> GeomPair;
 
 struct ScanGeom { int warps, ring, slice; }; // host-side mirror of the chosen Geom
 
@@ -46,7 +55,7 @@ struct TileDesc {
 static_assert(sizeof(TileDesc) == 32, "TileDesc layout");
 
 // One segment == one slice; candidates of a segment are contiguous and ordered in the candidate
-// buffer.  seg id = tile * slices_per_tile + slice.
+// buffer.  seg id = (tile << spt_shift) + slice.
 struct SegEntry { uint32_t base, n; }; // n: low 16 bits count (<= slice bytes), high 16 bits generation tag of the scan that wrote it
 __host__ __device__ inline uint32_t seg_count(const SegEntry &e, uint32_t tag) { return (e.n >> 16) == tag ? (e.n & 0xffffu) : 0u; }
 
@@ -72,17 +81,21 @@ struct FixedParams {
 	// triples (anchor, anchor + delta, anchor + d2): stage 2 of the pair filter (flagged rows only), or --
 	// stage1_triples -- the stage-1 filter itself (Fixed3Engine; sh1/sh2 = 8*delta, 8*d2 funnel-shift amounts)
 	uint32_t n2, d2, stage1_triples, exact3, sh1, sh2;
+	// balanced pair filter (FixedBEngine): test k in subtract form (w | 0x80..) + b_c0[k] / XOR form ^ b_x0[k]; the third byte
+	// of alternative k (stage 2, aligned with test k) is ((s2 & b_m2[k]) ^ b_v2[k]) == 0, s2 = the bytes b_sh2 / 8 further on
+	uint32_t b_engine, b_aligned, b_sh2;
+	uint32_t b_c0[8], b_c1[8], b_x0[8], b_x1[8], b_m2[8], b_v2[8];
 	uint32_t t2_m0[16], t2_v0[16], t2_m1[16], t2_v1[16], t2_m2[16], t2_v2[16];
 };
 
 // FIXED, hashed: exact membership of the 2 or 3 bytes at every position in a perfect-hash table held in
 // shared memory; hits are verified against the alternatives sharing the key
 struct HashParams {
-	uint32_t mul;        // slot = umulhi(key * mul, nslots): two IMADs, nothing on the ALU pipe
-	uint32_t nslots;
-	uint32_t key_mask;   // 0xffff or 0xffffff
-	uint32_t stride;     // bytes between slots in shared memory: 4, or 128 when the table is replicated per bank
-	const uint32_t *table;      // [nslots] key or 0xffffffff (copied to shared memory at kernel start)
+	uint32_t mulsh;      // h = window * mulsh (mulsh = mul << 8 * (4 - L): the bytes beyond the key fall off the top, no mask);
+	uint32_t nslots;     //   slot = umulhi(h, nslots): IMADs only, nothing on the ALU pipe
+	uint32_t stride;     // bytes between slots in shared memory: 128 when the table is replicated per bank, else 4
+	uint32_t neg1;       // == 0xffffffff, opaque to the compiler: h * neg1 + entry is an IMAD (FMA pipe) where a XOR would be ALU
+	const uint32_t *table;      // [nslots] h of the slot's key, or 0xffffffff (copied to shared memory at kernel start)
 	const uint32_t *slot_first; // [nslots] first index into slot_seqs
 	const uint32_t *slot_count; // [nslots]
 	const uint32_t *slot_seqs;  // alternatives of a key, preference order
@@ -93,11 +106,12 @@ struct HashParams {
 	const uint32_t *cls_bm;
 };
 constexpr int kHashMaxSlots = 8192;
-// copies of the table in shared memory (slot s, copy c at word s * copies + c; lane l reads copy l % copies): 32 copies
-// put every lane of a warp on its own bank (one wavefront per lookup instead of ~3.4 for random slots), 16 copies
-// two lanes per bank; the table then still fits in 32 KiB beside the 20-warp ring
+// copies of the table in shared memory (slot s, copy c at word s * copies + c; lane l reads copy l): 32 copies put every
+// lane of a warp on its own bank -- one wavefront per lookup instead of ~3.4 for random slots (and 2 with 16 copies: at
+// 16 lookups per 512-byte row that alone caps the kernel near 4 TB/s).  512 slots x 128 bytes = 64 KiB, beside a 20-warp ring
+// of 2 x 4 KiB slots
 constexpr uint32_t kHashReplicatedSlots = 512;
-static inline uint32_t hash_table_copies(uint32_t nslots) { return nslots <= 256 ? 32u : (nslots <= kHashReplicatedSlots ? 16u : 1u); }
+static inline uint32_t hash_table_copies(uint32_t nslots) { return nslots <= kHashReplicatedSlots ? 32u : 1u; }
 
 struct RunParams {
 	uint32_t one;         // == 1, opaque (see FixedParams)
@@ -118,6 +132,7 @@ struct ScanArgs {
 	unsigned long long *cursor; // [0]: candidates reserved so far
 	SegEntry *segs;
 	Cand *scratch;  // [gridDim.x * warps][slice bytes]: one private list per warp
+	uint32_t spt_shift;  // log2(slices per tile) = batch tile_shift - log2(Geom::kSlice)
 	uint32_t extra_smem; // bytes of engine-private shared memory behind the rings (hash table)
 	uint32_t tag;        // generation of this scan (1..65535), stored in the segment entries it writes
 };

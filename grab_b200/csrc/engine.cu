@@ -78,6 +78,7 @@ struct gscan_batch {
 	DevUnit *d_units = nullptr;
 	uint8_t *d_arena = nullptr;  // staged copies of host units (owned)
 	uint32_t n_tiles = 0;
+	uint32_t tile_shift = kMaxTileShift; // tiles of this batch are 2^tile_shift bytes (device_types.h)
 	uint64_t bytes = 0;
 	float h2d_ms = 0;
 	bool pooled = false;         // device buffers belong to the context (gscan_scan_batch's transient batches)
@@ -185,6 +186,29 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 			F.m0[k] = rep4(pr.tests[k].m0); F.v0[k] = rep4(pr.tests[k].v0);
 			F.m1[k] = rep4(pr.tests[k].m1); F.v1[k] = rep4(pr.tests[k].v1);
 		}
+		{ // balanced pair filter (FixedBEngine): exact byte pairs, 2..8 tests; stage 2 needs one third-byte test per pair test
+			F.b_engine = 0; F.b_aligned = 0; F.b_sh2 = 8u * (uint32_t)pr.delta2;
+			for (int k = 0; k < 8; k++) { F.b_c0[k] = 0; F.b_c1[k] = 0; F.b_x0[k] = 0; F.b_x1[k] = 0; F.b_m2[k] = 0; F.b_v2[k] = 0xffffffffu; }
+			const size_t nt = pr.tests.size();
+			bool aligned = !pr.triples.empty() && pr.triples.size() == nt;
+			for (size_t k = 0; k < nt && k < 8; k++) {
+				const FilterTest &t = pr.tests[k];
+				F.b_c0[k] = 0u - rep4(t.v0 & 0x7f); F.b_c1[k] = 0u - rep4(t.v1 & 0x7f);
+				F.b_x0[k] = rep4(t.v0 | 0x80); F.b_x1[k] = rep4(t.v1 | 0x80);
+				int hit = -1, hits = 0;
+				for (size_t j = 0; j < pr.triples.size(); j++) {
+					const Program::Triple &q = pr.triples[j];
+					if (q.m0 == t.m0 && q.v0 == t.v0 && q.m1 == t.m1 && q.v1 == t.v1) { hit = (int)j; hits++; }
+				}
+				if (hits != 1) aligned = false;
+				else { F.b_m2[k] = rep4(pr.triples[(size_t)hit].m2); F.b_v2[k] = rep4(pr.triples[(size_t)hit].v2); }
+			}
+			F.b_aligned = aligned ? 1u : 0u;
+			const char *off = getenv("GSCAN_NO_FIXEDB"); // A/B switch for measurements
+			if (F.exact && nt >= 2 && nt <= 8 && pr.delta >= 1 && pr.delta <= 4 && !pr.use_hash && !(off && *off == '1') &&
+			    (aligned || pr.pair_flag_prior * 512.0 <= 0.01))
+				F.b_engine = 1;
+		}
 		F.anchor = (uint32_t)pr.anchor;
 		F.nseq = (uint32_t)pr.seqs.size();
 		F.maxlen = (uint32_t)pr.maxlen;
@@ -210,10 +234,10 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 		for (auto &c : classes) for (int i = 0; i < 8; i++) p->cls_bm.push_back(c.w[i]);
 		if (pr.use_hash) {
 			HashParams &H = p->hash;
-			H.mul = pr.hash_mul;
+			H.mulsh = pr.hash_mul << (8 * (4 - pr.hash_len));
 			H.nslots = pr.hash_slots;
 			H.stride = hash_table_copies(pr.hash_slots) * 4u;
-			H.key_mask = pr.hash_len == 2 ? 0xffffu : 0xffffffu;
+			H.neg1 = 0xffffffffu;
 			H.uniform_len = F.uniform_len;
 			H.maxlen = F.maxlen;
 		}
@@ -433,6 +457,19 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 	// pass 1: validate, size the staging arena
 	uint64_t arena_bytes = 0, n_tiles64 = 0;
 	std::vector<uint64_t> arena_off(n_units, 0);
+	{ // tile size: the power of two next to the average unit length, 4 KiB .. 64 KiB (many small files: no empty slices)
+		uint64_t total = 0, live = 0;
+		for (size_t i = 0; i < n_units; i++) if (units[i].len) { total += units[i].len; live++; }
+		const uint64_t avg = live ? (total + live - 1) / live : 0;
+		uint32_t sh = kMinTileShift;
+		while (sh < (uint32_t)kMaxTileShift && (1ull << sh) < avg) sh++;
+		if (const char *e = getenv("GSCAN_TILE_SHIFT")) { // tests: every tile size against the oracle
+			const int v = atoi(e);
+			if (v >= kMinTileShift && v <= kMaxTileShift) sh = (uint32_t)v;
+		}
+		b->tile_shift = sh;
+	}
+	const uint64_t tile_bytes = 1ull << b->tile_shift;
 	for (size_t i = 0; i < n_units; i++) {
 		const gscan_unit &u = units[i];
 		if (u.len == 0) continue;
@@ -444,9 +481,9 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 			arena_off[i] = arena_bytes;
 			arena_bytes += (u.len + 255u) & ~255ull;
 		}
-		n_tiles64 += (u.len + kTileBytes - 1) / kTileBytes;
+		n_tiles64 += (u.len + tile_bytes - 1) >> b->tile_shift;
 	}
-	if (n_tiles64 >= (1ull << 27)) return fail(ctx, "gscan_batch_create: batch too large (more than 4 TiB of tiles)");
+	if ((n_tiles64 << (b->tile_shift - 9)) >= (1ull << 32)) return fail(ctx, "gscan_batch_create: batch too large (2 TiB of tiles or more)");
 	if (arena_bytes) {
 		if (pooled) { CK(ctx, ctx->pool_arena.ensure(arena_bytes + 256)); b->d_arena = ctx->pool_arena.p; }
 		else CK(ctx, cudaMalloc(&b->d_arena, arena_bytes + 256));
@@ -506,12 +543,12 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 		du.pad = 0;
 		const uint32_t unit_index = (uint32_t)dunits.size();
 		dunits.push_back(du);
-		for (uint64_t off = 0; off < u.len; off += kTileBytes) {
+		for (uint64_t off = 0; off < u.len; off += tile_bytes) {
 			TileDesc t;
 			t.src = du.ptr + off;
 			t.unit = unit_index;
 			t.off = (uint32_t)off;
-			t.len = (uint32_t)std::min<uint64_t>(kTileBytes, u.len - off);
+			t.len = (uint32_t)std::min<uint64_t>(tile_bytes, u.len - off);
 			t.ulen = (uint32_t)u.len;
 			t.pad[0] = t.pad[1] = 0;
 			tiles.push_back(t);
@@ -580,7 +617,10 @@ static int ensure_pattern(gscan_ctx *ctx, const gscan_pattern *pat)
 			const size_t nt = pr.hash_table.size() * 4, ns = pr.slot_seqs.size() * 4;
 			CK(ctx, ctx->hash_tables.ensure(3 * nt + ns + 64));
 			uint8_t *h = ctx->hash_tables.p;
-			CK(ctx, cudaMemcpyAsync(h, pr.hash_table.data(), nt, cudaMemcpyHostToDevice, ctx->stream));
+			std::vector<uint32_t> hashed(pr.hash_table.size()); // the device table holds the hash of the slot's key
+			for (size_t i = 0; i < hashed.size(); i++)
+				hashed[i] = pr.hash_table[i] == 0xffffffffu ? 0xffffffffu : pr.hash_table[i] * pat->hash.mulsh;
+			CK(ctx, cudaMemcpyAsync(h, hashed.data(), nt, cudaMemcpyHostToDevice, ctx->stream));
 			CK(ctx, cudaMemcpyAsync(h + nt, pr.slot_first.data(), nt, cudaMemcpyHostToDevice, ctx->stream));
 			CK(ctx, cudaMemcpyAsync(h + 2 * nt, pr.slot_count.data(), nt, cudaMemcpyHostToDevice, ctx->stream));
 			if (ns) CK(ctx, cudaMemcpyAsync(h + 3 * nt, pr.slot_seqs.data(), ns, cudaMemcpyHostToDevice, ctx->stream));
@@ -632,9 +672,11 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 
 	const bool hashed = pat->prog.kind == ENGINE_FIXED && pat->prog.use_hash;
 	const uint32_t table_bytes = hashed ? pat->prog.hash_slots * 4u * hash_table_copies(pat->prog.hash_slots) : 0u;
-	const ScanGeom geom = scan_geom(hashed ? 4 : (int)pat->prog.kind, pat->prog.kind == ENGINE_FIXED ? (uint32_t)pat->prog.tests.size() : 99u);
-	const uint32_t spt = (uint32_t)(kTileBytes / geom.slice);
-	const uint32_t n_segs = b->n_tiles * spt;
+	const bool fixedb = pat->prog.kind == ENGINE_FIXED && !hashed && pat->fixed.b_engine;
+	const ScanGeom geom = scan_geom(hashed ? 4 : (fixedb ? 5 : (int)pat->prog.kind), pat->prog.kind == ENGINE_FIXED ? (uint32_t)pat->prog.tests.size() : 99u);
+	uint32_t spt_shift = b->tile_shift;
+	for (int sl = geom.slice; sl > 1; sl >>= 1) spt_shift--; // log2(tile bytes / slice bytes)
+	const uint32_t n_segs = b->n_tiles << spt_shift;
 	const int grid = (int)std::min<uint32_t>((uint32_t)ctx->num_sms, b->n_tiles);
 	if (ensure_segs(ctx, n_segs) < 0) return -1;
 	CK(ctx, ctx->scratch.ensure((size_t)ctx->num_sms * geom.warps * geom.slice));
@@ -652,6 +694,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	A.segs = ctx->segs.p;
 	A.scratch = ctx->scratch.p;
 	A.extra_smem = table_bytes;
+	A.spt_shift = spt_shift;
 	A.tag = ctx->seg_tag;
 
 	unsigned long long *h_cursor = reinterpret_cast<unsigned long long *>(ctx->readback.p);
@@ -694,7 +737,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		R.tiles = b->d_tiles;
 		R.segs = ctx->segs.p;
 		R.n_segs = n_segs;
-		R.slices_per_tile = spt;
+		R.spt_shift = spt_shift;
 		R.tag = ctx->seg_tag;
 		R.cand = ctx->cand.p;
 		R.units = b->d_units;
@@ -773,6 +816,14 @@ extern "C" int gscan_scan_batch(gscan_ctx *ctx, const gscan_pattern *pat, const 
 	return rc;
 }
 
+extern "C" int gscan_last_device_matches(gscan_ctx *ctx, const gscan_match **dptr, size_t *n)
+{
+	if (!ctx || !dptr || !n) return fail(ctx, "gscan_last_device_matches: null argument");
+	*n = (size_t)ctx->stats.n_matches;
+	*dptr = *n ? reinterpret_cast<const gscan_match *>(ctx->out.p) : nullptr;
+	return 0;
+}
+
 extern "C" void gscan_free_matches(gscan_ctx *ctx, gscan_match *m)
 {
 	if (!ctx || !m) return;
@@ -846,14 +897,16 @@ extern "C" int gscan_tma_probe(gscan_ctx *ctx, gscan_batch *b, int geom, float *
 	CK(ctx, cudaSetDevice(ctx->device));
 	const ScanGeom g = geom == 0 ? ScanGeom{GeomStream::kWarps, GeomStream::kRing, GeomStream::kSlice}
 	                             : ScanGeom{GeomBalanced::kWarps, GeomBalanced::kRing, GeomBalanced::kSlice};
-	const uint32_t n_segs = b->n_tiles * (uint32_t)(kTileBytes / g.slice);
+	uint32_t spt_shift = b->tile_shift;
+	for (int sl = g.slice; sl > 1; sl >>= 1) spt_shift--;
+	const uint32_t n_segs = b->n_tiles << spt_shift;
 	if (ensure_segs(ctx, n_segs) < 0) return -1;
 	CK(ctx, ctx->scratch.ensure((size_t)ctx->num_sms * g.warps * g.slice));
 	CK(ctx, ctx->cursor.ensure(2));
 	if (ctx->cand.cap == 0) CK(ctx, ctx->cand.ensure(1u << 20));
 	ScanArgs A;
 	A.tiles = b->d_tiles; A.n_tiles = b->n_tiles; A.cand = ctx->cand.p; A.cand_cap = (uint32_t)ctx->cand.cap;
-	A.cursor = ctx->cursor.p; A.segs = ctx->segs.p; A.scratch = ctx->scratch.p; A.extra_smem = 0; A.tag = ctx->seg_tag;
+	A.cursor = ctx->cursor.p; A.segs = ctx->segs.p; A.scratch = ctx->scratch.p; A.extra_smem = 0; A.tag = ctx->seg_tag; A.spt_shift = spt_shift;
 	CK(ctx, launch_fill_u32(reinterpret_cast<uint32_t *>(ctx->cursor.p), 8, 0u, ctx->stream));
 	CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
 	CK(ctx, launch_scan_null(A, geom, (int)std::min<uint32_t>((uint32_t)ctx->num_sms, b->n_tiles), ctx->stream));

@@ -8,7 +8,7 @@
 
 namespace gscan {
 
-size_t scan_smem_bytes(const ScanGeom &g);
+size_t scan_smem_bytes(const ScanGeom &g, bool look_behind);
 ScanGeom scan_geom(int engine, uint32_t n_tests_or_ranges);
 cudaError_t launch_scan_fixed(const ScanArgs &A, const FixedParams &P, int delta, const ScanGeom &g, int grid, cudaStream_t st);
 cudaError_t launch_scan_hash(const ScanArgs &A, const HashParams &P, int grid, cudaStream_t st);
@@ -35,7 +35,7 @@ struct ResolveArgs {
 	const TileDesc *tiles;
 	const SegEntry *segs;
 	uint32_t n_segs;
-	uint32_t slices_per_tile;
+	uint32_t spt_shift;   // log2(slices per tile)
 	uint32_t tag;         // generation of the scan that filled segs
 	const Cand *cand;
 	const DevUnit *units;

@@ -836,9 +836,11 @@ bool build_hash(Program &out, int L)
 	distinct.erase(std::unique(distinct.begin(), distinct.end()), distinct.end());
 	uint64_t rng = 0x9E3779B97F4A7C15ull ^ (distinct.size() * 0xD1B54A32D192ED03ull);
 	const uint32_t kEmpty = 0xffffffffu; // never a key: keys are at most 3 bytes
-	// slot = umulhi(key * mul mod 2^32, slots): multiplicative hashing on the LOW product word (every key bit reaches
-	// its top bits; text keys differ mostly in their low bits) and a multiply-high range reduction, so the kernel
-	// computes the slot with two IMADs and no ALU-pipe instruction, and `slots` need not be a power of two.
+	// slot = umulhi(h, slots), h = key * (mul << 8 * (4 - L)) mod 2^32: multiplicative hashing on the LOW product word
+	// (every key bit reaches its top bits; text keys differ mostly in their low bits) and a multiply-high range
+	// reduction, so the kernel computes the slot with two IMADs and no ALU-pipe instruction, and `slots` need not be a
+	// power of two.  The multiplier carries the shift that pushes the bytes beyond the key out of the word: the kernel
+	// hashes the raw 32-bit window at every position without masking it, and the device table holds h, not the key.
 	std::vector<uint32_t> table;
 	auto search = [&](uint32_t ns, int attempts) -> bool {
 		for (int attempt = 0; attempt < attempts; attempt++) {
@@ -847,7 +849,7 @@ bool build_hash(Program &out, int L)
 			table.assign(ns, kEmpty);
 			bool ok = true;
 			for (uint32_t k : distinct) {
-				const uint32_t sl = umulhi32(k * mul, ns);
+				const uint32_t sl = umulhi32(k * (mul << (8 * (4 - L))), ns);
 				if (table[sl] != kEmpty) { ok = false; break; }
 				table[sl] = k;
 			}
@@ -876,7 +878,7 @@ bool build_hash(Program &out, int L)
 	const size_t n = distinct.size();
 	if (n + n / 8 <= 256 && search(256, 20000)) return true;
 	if (n + n / 8 <= 384 && search(384, 100000)) return true;
-	if (n + n / 8 <= 512 && search(512, 400000)) return true;
+	if (n + n / 8 <= 512 && search(512, 1000000)) return true;
 	for (uint32_t ns = 1024; ns <= 8192; ns <<= 1)
 		if (search(ns, 4000)) return true;
 	return false;

@@ -85,7 +85,7 @@ struct Program {
 	// share the key are verified
 	bool use_hash = false;
 	int hash_len = 0;                       // 2 or 3 key bytes
-	uint32_t hash_mul = 0, hash_slots = 0;  // slot = umulhi(key * mul mod 2^32, slots)
+	uint32_t hash_mul = 0, hash_slots = 0;  // slot = umulhi(key * (mul << 8 * (4 - hash_len)) mod 2^32, slots)
 	std::vector<uint32_t> hash_table;       // [slots] key, 0xffffffff = empty
 	std::vector<uint32_t> slot_first, slot_count, slot_seqs; // alternatives per slot, preference order
 

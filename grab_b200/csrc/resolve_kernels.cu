@@ -107,9 +107,9 @@ __global__ void k_gather(const ResolveArgs R)
 	for (int i = 0; i < kPerThread; i++) {
 		const uint32_t seg = base + i;
 		if (seg >= R.n_segs) break;
-		const uint32_t tile = seg / R.slices_per_tile;
+		const uint32_t tile = seg >> R.spt_shift;
 		const TileDesc td = R.tiles[tile];
-		if (td.off == 0 && seg % R.slices_per_tile == 0) R.unit_start[td.unit] = p; // first segment of a unit
+		if (td.off == 0 && (seg & ((1u << R.spt_shift) - 1u)) == 0) R.unit_start[td.unit] = p; // first segment of a unit
 		if (cnt[i]) {
 			const Cand *src = R.cand + R.segs[seg].base;
 			for (uint32_t k = 0; k < cnt[i]; k++) {

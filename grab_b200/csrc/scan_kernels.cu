@@ -68,6 +68,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 	    "r"(parity)
 	    : "memory");
 }
+// one LOP3 with the given truth table (a = 0xF0, b = 0xCC, c = 0xAA)
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
+{
+	uint32_t d;
+	asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+	return d;
+}
 // L2 eviction policy for the corpus stream: every byte is read exactly once, so its lines are the first to go.
 // Without it the stream (126 MB of L2 turn over every ~18 us) evicts the rarely executed slow-path code and the
 // pattern tables from L2, and a warp that finally hits a match fetches its instructions from DRAM one line at a
@@ -111,9 +119,10 @@ struct __align__(16) SlotCtl {
 	uint32_t off, ulen, tile_len, begin, niter, pad;
 };
 
-size_t scan_smem_bytes(const ScanGeom &g)
+// a slot: [16 bytes before the slice, engines with a look-behind only] slice [16 bytes after it]
+size_t scan_smem_bytes(const ScanGeom &g, bool look_behind)
 {
-	return (size_t)g.warps * g.ring * ((size_t)g.slice + 2 * kHalo + sizeof(SlotCtl)) + 64;
+	return (size_t)g.warps * g.ring * ((size_t)g.slice + (look_behind ? 2 : 1) * kHalo + sizeof(SlotCtl)) + 64;
 }
 
 // what a warp knows about the slice it is scanning
@@ -402,6 +411,96 @@ struct Fixed3Engine {
 };
 
 // ------------------------------------------------------------------------------------------
+// FIXED engine, balanced pair filter (exact byte pairs, 2..8 alternatives: `foo|bar|baz|quux`, BASELINE
+// configs[2]).  The pair and triple filters above are ALU-pipe bound (LOP3/SHF issue at half rate): the triple
+// filter spends 17 ALU-pipe instructions per word on three alternatives.  Here
+//   * equality is a subtraction on the FMA pipe.  w80 = w | 0x80808080 (bit 7 forced), a = w80 - V0, b = s80 - V1
+//     with V = the pattern byte & 0x7f replicated: no byte borrows (0x80+x - v >= 1) and a byte of a is 0x80 iff
+//     the text byte equals the pattern byte (mod bit 7: a superset, the verification is exact).  One LOP3 then
+//     forms t = (a | b) ^ 0x80808080 -- zero byte iff both match -- and the usual zero-byte test (IMAD + LOP3)
+//     ORs it into the row's flag word: 2 ALU-pipe + 3 FMA-pipe instructions per test and word instead of 3 + 1
+//     (GS_FB_A of the K tests can be switched back to the XOR form to balance the two pipes);
+//   * the cheap pair test flags one row in six on random text, so the third byte is NOT tested up front but in an
+//     inline stage 2 on the flagged rows only, reusing the kept t words (t | third-byte mismatch), and only rows
+//     that survive both stages visit the out-of-line verification.
+// ------------------------------------------------------------------------------------------
+#ifndef GS_FB_A
+#define GS_FB_A 0
+#endif
+template <int D, int K, bool ALIGNED>
+struct FixedBEngine {
+	typedef FixedParams Params;
+	static constexpr bool kLookBehind = false, kLookAhead = true;
+	static constexpr int kA = GS_FB_A < K ? GS_FB_A : K; // tests [0, kA) in XOR form, [kA, K) in subtract form
+	static __device__ __forceinline__ void prologue(const FixedParams &, uint8_t *) {}
+
+	// t words of one text word: zero byte <=> pair test k passes at that byte (bit 7 of the text ignored).  Bit 7 of every
+	// byte of t is clear by construction (XOR form: both operands have it set; subtract form: a | b is never 0x00, so
+	// masking bit 7 leaves a zero byte exactly where a == b == 0x80), which halves the zero-byte test: t - 0x01 sets
+	// bit 7 where t is zero (or above a zero byte: a superset), no "& ~t" needed.
+	static __device__ __forceinline__ void word_t(const FixedParams &P, uint32_t w80, uint32_t s80, uint32_t (&t)[K])
+	{
+#pragma unroll
+		for (int k = 0; k < K; k++) {
+			if (k < kA) {
+				t[k] = (w80 ^ P.b_x0[k]) | (s80 ^ P.b_x1[k]);
+			} else {
+				const uint32_t a = w80 * P.one + P.b_c0[k], b = s80 * P.one + P.b_c1[k];
+				t[k] = (a | b) & kLow7;
+			}
+		}
+	}
+	static __device__ __forceinline__ uint32_t dec(const FixedParams &P, uint32_t t) { return t * P.one + 0xfefefeffu; }
+	// general zero-byte test (stage 2: the third-byte term can have bit 7 set)
+	static __device__ __forceinline__ uint32_t zero_flags(const FixedParams &P, uint32_t t, uint32_t f)
+	{
+		return ((t * P.one + 0xfefefeffu) & ~t) | f;
+	}
+
+	template <class G>
+	static __device__ __forceinline__ void run(const FixedParams &P, const Slice &S, Emitter &E, uint32_t lane)
+	{
+		const uint32_t base = S.begin + lane * 16;
+#pragma unroll 2
+		for (uint32_t it = 0; it < S.niter; it++) {
+			const uint32_t c0 = base + it * 512;
+			uint32_t w[5], w80[5], t[4][K];
+			const uint4 a = *reinterpret_cast<const uint4 *>(S.tile + c0);
+			w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+			w[4] = *reinterpret_cast<const uint32_t *>(S.tile + c0 + 16);
+#pragma unroll
+			for (int j = 0; j < 5; j++) w80[j] = w[j] | kHigh;
+			uint32_t f = 0;
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const uint32_t s80 = D == 4 ? w80[j + 1] : __funnelshift_r(w80[j], w80[j + 1], 8 * D);
+				word_t(P, w80[j], s80, t[j]);
+#pragma unroll
+				for (int k = 0; k < K; k++) f |= dec(P, t[j][k]);
+			}
+			if (!__any_sync(0xffffffffu, (f & kHigh) != 0)) continue;
+			// ---- stage 2 (flagged rows): per-word flags, narrowed by the third byte of every alternative ----
+			uint32_t g[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				g[j] = 0;
+				if (ALIGNED) {
+					const uint32_t s2 = __funnelshift_r(w[j], w[j + 1], P.b_sh2);
+#pragma unroll
+					for (int k = 0; k < K; k++) g[j] = zero_flags(P, t[j][k] | ((s2 & P.b_m2[k]) ^ P.b_v2[k]), g[j]);
+				} else {
+#pragma unroll
+					for (int k = 0; k < K; k++) g[j] |= dec(P, t[j][k]);
+				}
+			}
+			if (!__any_sync(0xffffffffu, ((g[0] | g[1] | g[2] | g[3]) & kHigh) != 0)) continue;
+			E.n += fixed_slow_row(P, S.tile, S.gtile, (int)S.begin, (int)(S.begin + S.niter * 512 + kHalo), S.off, S.ulen, S.tile_len,
+			                      E.scratch + E.n, lane, c0, g[0], g[1], g[2], g[3]);
+		}
+	}
+};
+
+// ------------------------------------------------------------------------------------------
 // HASH engine: FIXED with many alternatives (literal sets).  The first L = 2 or 3 bytes at every position
 // are looked up in a perfect-hash table in shared memory -- exact membership, one multiply (FMA pipe),
 // one LDS and four ALU ops per position, independent of how many alternatives there are.  Only true
@@ -412,6 +511,9 @@ struct Fixed3Engine {
 // copy the 32 random slots of a warp cost ~3.4 wavefronts and the shared-memory data pipe is the bottleneck (95 %
 // busy, profiles/r01_scan_v5_lits8_single_table_ncu.txt).
 // ------------------------------------------------------------------------------------------
+#ifndef GS_HASH_SUB
+#define GS_HASH_SUB 2
+#endif
 struct HashEngine {
 	typedef HashParams Params;
 	static constexpr bool kLookBehind = false, kLookAhead = true;
@@ -449,27 +551,28 @@ struct HashEngine {
 		return 0;
 	}
 
-	static __device__ __forceinline__ uint32_t key_at(const HashParams &P, uint32_t lo, uint32_t hi, int k)
-	{
-		return (k ? __funnelshift_r(lo, hi, 8 * k) : lo) & P.key_mask;
-	}
-	static __device__ __forceinline__ uint32_t slot_of(const HashParams &P, uint32_t y) { return __umulhi(y * P.mul, P.nslots); }
+	// the 32-bit window at byte k of the word pair; the bytes beyond the key fall off the top of window * mulsh
+	static __device__ __forceinline__ uint32_t window(uint32_t lo, uint32_t hi, int k) { return k ? __funnelshift_r(lo, hi, 8 * k) : lo; }
+	static __device__ __forceinline__ uint32_t slot_of(const HashParams &P, uint32_t h) { return __umulhi(h, P.nslots); }
 	// tbl: the table in shared memory, for a replicated table already advanced to this lane's bank (+ lane * 4).
-	// Slot and address are three IMADs (FMA pipe); zero <=> the position holds a key of the set.
+	// Hash, slot and address are three IMADs (FMA pipe); zero <=> the position holds a key of the set.  SUB: the
+	// comparison as entry - h on the FMA pipe instead of entry ^ h on the ALU pipe (GS_HASH_SUB of every 4 positions).
+	template <bool SUB>
 	static __device__ __forceinline__ uint32_t probe(const HashParams &P, const uint8_t *tbl, uint32_t y)
 	{
-		return *reinterpret_cast<const uint32_t *>(tbl + slot_of(P, y) * P.stride) ^ y;
+		const uint32_t h = y * P.mulsh;
+		const uint32_t e = *reinterpret_cast<const uint32_t *>(tbl + slot_of(P, h) * P.stride);
+		return SUB ? h * P.neg1 + e : e ^ h;
 	}
 
-	// min over the 16 positions of (table[slot(key)] ^ key), two positions per 3-input minimum
+	// min over the 16 positions of (table[slot(h)] ^ h), two positions per 3-input minimum
 	static __device__ __forceinline__ uint32_t row_min(const HashParams &P, const uint8_t *tbl, const uint32_t (&w)[5])
 	{
 		uint32_t mn = 0xffffffffu;
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
-#pragma unroll
-			for (int k = 0; k < 4; k += 2)
-				mn = __vimin3_u32(mn, probe(P, tbl, key_at(P, w[j], w[j + 1], k)), probe(P, tbl, key_at(P, w[j], w[j + 1], k + 1)));
+			mn = __vimin3_u32(mn, probe<(GS_HASH_SUB > 0)>(P, tbl, window(w[j], w[j + 1], 0)), probe<(GS_HASH_SUB > 1)>(P, tbl, window(w[j], w[j + 1], 1)));
+			mn = __vimin3_u32(mn, probe<(GS_HASH_SUB > 2)>(P, tbl, window(w[j], w[j + 1], 2)), probe<(GS_HASH_SUB > 3)>(P, tbl, window(w[j], w[j + 1], 3)));
 		}
 		return mn;
 	}
@@ -483,18 +586,18 @@ struct HashEngine {
 		uint32_t hits = 0; // positions whose leading bytes are a key of the set (unrolled: straight-line, no divergence yet)
 #pragma unroll
 		for (int b = 0; b < 16; b++)
-			hits |= (probe(P, tbl, key_at(P, w[b >> 2], w[(b >> 2) + 1], b & 3)) == 0u ? 1u : 0u) << b;
-		// the key at position b for a run-time b (rolled loops below: the slow path stays small)
-		auto key_rt = [&](int b) -> uint32_t { return __funnelshift_r(w[b >> 2], w[(b >> 2) + 1], 8 * (b & 3)) & P.key_mask; };
+			hits |= (probe<false>(P, tbl, window(w[b >> 2], w[(b >> 2) + 1], b & 3)) == 0u ? 1u : 0u) << b;
+		// the slot at position b for a run-time b (rolled loops below: the slow path stays small)
+		auto slot_rt = [&](int b) -> uint32_t { return slot_of(P, __funnelshift_r(w[b >> 2], w[(b >> 2) + 1], 8 * (b & 3)) * P.mulsh); };
 		while (hits) { // verify() is out of line: one copy, the kernel stays instruction-cache resident
 			const int b = __ffs(hits) - 1;
 			hits &= hits - 1;
 			const int p = (int)c0 + b;
-			if (p < (int)tile_len && verify(P, gtile, off, ulen, p, slot_of(P, key_rt(b)))) mm |= 1u << b;
+			if (p < (int)tile_len && verify(P, gtile, off, ulen, p, slot_rt(b))) mm |= 1u << b;
 		}
 		return Emitter::emit_at(dst, mm, off + c0, [&](uint32_t b) -> uint32_t {
 			if (P.uniform_len) return P.uniform_len;
-			return verify(P, gtile, off, ulen, (int)(c0 + b), slot_of(P, key_rt((int)b)));
+			return verify(P, gtile, off, ulen, (int)(c0 + b), slot_rt((int)b));
 		}, lane);
 	}
 
@@ -547,9 +650,44 @@ struct RunEngine {
 		if (NHI) return ((lo & ~x) | (hi & x)) & kHigh;
 		return lo & ~x & kHigh;
 	}
+	// The same for words whose bytes are all below 0x80 (plain ASCII text, checked per slice by the caller) and a class
+	// without high ranges: membership is the PARITY of the thresholds lo, hi + 1 at or below the byte, each one bit 7 of
+	// x + (0x80 - threshold) (an IMAD, no carry leaves a byte since x <= 0x7f), so all ranges reduce with 3-input XORs:
+	// 5 ALU-pipe instructions per word instead of 8 ([A-Za-z0-9_]: one OR for the case fold, three XOR3, the nibble insert).
+	static __device__ __forceinline__ uint32_t class_flags_ascii(const RunParams &P, uint32_t x)
+	{
+		constexpr int kTerms = 2 * NLO + 2 * NFO; // >= 2
+		uint32_t t[kTerms];
+#pragma unroll
+		for (int r = 0; r < NLO; r++) { t[2 * r] = x * P.one + P.add_ge_lo[r]; t[2 * r + 1] = x * P.one + P.add_gt_lo[r]; }
+		if (NFO) {
+			const uint32_t y = x | 0x20202020u;
+			t[2 * NLO] = y * P.one + P.add_ge_fold;
+			t[2 * NLO + 1] = y * P.one + P.add_gt_fold;
+		}
+		// XOR3 chain, the last step fused with the bit-7 mask: (kTerms + 1) / 2 LOP3 in all (inline PTX: the compiler
+		// would otherwise pair the terms first and spend one more)
+		uint32_t acc = t[0];
+		int i = 1;
+#pragma unroll
+		for (; i + 2 < kTerms; i += 2) acc = lop3<0x96>(acc, t[i], t[i + 1]);
+		if (i + 1 < kTerms) { acc = lop3<0x96>(acc, t[i], t[i + 1]); return acc & kHigh; }
+		return lop3<0x28>(acc, t[i], kHigh); // (acc ^ t) & 0x80808080
+	}
 	static __device__ __forceinline__ bool in_class(const RunParams &P, uint32_t b)
 	{
 		return (P.bitmap[b >> 5] >> (b & 31)) & 1u;
+	}
+	// class mask of 16 ASCII bytes inside the unit; `seen` collects the words so the caller can tell whether the slice was ASCII
+	static __device__ __forceinline__ uint32_t mask16_ascii(const RunParams &P, const uint8_t *p, uint32_t &seen)
+	{
+		const uint4 a = *reinterpret_cast<const uint4 *>(p);
+		seen |= a.x | a.y;
+		seen |= a.z | a.w;
+		uint32_t r = pack_top_nibble(class_flags_ascii(P, a.w)) >> 28;
+		r = __funnelshift_l(pack_top_nibble(class_flags_ascii(P, a.z)), r, 4);
+		r = __funnelshift_l(pack_top_nibble(class_flags_ascii(P, a.y)), r, 4);
+		return __funnelshift_l(pack_top_nibble(class_flags_ascii(P, a.x)), r, 4);
 	}
 	// 16-bit class mask of the 16 bytes at tile position c, bytes at or past the unit end read as 0
 	static __device__ __forceinline__ uint32_t mask16(const RunParams &P, const Slice &S, uint32_t c)
@@ -627,9 +765,26 @@ struct RunEngine {
 		if (S.niter == (uint32_t)kRows && (unsigned long long)S.off + send + 16 <= S.ulen) {
 			// ---- full slice strictly inside the unit: no validity masks, everything in registers ----
 			uint32_t cm[kRows + 1];
+			if (NHI == 0) {
+				// speculate that the slice is plain ASCII (cheaper classification); if a byte >= 0x80 shows up the masks are
+				// wrong (carries between bytes) and the slice goes through the general out-of-line path instead
+				uint32_t seen = 0;
 #pragma unroll
-			for (int r = 0; r < kRows; r++) cm[r] = mask16_inner(P, S.tile + S.begin + r * 512 + lane * 16);
-			{ // the 16 bytes after the slice: lanes 0..3 classify one word each of the look-ahead copy
+				for (int r = 0; r < kRows; r++) cm[r] = mask16_ascii(P, S.tile + S.begin + r * 512 + lane * 16, seen);
+				const uint32_t x = *reinterpret_cast<const uint32_t *>(S.tile + send + (lane & 3) * 4);
+				seen |= x;
+				uint32_t nib = (pack_top_nibble(class_flags_ascii(P, x)) >> 28) << ((lane & 3) * 4);
+				nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
+				nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
+				cm[kRows] = nib; // correct in lanes 0..3; only lane 0's copy is consumed (by lane 31)
+				if (__any_sync(0xffffffffu, (seen & kHigh) != 0)) {
+					E.n += run_tail(P, S.tile, S.gtile, S.off, S.ulen, S.begin, S.niter, prevbit, E.scratch + E.n, lane);
+					return;
+				}
+			} else {
+#pragma unroll
+				for (int r = 0; r < kRows; r++) cm[r] = mask16_inner(P, S.tile + S.begin + r * 512 + lane * 16);
+				// the 16 bytes after the slice: lanes 0..3 classify one word each of the look-ahead copy
 				const uint32_t x = *reinterpret_cast<const uint32_t *>(S.tile + send + (lane & 3) * 4);
 				uint32_t nib = (pack_top_nibble(class_flags(P, x)) >> 28) << ((lane & 3) * 4);
 				nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
@@ -715,18 +870,18 @@ struct NullEngine {
 // ------------------------------------------------------------------------------------------
 // the persistent kernel: warp-private TMA rings
 // ------------------------------------------------------------------------------------------
-// Slice s = 16 * tile + j is the j-th of the (up to) 16 contiguous 512-byte-row-aligned parts of a
-// tile.  Warp g (of all warps of the grid) scans slices g, g + G, g + 2G, ...  Each warp keeps kRing
+// Slice s = (tile << spt_shift) + j is the j-th kSlice-byte part of a tile.  Warp g (of all warps of the grid) scans slices g, g + G, g + 2G, ...  Each warp keeps kRing
 // slices in flight: after finishing a slice its lane 0 re-arms the slot's mbarrier and issues the
 // bulk copy for the slice kRing steps ahead.  No producer warp, no "empty" barriers, no __syncthreads.
 template <class G>
 __device__ __forceinline__ void slice_geometry(const TileDesc &d, uint32_t j, uint32_t &begin, uint32_t &niter)
 {
-	const uint32_t sub = ((d.len + G::kSlicesPerTile - 1) / G::kSlicesPerTile + 511u) & ~511u;
-	begin = j * sub;
+	// slice j of a tile is its bytes [j * kSlice, (j + 1) * kSlice): full slices wherever the unit has the bytes
+	// (a 16 KiB file in a 16 KiB tile is 4 slices of 8 rows), an empty one (niter 0) past the end of a short tile
+	begin = j * (uint32_t)G::kSlice;
 	niter = 0;
 	if (begin < d.len) {
-		const uint32_t end = begin + sub < d.len ? begin + sub : d.len;
+		const uint32_t end = begin + (uint32_t)G::kSlice < d.len ? begin + (uint32_t)G::kSlice : d.len;
 		niter = (end - begin + 511u) >> 9;
 	}
 }
@@ -737,13 +892,14 @@ scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename
 {
 	extern __shared__ __align__(128) uint8_t smem[];
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	constexpr uint32_t slot_bytes = G::kSlice + 2 * kHalo;
+	constexpr uint32_t kPre = Eng::kLookBehind ? kHalo : 0u;
+	constexpr uint32_t slot_bytes = G::kSlice + kPre + kHalo;
 	uint8_t *my = smem + (size_t)warp * G::kRing * slot_bytes;
 	SlotCtl *ctl = reinterpret_cast<SlotCtl *>(smem + (size_t)G::kWarps * G::kRing * slot_bytes) + warp * G::kRing;
 	uint8_t *extra = smem + (size_t)G::kWarps * G::kRing * (slot_bytes + sizeof(SlotCtl)) + 64;
 	Eng::prologue(P, extra);
 
-	const uint32_t total = A.n_tiles * G::kSlicesPerTile;
+	const uint32_t total = A.n_tiles << A.spt_shift, spt_mask = (1u << A.spt_shift) - 1u;
 	const uint32_t stride = gridDim.x * G::kWarps;
 	const uint32_t first = blockIdx.x * G::kWarps + warp;
 
@@ -757,7 +913,7 @@ scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename
 	// lane 0: describe slice `s` in slot `slot` and start its copy
 	auto issue = [&](uint32_t slot, uint32_t s, const TileDesc &d) {
 		uint32_t begin, niter;
-		slice_geometry<G>(d, s % G::kSlicesPerTile, begin, niter);
+		slice_geometry<G>(d, s & spt_mask, begin, niter);
 		SlotCtl *c = &ctl[slot];
 		c->src = d.src; c->off = d.off; c->ulen = d.ulen; c->tile_len = d.len; c->begin = begin; c->niter = niter;
 		if (niter == 0) { mbar_arrive(&c->full); return; }
@@ -765,7 +921,7 @@ scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename
 		const uint32_t bytes = rest > niter * 512u ? niter * 512u : rest;
 		const bool behind = Eng::kLookBehind && (d.off + begin) != 0;
 		const bool ahead = Eng::kLookAhead && rest >= niter * 512u + kHalo;
-		uint8_t *dst = my + (size_t)slot * slot_bytes + kHalo;
+		uint8_t *dst = my + (size_t)slot * slot_bytes + kPre;
 		mbar_arrive_expect_tx(&c->full, bytes + (behind ? kHalo : 0u) + (ahead ? kHalo : 0u));
 		tma_load_1d(dst, reinterpret_cast<const void *>(d.src + begin), bytes, &c->full, policy);
 		if (behind) tma_load_1d(dst - kHalo, reinterpret_cast<const void *>(d.src + begin - kHalo), kHalo, &c->full, policy);
@@ -775,7 +931,7 @@ scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename
 	if (lane == 0) {
 		for (uint32_t k = 0; k < (uint32_t)G::kRing; k++) {
 			const uint32_t s = first + k * stride;
-			if (s < total) issue(k, s, A.tiles[s / G::kSlicesPerTile]);
+			if (s < total) issue(k, s, A.tiles[s >> A.spt_shift]);
 		}
 	}
 	__syncwarp();
@@ -788,7 +944,7 @@ scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename
 		// descriptor of the slice that will reuse this slot: fetched now, needed after the scan
 		const uint32_t nxt = s + G::kRing * stride;
 		TileDesc dn;
-		if (lane == 0 && nxt < total) dn = A.tiles[nxt / G::kSlicesPerTile];
+		if (lane == 0 && nxt < total) dn = A.tiles[nxt >> A.spt_shift];
 
 		mbar_wait(&ctl[slot].full, phase);
 		Slice S;
@@ -797,7 +953,7 @@ scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename
 		S.tile_len = ctl[slot].tile_len;
 		S.begin = ctl[slot].begin;
 		S.niter = ctl[slot].niter;
-		S.tile = my + (size_t)slot * slot_bytes + kHalo - S.begin; // address of tile byte 0 (only the slice window is resident)
+		S.tile = my + (size_t)slot * slot_bytes + kPre - S.begin; // address of tile byte 0 (only the slice window is resident)
 		S.gtile = reinterpret_cast<const uint8_t *>(ctl[slot].src);
 		S.extra = extra;
 		Eng::template run<G>(P, S, E, lane);
@@ -815,7 +971,7 @@ template <class Eng, class G>
 static cudaError_t launch_g(const ScanArgs &A, const typename Eng::Params &P, int grid, cudaStream_t st)
 {
 	const ScanGeom g{G::kWarps, G::kRing, G::kSlice};
-	const size_t smem = scan_smem_bytes(g) + A.extra_smem;
+	const size_t smem = scan_smem_bytes(g, Eng::kLookBehind) + A.extra_smem;
 	cudaError_t e = cudaFuncSetAttribute(scan_kernel<Eng, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	scan_kernel<Eng, G><<<grid, G::kThreads, smem, st>>>(A, P);
@@ -834,6 +990,7 @@ static cudaError_t launch(const ScanArgs &A, const typename Eng::Params &P, cons
 ScanGeom scan_geom(int engine, uint32_t n_tests_or_ranges)
 {
 	if (engine == 4 /*FIXED, hashed*/) return ScanGeom{GeomHash::kWarps, GeomHash::kRing, GeomHash::kSlice};
+	if (engine == 5 /*FIXED, balanced pair filter*/) return ScanGeom{GeomPair::kWarps, GeomPair::kRing, GeomPair::kSlice};
 	if (engine == 1 /*FIXED*/ || (engine == 2 && GS_RUN_STREAM)) return ScanGeom{GeomStream::kWarps, GeomStream::kRing, GeomStream::kSlice};
 	return ScanGeom{GeomBalanced::kWarps, GeomBalanced::kRing, GeomBalanced::kSlice};
 }
@@ -876,8 +1033,33 @@ static cudaError_t launch_fixed_de(const ScanArgs &A, const FixedParams &P, cons
 	}
 }
 
+template <int D, bool AL>
+static cudaError_t launch_fixedb_k(const ScanArgs &A, const FixedParams &P, int grid, cudaStream_t st)
+{
+	switch (P.ntests) {
+	case 2: return launch_g<FixedBEngine<D, 2, AL>, GeomPair>(A, P, grid, st);
+	case 3: return launch_g<FixedBEngine<D, 3, AL>, GeomPair>(A, P, grid, st);
+	case 4: return launch_g<FixedBEngine<D, 4, AL>, GeomPair>(A, P, grid, st);
+	case 5: case 6: return launch_g<FixedBEngine<D, 6, AL>, GeomPair>(A, P, grid, st);
+	default: return launch_g<FixedBEngine<D, 8, AL>, GeomPair>(A, P, grid, st);
+	}
+}
+template <int D>
+static cudaError_t launch_fixedb(const ScanArgs &A, const FixedParams &P, int grid, cudaStream_t st)
+{
+	return P.b_aligned ? launch_fixedb_k<D, true>(A, P, grid, st) : launch_fixedb_k<D, false>(A, P, grid, st);
+}
+
 cudaError_t launch_scan_fixed(const ScanArgs &A, const FixedParams &P, int delta, const ScanGeom &g, int grid, cudaStream_t st)
 {
+	if (P.b_engine) {
+		switch (delta) {
+		case 1: return launch_fixedb<1>(A, P, grid, st);
+		case 2: return launch_fixedb<2>(A, P, grid, st);
+		case 3: return launch_fixedb<3>(A, P, grid, st);
+		default: return launch_fixedb<4>(A, P, grid, st);
+		}
+	}
 	if (P.stage1_triples) return P.exact3 ? launch_fixed3<true>(A, P, g, grid, st) : launch_fixed3<false>(A, P, g, grid, st);
 	const bool ex = P.exact != 0;
 	switch (delta) {

@@ -83,12 +83,96 @@ def gather_counts_start(n_local, group=None):
     return PendingCounts(out, work, int(n_local))
 
 
+def merge_parts(parts):
+    """Records of several ranks -> one array ordered by (file_id, start).  Every part is already ordered (the engine
+    returns records by unit, then offset); when the ranks own increasing, disjoint file-id ranges (block sharding) the
+    concatenation is the answer, otherwise (stride sharding) a lexsort by (file_id, start)."""
+    parts = [p for p in parts if len(p)]
+    if not parts:
+        return np.zeros(0, dtype=MATCH_DTYPE)
+    allm = parts[0] if len(parts) == 1 else np.concatenate(parts)
+    if all(int(parts[i]["file_id"][-1]) < int(parts[i + 1]["file_id"][0]) for i in range(len(parts) - 1)):
+        return allm
+    return allm[np.lexsort((allm["start"], allm["file_id"]))]
+
+
+class _DevRecords:
+    """__cuda_array_interface__ over the engine's device records, so torch can wrap them without a copy."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, True), "version": 2}
+
+
+class PendingMatches:
+    """A gather of match records in flight (gather_matches_start): finish() returns the merged records on `dst` (a view of a
+    pinned buffer that stays valid until the next finish()), None elsewhere."""
+
+    _pinned = None  # grow-only pinned landing buffer on the destination rank
+
+    def __init__(self, result=None, event=None, counts=None, host=None, is_dst=False, keep=None):
+        self._result, self._event, self._counts, self._host, self._is_dst, self._keep = result, event, counts, host, is_dst, keep
+
+    def finish(self):
+        if self._event is None:
+            return self._result
+        self._event.synchronize()
+        self._keep = None
+        if not self._is_dst:
+            return None
+        offs = np.concatenate([[0], np.cumsum(self._counts)])
+        rec = self._host.numpy()[: int(offs[-1]) * MATCH_DTYPE.itemsize].view(MATCH_DTYPE)
+        return merge_parts([rec[int(offs[r]):int(offs[r + 1])] for r in range(len(self._counts))])
+
+
+def gather_matches_start(local, dst=0, group=None, device_records=None):
+    """Asynchronous gather_matches(): counts first (small blocking all-gather: they size the exchange), then ONE padded
+    all-gather of the raw records on a side stream, followed on the destination rank by device-to-host copies of every
+    rank's live part straight into a contiguous pinned buffer -- all enqueued, nothing waited for: the caller scans the
+    next batch meanwhile and collects with finish().  device_records = (device pointer, count) of the records in HBM
+    (Context.last_device_matches()) avoids bouncing this rank's records through the host."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1 or dist.get_backend(group) != "nccl":
+        return PendingMatches(result=gather_matches(local, dst, group))
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_local = len(local) if device_records is None else int(device_records[1])
+    counts = gather_counts(n_local, group)
+    cap = max(int(counts.max()), 1) * MATCH_DTYPE.itemsize
+    dev = _device(group)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        buf = torch.empty(cap, dtype=torch.uint8, device=dev)
+        nb = n_local * MATCH_DTYPE.itemsize
+        if nb:
+            if device_records is not None:
+                buf[:nb].copy_(torch.as_tensor(_DevRecords(int(device_records[0]), nb), device=dev))
+            else:
+                local = np.ascontiguousarray(local, dtype=MATCH_DTYPE)
+                buf[:nb].copy_(torch.from_numpy(local.view(np.uint8).reshape(-1)), non_blocking=False)
+        out = torch.empty(world * cap, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, buf, group=group)  # enqueued on `side` (NCCL orders it after the copies above)
+        host = None
+        if rank == dst:
+            total = int(counts.sum()) * MATCH_DTYPE.itemsize
+            if PendingMatches._pinned is None or PendingMatches._pinned.numel() < total:
+                PendingMatches._pinned = torch.empty(max(total * 5 // 4, 1 << 20), dtype=torch.uint8, pin_memory=True)
+            host = PendingMatches._pinned
+            o = 0
+            for r in range(world):
+                nbr = int(counts[r]) * MATCH_DTYPE.itemsize
+                if nbr:
+                    host[o:o + nbr].copy_(out[r * cap:r * cap + nbr], non_blocking=True)
+                o += nbr
+        ev = torch.cuda.Event()
+        ev.record(side)
+    return PendingMatches(event=ev, counts=counts, host=host, is_dst=rank == dst, keep=(buf, out, side))
+
+
 def gather_matches(local, dst=0, group=None):
     """Gathers MATCH_DTYPE records of all ranks on `dst`, merged by (file_id, start); others get None.
     Counts first (all-gather), then one padded all-gather of the raw record bytes."""
     local = np.ascontiguousarray(local, dtype=MATCH_DTYPE)
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return np.sort(local, order=["file_id", "start"], kind="stable")
+        return merge_parts([local])
     counts = gather_counts(len(local), group)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     cap = int(counts.max())
@@ -102,6 +186,4 @@ def gather_matches(local, dst=0, group=None):
     if rank != dst:
         return None
     raw = out.cpu().numpy().reshape(world, -1)
-    parts = [raw[r, : int(counts[r]) * MATCH_DTYPE.itemsize].view(MATCH_DTYPE) for r in range(world)]
-    allm = np.concatenate(parts) if parts else np.zeros(0, dtype=MATCH_DTYPE)
-    return np.sort(allm, order=["file_id", "start"], kind="stable")
+    return merge_parts([raw[r, : int(counts[r]) * MATCH_DTYPE.itemsize].view(MATCH_DTYPE) for r in range(world)])

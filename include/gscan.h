@@ -129,6 +129,10 @@ int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_batch *batc
 void gscan_batch_free(gscan_ctx *ctx, gscan_batch *batch);
 
 int gscan_last_stats(const gscan_ctx *ctx, gscan_stats *out);
+/* The records of the last successful scan as they sit in device memory (same bytes, same order as *out of that call):
+ * for a device-side exchange -- BASELINE config 5's gather of (file id, offset) records to one rank over NCCL reads
+ * them from here instead of bouncing through the host.  Valid until the next scan on this context. */
+int gscan_last_device_matches(gscan_ctx *ctx, const gscan_match **dptr, size_t *n);
 
 /* ---- utilities (bench / tests; not part of the reference surface) ---------------------- */
 

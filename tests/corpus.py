@@ -67,6 +67,23 @@ def synth_file(seed, file_id, length, needle=None, needle_every=0):
     return out
 
 
+def synth_range(seed, file_id, off, length):
+    """Bytes [off, off + length) of synthetic file `file_id` without needles (off a multiple of 8): the generator is
+    counter based per 8-byte block, so a big file can be regenerated piecewise (bench.py, the 256 MiB config)."""
+    assert off % 8 == 0
+    nblk = (length + 7) // 8
+    j = np.arange(off // 8, off // 8 + nblk, dtype=np.uint64)
+    base = np.uint64(((seed * K_SEED) + (file_id * K_FILE)) & M64)
+    with np.errstate(over="ignore"):
+        h1 = _mix64_np(base + j)
+        h2 = _mix64_np(h1 ^ np.uint64(K_H2))
+    b1 = h1.view(np.uint8).reshape(-1, 8).astype(np.uint32)
+    b2 = h2.view(np.uint8).reshape(-1, 8)
+    out = (0x20 + ((b1 * 95) >> 8)).astype(np.uint8)
+    out[b2 < 3] = 10
+    return out.reshape(-1)[:length].copy()
+
+
 def b3_corpus(n=256 << 20, seed=12345):
     """SURVEY.md Appendix B.3 (numpy 2.x default_rng bit stream)."""
     rng = np.random.default_rng(seed)

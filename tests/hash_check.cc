@@ -19,7 +19,7 @@ static uint32_t rnd() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 
 // what HashEngine::probe computes (scan_kernels.cu): slot = umulhi(key * mul, slots); hit <=> table[slot] == key
 static bool lookup(const Program &p, uint32_t key, uint32_t *slot)
 {
-	*slot = umulhi32(key * p.hash_mul, p.hash_slots);
+	*slot = umulhi32(key * (p.hash_mul << (8 * (4 - p.hash_len))), p.hash_slots);
 	return p.hash_table[*slot] == key;
 }
 
