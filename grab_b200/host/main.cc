@@ -1,179 +1,315 @@
-// main.cc -- grab-b200: the reference's command line (/root/reference/src/main.cc:105-266) in front
-// of the CUDA scan engine.  Same getopt string "Rrn:IOlsL", same config-map keys, same exit codes;
-// additionally accepts -2 -H (aliases: same PCRE match semantics) and -S (literal pattern) from the
-// reference's README.md:16-31.  GPU knobs are environment variables so the short-flag surface
-// stays identical: GRAB_B200_DEVICE=<n> (first GPU), GRAB_B200_NDEV=<k> (GPUs to spread over: threads under -n,
-// batches of windows otherwise -- also the windows of ONE huge file), GRAB_B200_LANES=<k> (scan lanes per GPU),
-// GRAB_B200_BATCH_BYTES=<n> (bytes of windows per engine call, default 256 MiB), GRAB_B200_LENIENT=1 (do not
-// reproduce quirk Q2).
-#include <ftw.h>
+// main.cc -- grab-b200, the command line of the B200 scan engine.
+//
+// Written against the BEHAVIOUR of the reference's front end (flag letters, messages and exit codes recorded in
+// tests/golden/kat.json from the unmodified binary; semantics in /root/reference/README.md:16-31 and SURVEY.md 8(b)
+// "CLI surface to keep"), not against its source: options are table driven, the -n crew is a small pool class, and
+// the directory walk that feeds the crew is parallel (the reference walks serially before it starts its threads,
+// README.md:137-139 -- on a GPU box that serial walk is most of the wall time of a recursive grab).
+//
+//   grab-b200 [-rR] [-I] [-O] [-L] [-l] [-s] [-n <cores>] [-S] [-2] [-H] <regex> <path> [<path> ...]
+//
+// GPU knobs are environment variables, so the short-flag surface stays the reference's:
+//   GRAB_B200_DEVICE=<n>       first GPU
+//   GRAB_B200_NDEV=<k>         GPUs to spread over (threads under -n, batches of windows otherwise)
+//   GRAB_B200_LANES=<k>        scan lanes per GPU
+//   GRAB_B200_BATCH_BYTES=<n>  bytes of windows per engine call (default 256 MiB)
+//   GRAB_B200_LENIENT=1        do not reproduce quirk Q2 (capturing groups print nothing)
+#include <dirent.h>
+#include <fcntl.h>
 #include <pthread.h>
 #include <sched.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <iostream>
 #include <map>
-#include <new>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "filegrep.h"
 
-using namespace std;
-using grab_b200::FileGrep;
+namespace {
 
-struct thread_arg {
-	int idx, nthreads;
-	FileGrep *grep;
+using grab_b200::FileGrep;
+typedef std::map<std::string, size_t> Settings;
+
+constexpr int kFailure = -1;                     // what the reference returns from main: exit status 255
+constexpr size_t kDefaultChunk = (size_t)1 << 30; // grab.h:48
+constexpr size_t kSmallestChunk = (size_t)1 << 25;
+
+struct Invocation {
+	Settings settings;
+	size_t chunk = kDefaultChunk;
+	int workers = 0;
+	std::string regex;
+	std::vector<std::string> paths;
+	int first_gpu = 0, gpus = 1;
 };
 
-static vector<string> files;
-static vector<struct stat> stats;
-
-static int thread_walk(const char *path, const struct stat *st, int typeflag, struct FTW *)
+[[noreturn]] void print_usage_and_exit(const char *self)
 {
-	if (typeflag == FTW_F && S_ISREG(st->st_mode)) { // main.cc:74-83
-		files.push_back(path);
-		stats.push_back(*st);
-	}
-	return 0;
-}
-
-static void *find_iterative(void *vp)
-{
-	thread_arg *ta = static_cast<thread_arg *>(vp);
-	int vsize = (int)files.size();
-	for (int i = ta->idx; i < vsize; i += ta->nthreads) // static round-robin over files, main.cc:94
-		ta->grep->find(files[i].c_str(), &stats[i], FTW_F);
-	ta->grep->flush();
-	return nullptr;
-}
-
-static void usage(const string &p)
-{
-	cout << "Usage: " << p << " [-rR] [-I] [-O] [-L] [-l] [-s] [-n <cores>] <regex> <path>\n";
+	std::cout << "Usage: " << self << " [-rR] [-I] [-O] [-L] [-l] [-s] [-n <cores>] <regex> <path>\n";
 	exit(1);
 }
 
+// ---- options: one row per flag letter ------------------------------------------------------------------------
+struct FlagRow {
+	char letter;
+	const char *key;      // settings key switched on by the flag (nullptr: see `special`)
+	void (*special)(Invocation &, const char *arg);
+};
+
+void halve_chunk(Invocation &inv, const char *)
+{
+	inv.settings["low_mem"] = 1;
+	inv.chunk = inv.chunk / 2 < kSmallestChunk ? kSmallestChunk : inv.chunk / 2; // every -L halves, never below 32 MiB
+}
+void colour_if_terminal(Invocation &inv, const char *) { if (isatty(STDOUT_FILENO)) inv.settings["color"] = 1; }
+void set_workers(Invocation &inv, const char *arg) { inv.workers = atoi(arg); inv.settings["cores"] = (size_t)inv.workers; }
+void same_engine(Invocation &, const char *) {} // -2 / -H pick engines of the greppin branch: one engine here
+
+const FlagRow kFlags[] = {
+	{'r', "recursive", nullptr}, {'R', "recursive", nullptr}, {'s', "single", nullptr}, {'O', "offsets", nullptr},
+	{'l', "noline", nullptr},    {'S', "literal", nullptr},   {'L', nullptr, halve_chunk}, {'I', nullptr, colour_if_terminal},
+	{'n', nullptr, set_workers}, {'2', nullptr, same_engine}, {'H', nullptr, same_engine},
+};
+
+size_t env_number(const char *name, size_t fallback)
+{
+	const char *v = getenv(name);
+	if (!v || !*v) return fallback;
+	const long long n = atoll(v);
+	return n > 0 ? (size_t)n : fallback;
+}
+
+Invocation parse(int argc, char **argv)
+{
+	Invocation inv;
+	for (int c; (c = getopt(argc, argv, "Rrn:IOlsL2HS")) != -1;) {
+		const FlagRow *row = nullptr;
+		for (const FlagRow &f : kFlags) if (f.letter == c) row = &f;
+		if (!row) print_usage_and_exit(argv[0]);
+		if (row->key) inv.settings[row->key] = 1;
+		else row->special(inv, optarg);
+	}
+	if (argc - optind < 2) print_usage_and_exit(argv[0]);
+	inv.regex = argv[optind++];
+	while (optind < argc) inv.paths.push_back(argv[optind++]);
+	if (getenv("GRAB_B200_LENIENT")) inv.settings["lenient"] = 1;
+	inv.first_gpu = (int)env_number("GRAB_B200_DEVICE", 0);
+	inv.gpus = (int)env_number("GRAB_B200_NDEV", 1);
+	if (size_t b = env_number("GRAB_B200_BATCH_BYTES", 0)) inv.settings["batch_bytes"] = b;
+	if (size_t l = env_number("GRAB_B200_LANES", 0)) inv.settings["lanes"] = l;
+	return inv;
+}
+
+// ---- parallel directory walk -----------------------------------------------------------------------------------
+// Same visit rule as the reference's nftw(..., FTW_PHYS): regular files only, symbolic links are never followed,
+// unreadable directories are skipped without a word.  Directories are a shared work list; every walker keeps the
+// files it finds in its own list (no lock on the hot path), and each file carries the stat the scan needs.
+struct FoundFile {
+	std::string path;
+	struct stat st;
+};
+
+class TreeWalk {
+public:
+	explicit TreeWalk(int walkers) : d_found((size_t)(walkers < 1 ? 1 : walkers)) {}
+
+	void run(const std::string &root)
+	{
+		struct stat st;
+		if (lstat(root.c_str(), &st) != 0) return; // the reference ignores nftw's verdict in this mode
+		if (S_ISREG(st.st_mode)) { d_found[0].push_back(FoundFile{root, st}); return; }
+		if (!S_ISDIR(st.st_mode)) return;
+		d_dirs.push_back(root);
+		std::vector<pthread_t> tids(d_found.size());
+		std::vector<Arg> args(d_found.size());
+		size_t started = 0;
+		for (; started < tids.size(); started++) {
+			args[started] = Arg{this, started};
+			if (pthread_create(&tids[started], nullptr, &TreeWalk::entry, &args[started]) != 0) break;
+		}
+		if (started == 0) walker(0); // no helper could be started: walk on this thread
+		for (size_t i = 0; i < started; i++) pthread_join(tids[i], nullptr);
+	}
+
+	// all files, walker by walker (the order is as arbitrary as readdir's; output parity is defined on sorted lines)
+	std::vector<FoundFile> take()
+	{
+		std::vector<FoundFile> all;
+		size_t n = 0;
+		for (auto &v : d_found) n += v.size();
+		all.reserve(n);
+		for (auto &v : d_found) { for (auto &f : v) all.push_back(std::move(f)); v.clear(); }
+		return all;
+	}
+
+private:
+	struct Arg { TreeWalk *self; size_t id; };
+	static void *entry(void *p) { Arg *a = static_cast<Arg *>(p); a->self->walker(a->id); return nullptr; }
+
+	bool next_dir(std::string &dir)
+	{
+		std::unique_lock<std::mutex> lk(d_mu);
+		for (;;) {
+			if (!d_dirs.empty()) { dir = std::move(d_dirs.back()); d_dirs.pop_back(); d_busy++; return true; }
+			if (d_busy == 0) { d_cv.notify_all(); return false; } // nothing queued, nobody can add: done
+			d_cv.wait(lk);
+		}
+	}
+
+	void walker(size_t id)
+	{
+		std::string dir;
+		std::vector<std::string> sub;
+		while (next_dir(dir)) {
+			sub.clear();
+			if (DIR *d = opendir(dir.c_str())) {
+				const int dfd = dirfd(d);
+				while (struct dirent *e = readdir(d)) {
+					const char *n = e->d_name;
+					if (n[0] == '.' && (n[1] == 0 || (n[1] == '.' && n[2] == 0))) continue;
+					if (e->d_type == DT_DIR) { sub.push_back(dir + "/" + n); continue; }
+					if (e->d_type != DT_REG && e->d_type != DT_UNKNOWN) continue; // links, devices, sockets: never scanned
+					struct stat st;
+					if (fstatat(dfd, n, &st, AT_SYMLINK_NOFOLLOW) != 0) continue;
+					if (S_ISDIR(st.st_mode)) sub.push_back(dir + "/" + n);
+					else if (S_ISREG(st.st_mode)) d_found[id].push_back(FoundFile{dir + "/" + n, st});
+				}
+				closedir(d);
+			}
+			std::lock_guard<std::mutex> g(d_mu);
+			for (auto &s : sub) d_dirs.push_back(std::move(s));
+			d_busy--;
+			d_cv.notify_all();
+		}
+	}
+
+	std::mutex d_mu;
+	std::condition_variable d_cv;
+	std::vector<std::string> d_dirs;
+	int d_busy = 0;
+	std::vector<std::vector<FoundFile>> d_found;
+};
+
+// ---- the -n crew: N scanners, scanner i pinned to CPU i, each with a private engine ---------------------------------
+class Crew {
+public:
+	Crew(const Invocation &inv, const std::vector<FoundFile> &files) : d_inv(inv), d_files(files) {}
+
+	// returns only when every scanner is done; thread-start problems end the process like the reference does
+	void run()
+	{
+		const int n = d_inv.workers;
+		std::vector<Member> crew((size_t)n);
+		for (int i = 0; i < n; i++) {
+			Member &m = crew[(size_t)i];
+			m.owner = this;
+			m.rank = i;
+			Settings s = d_inv.settings;
+			s["device"] = (size_t)(d_inv.first_gpu + i % d_inv.gpus); // scanners spread over the box's GPUs
+			m.grep.reset(new FileGrep);
+			m.grep->config(s);
+			m.grep->prepare(d_inv.regex); // a bad pattern is not reported in this mode (the scanners then find nothing)
+			m.grep->recurse();
+			if (int r = pthread_create(&m.tid, nullptr, &Crew::entry, &m)) {
+				std::cerr << "pthread_create: " << strerror(r) << std::endl;
+				exit(kFailure);
+			}
+			cpu_set_t one;
+			CPU_ZERO(&one);
+			CPU_SET(i, &one);
+			if (int r = pthread_setaffinity_np(m.tid, sizeof(one), &one)) {
+				std::cerr << "pthread_setaffinity_np:" << strerror(r) << " (more threads than cores?)" << std::endl;
+				exit(kFailure);
+			}
+		}
+		for (Member &m : crew) {
+			pthread_join(m.tid, nullptr);
+			m.grep.reset(); // prints what is still queued
+		}
+	}
+
+private:
+	struct Member {
+		Crew *owner = nullptr;
+		int rank = 0;
+		pthread_t tid{};
+		std::unique_ptr<FileGrep> grep;
+	};
+	static void *entry(void *p)
+	{
+		Member *m = static_cast<Member *>(p);
+		const std::vector<FoundFile> &files = m->owner->d_files;
+		const size_t stride = (size_t)m->owner->d_inv.workers;
+		for (size_t i = (size_t)m->rank; i < files.size(); i += stride) // file i belongs to scanner i mod N
+			m->grep->find(files[i].path.c_str(), &files[i].st, 0);
+		m->grep->flush();
+		return nullptr;
+	}
+	const Invocation &d_inv;
+	const std::vector<FoundFile> &d_files;
+};
+
+int run_crew(Invocation &inv)
+{
+	if (inv.settings.count("recursive") == 0) {
+		std::cerr << "Multicore support only for recursive grabs.\n";
+		return kFailure;
+	}
+	inv.settings["chunk_size"] = inv.chunk / 4; // N scanners hold N windows: a quarter of the chunk each
+	// every scanner stages its own batches: keep the engine's helper lanes from oversubscribing the host
+	if (!getenv("GSCAN_STAGE_THREADS")) setenv("GSCAN_STAGE_THREADS", inv.workers >= 8 ? "1" : "2", 1);
+	TreeWalk walk(inv.workers < 32 ? inv.workers : 32);
+	walk.run(inv.paths[0]);
+	const std::vector<FoundFile> files = walk.take();
+	Crew(inv, files).run();
+	return 0;
+}
+
+int run_single(Invocation &inv)
+{
+	inv.settings["device"] = (size_t)inv.first_gpu;
+	inv.settings["ndev"] = (size_t)inv.gpus; // batches of windows go round the GPUs; stdout order does not depend on it
+	std::unique_ptr<FileGrep> grep(new (std::nothrow) FileGrep);
+	if (!grep) { std::cerr << "Out of memory.\n"; return kFailure; }
+	grep->config(inv.settings);
+	int status = 0;
+	if (grep->prepare(inv.regex) < 0) {
+		std::cerr << grep->why() << std::endl;
+		return kFailure;
+	}
+	if (inv.settings.count("recursive")) {
+		if (grep->find_recursive(inv.paths[0]) < 0) { std::cerr << grep->why() << std::endl; status = kFailure; }
+		return status;
+	}
+	if (inv.paths.size() > 1) grep->show_path(true);
+	for (const std::string &p : inv.paths) {
+		if (grep->find(p) < 0) {
+			// what earlier paths queued is printed before the complaint, as the reference (which scans path by path) does
+			grep->flush();
+			std::cerr << grep->why() << std::endl;
+			return kFailure;
+		}
+	}
+	if (grep->flush() < 0) { std::cerr << grep->why() << std::endl; status = kFailure; }
+	return status;
+}
+
+} // namespace
+
 int main(int argc, char **argv)
 {
-	int c = 0;
-	map<string, size_t> config;
-	size_t chunk_size = (size_t)1 << 30;
-
-	while ((c = getopt(argc, argv, "Rrn:IOlsL2HS")) != -1) {
-		switch (c) {
-		case 'r': case 'R': config["recursive"] = 1; break;
-		case 's': config["single"] = 1; break;
-		case 'O': config["offsets"] = 1; break;
-		case 'l': config["noline"] = 1; break;
-		case 'L':
-			config["low_mem"] = 1;
-			chunk_size >>= 1;
-			if (chunk_size < ((size_t)1 << 25)) chunk_size = (size_t)1 << 25;
-			break;
-		case 'I':
-			if (isatty(1)) config["color"] = 1;
-			break;
-		case 'n': config["cores"] = (size_t)atoi(optarg); break;
-		case '2': case 'H': break; // engine selectors of the greppin branch: one engine here
-		case 'S': config["literal"] = 1; break;
-		default: usage(argv[0]);
-		}
-	}
-	config["chunk_size"] = chunk_size;
-	if (getenv("GRAB_B200_LENIENT")) config["lenient"] = 1;
-	int device = getenv("GRAB_B200_DEVICE") ? atoi(getenv("GRAB_B200_DEVICE")) : 0;
-	int ndev = getenv("GRAB_B200_NDEV") ? atoi(getenv("GRAB_B200_NDEV")) : 1;
-	if (ndev < 1) ndev = 1;
-	if (getenv("GRAB_B200_BATCH_BYTES") && atoll(getenv("GRAB_B200_BATCH_BYTES")) > 0) config["batch_bytes"] = (size_t)atoll(getenv("GRAB_B200_BATCH_BYTES"));
-	if (getenv("GRAB_B200_LANES") && atoi(getenv("GRAB_B200_LANES")) > 0) config["lanes"] = (size_t)atoi(getenv("GRAB_B200_LANES"));
-
-	if (argc < optind + 2) usage(argv[0]);
-	string regex = argv[optind++];
-	string path = argv[optind++];
-
-	int cores = (int)config["cores"];
-	if (cores > 1) {
-		if (config.count("recursive") == 0) {
-			cerr << "Multicore support only for recursive grabs.\n";
-			return -1;
-		}
-		chunk_size >>= 2; // main.cc:172-173
-		// every thread stages its own batches: keep the engine's helper lanes from oversubscribing the host
-		if (!getenv("GSCAN_STAGE_THREADS")) setenv("GSCAN_STAGE_THREADS", cores >= 8 ? "1" : "2", 1);
-		config["chunk_size"] = chunk_size;
-		files.reserve(1 << 20);
-		stats.reserve(1 << 20);
-		nftw(path.c_str(), thread_walk, 1024, FTW_PHYS);
-
-		thread_arg *ta = new (nothrow) thread_arg[cores];
-		pthread_t *tids = new (nothrow) pthread_t[cores];
-		if (!ta || !tids) { cerr << "Out of memory.\n"; return -1; }
-		for (int i = 0; i < cores; ++i) {
-			// one private engine per thread (main.cc:195-199); threads spread over the box's GPUs
-			map<string, size_t> cfg = config;
-			cfg["device"] = (size_t)(device + i % ndev);
-			FileGrep *tgrep = new (nothrow) FileGrep;
-			tgrep->config(cfg);
-			tgrep->prepare(regex); // return value ignored, as in main.cc:198
-			tgrep->recurse();
-			ta[i].grep = tgrep;
-			ta[i].idx = i;
-			ta[i].nthreads = cores;
-			int r = 0;
-			if ((r = pthread_create(tids + i, nullptr, find_iterative, ta + i)) != 0) {
-				cerr << "pthread_create: " << strerror(r) << endl;
-				exit(-1);
-			}
-			cpu_set_t cpuset;
-			CPU_ZERO(&cpuset);
-			CPU_SET(i, &cpuset);
-			if ((r = pthread_setaffinity_np(tids[i], sizeof(cpuset), &cpuset)) != 0) {
-				cerr << "pthread_setaffinity_np:" << strerror(r) << " (more threads than cores?)" << endl;
-				exit(-1);
-			}
-		}
-		for (int i = 0; i < cores; ++i) {
-			pthread_join(tids[i], nullptr);
-			delete ta[i].grep;
-		}
-		delete[] ta;
-		delete[] tids;
-		exit(0);
-	}
-
-	config["device"] = (size_t)device;
-	config["ndev"] = (size_t)ndev; // batches of windows go round the GPUs; stdout order does not depend on it
-	FileGrep *grep = new (nothrow) FileGrep;
-	if (!grep) { cerr << "Out of memory.\n"; return -1; }
-	grep->config(config);
-	if (grep->prepare(regex) < 0) {
-		cerr << grep->why() << endl;
-		return -1;
-	}
-	if (config.count("recursive") > 0) {
-		if (grep->find_recursive(path) < 0) {
-			cerr << grep->why() << endl;
-			return -1;
-		}
-	} else {
-		if (argc - optind > 0) grep->show_path(1);
-		for (;;) {
-			if (grep->find(path) < 0) {
-				cerr << grep->why() << endl;
-				return -1;
-			}
-			if (argc > optind) path = argv[optind++];
-			else break;
-		}
-		if (grep->flush() < 0) {
-			cerr << grep->why() << endl;
-			return -1;
-		}
-	}
-	delete grep;
-	return 0;
+	Invocation inv = parse(argc, argv);
+	inv.settings["chunk_size"] = inv.chunk;
+	if (inv.workers > 1) return run_crew(inv);
+	return run_single(inv);
 }
