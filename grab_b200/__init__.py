@@ -16,6 +16,7 @@ MODE_ALL, MODE_FIRST, MODE_LINE = 0, 1, 2
 LITERAL, STRICT_REF = 1, 2
 UNIT_DEVICE = 1
 ENGINE_FIXED, ENGINE_RUN, ENGINE_NONE, ENGINE_VM = 1, 2, 3, 4
+KERNEL_NONE, KERNEL_PAIR, KERNEL_TRIPLE, KERNEL_BALANCED, KERNEL_HASH, KERNEL_RUN = 0, 1, 2, 3, 4, 5
 
 
 class GscanError(RuntimeError):
@@ -37,14 +38,14 @@ UNIT_DTYPE = np.dtype([("ptr", "<u8"), ("len", "<u8"), ("base_off", "<u8"), ("fi
 
 class PatternInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("minlen", "maxlen", "captures", "engine", "n_sequences",
-                                              "n_filter_tests", "filter_anchor", "filter_delta")]
+                                              "n_filter_tests", "filter_anchor", "filter_delta", "scan_kernel", "reserved")]
 
 
 class Stats(ctypes.Structure):
     _fields_ = [("bytes_scanned", ctypes.c_uint64), ("n_candidates", ctypes.c_uint64), ("n_matches", ctypes.c_uint64),
                 ("n_units", ctypes.c_uint32), ("n_tiles", ctypes.c_uint32), ("scan_launches", ctypes.c_uint32),
                 ("total_launches", ctypes.c_uint32), ("scan_kernel_ms", ctypes.c_float), ("resolve_ms", ctypes.c_float),
-                ("h2d_ms", ctypes.c_float), ("total_ms", ctypes.c_float)]
+                ("h2d_ms", ctypes.c_float), ("total_ms", ctypes.c_float), ("vm_limit_hit", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -198,22 +199,31 @@ class Context:
         arr["flags"] = UNIT_DEVICE
         return arr
 
-    def _take(self, out, n):
+    def _take(self, out, n, copy=True):
+        """The records of a scan as a numpy array.  copy=False: a view of the context's pinned result buffer, valid until
+        the next scan on this context with copy=False (or close()) -- no per-record work on the host."""
+        if not copy and getattr(self, "_lent", None):
+            lib().gscan_free_matches(self._h, self._lent)
+            self._lent = None
         if n.value == 0:
             return np.zeros(0, dtype=MATCH_DTYPE)
         buf = (ctypes.c_char * (n.value * MATCH_DTYPE.itemsize)).from_address(out.value)
-        res = np.frombuffer(buf, dtype=MATCH_DTYPE).copy()
+        res = np.frombuffer(buf, dtype=MATCH_DTYPE)
+        if not copy:
+            self._lent = out
+            return res
+        res = res.copy()
         lib().gscan_free_matches(self._h, out)
         return res
 
     # ---- scanning ----------------------------------------------------------------------
-    def scan_units(self, pattern, units, mode=MODE_ALL):
+    def scan_units(self, pattern, units, mode=MODE_ALL, copy=True):
         """gscan_scan_batch over a UNIT_DTYPE array."""
         units = np.ascontiguousarray(units, dtype=UNIT_DTYPE)
         out, n = ctypes.c_void_p(), ctypes.c_size_t()
         self._check(lib().gscan_scan_batch(self._h, pattern._h, units.ctypes.data, len(units), mode,
                                            ctypes.byref(out), ctypes.byref(n)))
-        return self._take(out, n)
+        return self._take(out, n, copy)
 
     def scan(self, pattern, bufs, mode=MODE_ALL, file_ids=None, base_offs=None):
         units, keep = self.units_from_buffers(bufs, file_ids, base_offs)
@@ -227,10 +237,10 @@ class Context:
         self._check(lib().gscan_batch_create(self._h, units.ctypes.data, len(units), ctypes.byref(h)))
         return Batch(self, h, keepalive)
 
-    def batch_scan(self, pattern, batch, mode=MODE_ALL):
+    def batch_scan(self, pattern, batch, mode=MODE_ALL, copy=True):
         out, n = ctypes.c_void_p(), ctypes.c_size_t()
         self._check(lib().gscan_batch_scan(self._h, pattern._h, batch._h, mode, ctypes.byref(out), ctypes.byref(n)))
-        return self._take(out, n)
+        return self._take(out, n, copy)
 
     def last_device_matches(self):
         """(device pointer, count) of the last scan's records in HBM (valid until the next scan on this context)."""

@@ -300,6 +300,12 @@ extern "C" int gscan_pattern_get_info(const gscan_pattern *p, gscan_pattern_info
 	o->n_filter_tests = p->prog.use_hash ? -(int32_t)p->prog.hash_slots : (int32_t)p->prog.tests.size();
 	o->filter_anchor = p->prog.anchor;
 	o->filter_delta = p->prog.delta;
+	o->reserved = 0;
+	if (p->prog.kind == ENGINE_NONE) o->scan_kernel = GSCAN_KERNEL_NONE;
+	else if (p->prog.kind == ENGINE_RUN) o->scan_kernel = GSCAN_KERNEL_RUN;
+	else if (p->prog.use_hash) o->scan_kernel = GSCAN_KERNEL_HASH;
+	else if (p->fixed.b_engine) o->scan_kernel = GSCAN_KERNEL_BALANCED;
+	else o->scan_kernel = p->fixed.stage1_triples ? GSCAN_KERNEL_TRIPLE : GSCAN_KERNEL_PAIR;
 	return 0;
 }
 
@@ -763,7 +769,9 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		uint32_t *h_tot = reinterpret_cast<uint32_t *>((uint8_t *)ctx->readback.p + 16);
 		CK(ctx, cudaMemcpyAsync(h_tot, R.totals, 12, cudaMemcpyDeviceToHost, ctx->stream));
 		CK(ctx, cudaStreamSynchronize(ctx->stream));
-		if (h_tot[2]) return fail(ctx, "gscan_batch_scan: the backtracking VM hit its stack or step limit on this input (PCRE would report a match-limit error); nothing is returned rather than a guess");
+		// a unit on which the backtracking VM ran out of stack or steps stops there, like the reference's loop when
+		// pcre_exec reports a match-limit error (rc < 0 => break, grab.cc:179, quirk Q5); the other units are unaffected
+		S.vm_limit_hit = h_tot[2] ? 1u : 0u;
 		if (h_tot[0] != (uint32_t)total_cand) return fail(ctx, "gscan_batch_scan: internal: segment counts disagree with the cursor");
 		n = h_tot[1];
 		if (n) {

@@ -516,6 +516,30 @@ const Node *peel(const Node *n)
 	}
 }
 
+// like peel(), but a capturing group stays (the VM must see it close when capture participation matters, Q2)
+const Node *peel_noncapturing(const Node *n)
+{
+	for (;;) {
+		if (n->kind == Node::GROUP && !n->capturing) { n = n->kids[0].get(); continue; }
+		if ((n->kind == Node::CAT || n->kind == Node::ALT) && n->kids.size() == 1) { n = n->kids[0].get(); continue; }
+		return n;
+	}
+}
+
+// does EVERY match of n close at least one capturing group?  (pcre_exec with room for one offset pair returns 0 for
+// exactly the matches in which a group was set: quirk Q2)
+bool always_captures(const Node *n)
+{
+	switch (n->kind) {
+	case Node::SET: case Node::EMPTY: case Node::ASSERT: return false;
+	case Node::GROUP: return n->capturing || always_captures(n->kids[0].get());
+	case Node::CAT: for (auto &k : n->kids) if (always_captures(k.get())) return true; return false;
+	case Node::ALT: for (auto &k : n->kids) if (!always_captures(k.get())) return false; return !n->kids.empty();
+	case Node::REP: return n->rmin >= 1 && always_captures(n->kids[0].get());
+	}
+	return false;
+}
+
 struct Expander {
 	size_t budget_seqs = kMaxSequences;
 	size_t budget_bytes = 1u << 20;
@@ -657,6 +681,7 @@ bool can_overlap(const Sequence &a, const Sequence &b, size_t shift)
 struct VmGen {
 	std::vector<uint32_t> code; // 3 words per instruction: op | kind << 8 | set << 16, a, b
 	std::vector<ByteSet> sets;
+	bool track_caps = false;    // emit VM_CAP where a capturing group closes
 	bool failed = false;
 	std::string why;
 
@@ -681,7 +706,10 @@ struct VmGen {
 		case Node::EMPTY: return;
 		case Node::SET: emit(VM_SET, 0, set_id(n->set), 0, 0); return;
 		case Node::ASSERT: emit(VM_ASSERT, (uint32_t)n->akind, 0, 0, 0); return;
-		case Node::GROUP: gen(n->kids[0].get()); return;
+		case Node::GROUP:
+			gen(n->kids[0].get());
+			if (track_caps && n->capturing) emit(VM_CAP, 0, 0, 0, 0);
+			return;
 		case Node::CAT: for (auto &k : n->kids) gen(k.get()); return;
 		case Node::ALT: {
 			std::vector<uint32_t> jmps;
@@ -701,7 +729,7 @@ struct VmGen {
 			return;
 		}
 		case Node::REP: {
-			const Node *body = peel(n->kids[0].get());
+			const Node *body = track_caps ? peel_noncapturing(n->kids[0].get()) : peel(n->kids[0].get());
 			const uint32_t kind = n->lazy ? VM_Q_LAZY : n->possessive ? VM_Q_POSSESSIVE : VM_Q_GREEDY;
 			if (body->kind == Node::SET) { emit(VM_REP, kind, set_id(body->set), n->rmin, n->rmax); return; }
 			if (n->possessive) { failed = true; why = "possessive quantifier on a group is not supported"; return; }
@@ -917,16 +945,22 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 	}
 	out.minlen = ml > 65535 ? 65535 : (int)ml; // PCRE2's study caps MINLENGTH at 65535
 
-	if (out.strict_q2 && captures > 0) {
-		// Q2: pcre_exec returns 0 for every match => the loop breaks before printing (grab.cc:179)
+	if (out.strict_q2 && captures > 0 && always_captures(root.get())) {
+		// Q2: every match sets a capturing group, pcre_exec (ovecsize 3) returns 0 for every match => the loop breaks
+		// before printing anything (grab.cc:179)
 		out.kind = ENGINE_NONE;
 		out.maxlen = -1;
 		return true;
 	}
+	// Q2, mixed: `foo|(bar)`, `(x)?foo` -- pcre_exec returns 0 only for the matches in which a group took part: the loop
+	// prints until the first such match and then leaves the window.  Which match that is depends on the path taken, so
+	// these patterns run on the VM, which reports the flag with every match.
+	const bool cap_stops = out.strict_q2 && captures > 0;
+	out.cap_stops = cap_stops;
 
 	// RUN: the whole pattern is one byte class repeated {n,}
 	const Node *core = peel(root.get());
-	if (core->kind == Node::REP && core->rmax == kInf && !core->lazy) {
+	if (!cap_stops && core->kind == Node::REP && core->rmax == kInf && !core->lazy) {
 		const Node *body = peel(core->kids[0].get());
 		if (body->kind == Node::SET && core->rmin >= 1) {
 			if (core->rmin > (uint32_t)kMaxPatternLen) { err = "run minimum above 1024"; return false; }
@@ -951,12 +985,13 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 	// FIXED: expand into fixed-length sequences in backtracking (preference) order
 	Expander ex;
 	std::vector<Sequence> seqs;
-	if (!has_assert(root.get())) seqs = ex.expand(root.get());
+	if (!has_assert(root.get()) && !cap_stops) seqs = ex.expand(root.get());
 	else { ex.overflow = true; ex.general = true; }
 	if (ex.overflow && !ex.general) { err = ex.why; return false; }
 	if (ex.overflow) {
 		// general pattern: VM program + leading-byte prefixes as the candidate filter
 		VmGen g;
+		g.track_caps = cap_stops;
 		g.gen(root.get());
 		g.emit(VM_MATCH, 0, 0, 0, 0);
 		if (g.failed) { err = g.why; return false; }
@@ -966,7 +1001,7 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 		// Candidates are then the run starts (RUN scan kernel), far fewer than "every byte of the class".
 		{
 			const Node *top = peel(root.get());
-			if (top->kind == Node::CAT && top->kids.size() >= 2) {
+			if (!cap_stops && top->kind == Node::CAT && top->kids.size() >= 2) {
 				const Node *lead = top->kids[0].get();
 				while (lead->kind == Node::GROUP) lead = lead->kids[0].get();
 				const Node *body = lead->kind == Node::REP ? peel(lead->kids[0].get()) : nullptr;
@@ -1059,7 +1094,7 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 	for (int d = (mn >= 2 ? 1 : 0); d <= 4; d++) {
 		for (int a = 0; a + d < (int)mn && a <= 224; a++) {
 			std::vector<FilterTest> tests;
-			double p = 0;
+			double p = 0, cost = 0;
 			for (auto &s : out.seqs) {
 				MaskedEq e0 = masked_superset(s[a]);
 				MaskedEq e1 = d ? masked_superset(s[a + d]) : MaskedEq{0, 0, false, 256};
@@ -1067,12 +1102,15 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 				if (std::find(tests.begin(), tests.end(), t) == tests.end()) {
 					tests.push_back(t);
 					p += test_prior(e0) * (d ? test_prior(e1) : 1.0);
+					// a test of two plain bytes is cheaper than one with a mask (and an all-exact multi-test filter runs on the
+					// balanced pair engine, half the ALU-pipe work): prefer `ba` over `b.[rz]` when the priors are close
+					cost += (e0.mask == 0xff && (!d || e1.mask == 0xff)) ? 1.0 : 2.0;
 				}
 			}
 			if ((int)tests.size() > kMaxFilterTests) continue;
 			// each test costs ~4 ALU ops per 4 bytes (a distance of exactly one word needs no funnel shift:
 			// ~20 % cheaper); each flagged position costs a slow-path visit
-			double score = (p * 4000.0 + (double)tests.size()) * (d == 4 ? 0.8 : 1.0);
+			double score = (p * 4000.0 + cost) * (d == 4 ? 0.8 : 1.0);
 			if (score < best_score) { best_score = score; best_a = a; best_d = d; best_tests = tests; best_p = p; }
 		}
 		if (mn < 2) break;

@@ -127,7 +127,7 @@ __global__ void k_gather(const ResolveArgs R)
 // everything and give back one item at a time, lazy ones take one more on demand; explicit stack, no recursion.
 // `subj` is the subject as the reference's pcre_exec call sees it: it begins at the moving search start
 // (grab.cc:178), so ^, \A and \b at its first byte behave exactly as there.
-constexpr int kVmStack = 512; // entries of 12 bytes in thread-local memory; the VM walk runs in its own low-occupancy kernel
+constexpr int kVmStack = 2048; // entries of 12 bytes in thread-local memory (24 KiB per thread); the VM walk runs in its own low-occupancy kernel
 constexpr uint32_t kVmMaxSteps = 1u << 24;
 
 __device__ __forceinline__ bool vm_in_set(const ResolveArgs &R, uint32_t set, uint32_t b) { return (R.vm_sets[set * 8 + (b >> 5)] >> (b & 31)) & 1u; }
@@ -149,19 +149,22 @@ __device__ bool vm_assert(uint32_t kind, const uint8_t *s, uint32_t len, uint32_
 	}
 }
 
-// 1: match, *end set; 0: no match at `at`; -1: stack / step limit
+// 1: match, *end set; 2: match in which a capturing group took part (VM_CAP on the successful path: pcre_exec with room
+// for one offset pair returns 0 for it, quirk Q2); 0: no match at `at`; -1: stack / step limit
 __device__ int vm_exec(const ResolveArgs &R, const uint8_t *s, uint32_t len, uint32_t at, uint32_t *end)
 {
-	uint32_t st_pc[kVmStack], st_sp[kVmStack], st_lo[kVmStack]; // st_pc: pc | kind << 16 (0 plain, 1 give-back, 2 take-more)
+	// st_pc: pc | kind << 16 (0 plain, 1 give-back, 2 take-more) | capture flag at push time << 24
+	uint32_t st_pc[kVmStack], st_sp[kVmStack], st_lo[kVmStack];
 	int top = 0;
-	uint32_t pc = 0, sp = at, steps = 0;
+	uint32_t pc = 0, sp = at, steps = 0, cap = 0;
 	for (;;) {
 		if (++steps > kVmMaxSteps) return -1;
 		const uint32_t w0 = R.vm_code[3 * pc], a = R.vm_code[3 * pc + 1], b = R.vm_code[3 * pc + 2];
 		const uint32_t op = w0 & 0xffu, kind = (w0 >> 8) & 0xffu, set = w0 >> 16;
 		bool fail = false;
 		switch (op) {
-		case VM_MATCH: *end = sp; return 1;
+		case VM_MATCH: *end = sp; return cap ? 2 : 1;
+		case VM_CAP: cap = 1u << 24; pc++; break;
 		case VM_SET:
 			if (sp < len && vm_in_set(R, set, s[sp])) { sp++; pc++; } else fail = true;
 			break;
@@ -171,7 +174,7 @@ __device__ int vm_exec(const ResolveArgs &R, const uint8_t *s, uint32_t len, uin
 		case VM_JMP: pc = a; break;
 		case VM_SPLIT:
 			if (top == kVmStack) return -1;
-			st_pc[top] = b; st_sp[top] = sp; st_lo[top] = 0; top++;
+			st_pc[top] = b | cap; st_sp[top] = sp; st_lo[top] = 0; top++;
 			pc = a;
 			break;
 		default: { // VM_REP: one byte class, a = min, b = max
@@ -182,7 +185,7 @@ __device__ int vm_exec(const ResolveArgs &R, const uint8_t *s, uint32_t len, uin
 				if (k < a) { fail = true; break; }
 				if (b > a) { // may take more later: remember how many
 					if (top == kVmStack) return -1;
-					st_pc[top] = pc | (2u << 16); st_sp[top] = sp + k; st_lo[top] = b == 0xffffffffu ? 0xffffffffu : b - a; top++;
+					st_pc[top] = pc | (2u << 16) | cap; st_sp[top] = sp + k; st_lo[top] = b == 0xffffffffu ? 0xffffffffu : b - a; top++;
 				}
 				sp += k; pc++;
 			} else {
@@ -190,7 +193,7 @@ __device__ int vm_exec(const ResolveArgs &R, const uint8_t *s, uint32_t len, uin
 				if (k < a) { fail = true; break; }
 				if (kind == VM_Q_GREEDY && k > a) {
 					if (top == kVmStack) return -1;
-					st_pc[top] = (pc + 1) | (1u << 16); st_sp[top] = sp + k; st_lo[top] = sp + a; top++;
+					st_pc[top] = (pc + 1) | (1u << 16) | cap; st_sp[top] = sp + k; st_lo[top] = sp + a; top++;
 				}
 				sp += k; pc++;
 			}
@@ -200,8 +203,9 @@ __device__ int vm_exec(const ResolveArgs &R, const uint8_t *s, uint32_t len, uin
 		if (!fail) continue;
 		for (;;) { // backtrack
 			if (top == 0) return 0;
-			const uint32_t e = st_pc[top - 1], ek = e >> 16;
-			if (ek == 0) { pc = e; sp = st_sp[top - 1]; top--; break; }
+			const uint32_t e = st_pc[top - 1], ek = (e >> 16) & 0xffu;
+			cap = e & (1u << 24); // whatever closed after this choice point is undone
+			if (ek == 0) { pc = e & 0xffffu; sp = st_sp[top - 1]; top--; break; }
 			if (ek == 1) { // greedy repeat gives one item back
 				if (st_sp[top - 1] > st_lo[top - 1]) {
 					sp = --st_sp[top - 1];
@@ -317,6 +321,7 @@ __global__ void __launch_bounds__(64, 4) k_walk_vm(const ResolveArgs R)
 			if (start > 0 && in_class(R, data[start - 1]) && in_class(R, data[start])) {
 				const int rc = vm_exec(R, data + start, (uint32_t)(ulen - start), 0u, &e);
 				if (rc < 0) { atomicOr(R.totals + 2, 1u); break; }
+				if (rc == 2) break;                                                     // Q2: pcre_exec returns 0, the loop leaves the window
 				if (rc == 1) { pos = start; found = true; }
 			}
 			while (!found) {
@@ -325,6 +330,7 @@ __global__ void __launch_bounds__(64, 4) k_walk_vm(const ResolveArgs R)
 				pos = R.ord[i++].pos;
 				const int rc = vm_exec(R, data + start, (uint32_t)(ulen - start), (uint32_t)(pos - start), &e); // grab.cc:178
 				if (rc < 0) { atomicOr(R.totals + 2, 1u); i = end; break; }
+				if (rc == 2) { i = end; break; }                                        // Q2
 				found = rc == 1;
 			}
 			if (!found) break;
@@ -351,8 +357,9 @@ __global__ void __launch_bounds__(64, 4) k_walk_vm(const ResolveArgs R)
 				if (pos < start) continue;
 				uint32_t e = 0;
 				const int rc = vm_exec(R, data + start, (uint32_t)(ulen - start), (uint32_t)(pos - start), &e); // grab.cc:178
-				if (rc < 0) { atomicOr(R.totals + 2, 1u); break; }                      // limits: reported, never guessed
+				if (rc < 0) { atomicOr(R.totals + 2, 1u); break; }                      // limit: this unit stops here (pcre_exec error => break, grab.cc:179 / Q5)
 				if (rc == 0) continue;                                                  // next start offset, like PCRE
+				if (rc == 2) break;                                                     // Q2: a group was set => rc 0 => grab.cc:179 breaks
 				uint64_t me = start + e;
 				R.ord[i].len = (uint32_t)(me - pos);
 				R.ord[i].pad = 1;

@@ -762,8 +762,11 @@ struct RunEngine {
 		uint32_t prevbit = 0;
 		if (S.off + S.begin > 0) prevbit = in_class(P, S.tile[(int)S.begin - 1]); // 16-byte look-behind copy
 		const uint32_t send = S.begin + S.niter * 512;
-		if (S.niter == (uint32_t)kRows && (unsigned long long)S.off + send + 16 <= S.ulen) {
-			// ---- full slice strictly inside the unit: no validity masks, everything in registers ----
+		if (S.niter == (uint32_t)kRows && (unsigned long long)S.off + send <= S.ulen) {
+			// ---- full slice inside the unit (also its last one: a 16 KiB file is four of these): no validity masks but on
+			// the look-ahead bytes, everything in registers ----
+			const unsigned long long after = (unsigned long long)S.ulen - S.off - send; // bytes of the unit behind the slice
+			const uint32_t la_valid = after >= 16 ? 0xffffu : ((1u << (uint32_t)after) - 1u);
 			uint32_t cm[kRows + 1];
 			if (NHI == 0) {
 				// speculate that the slice is plain ASCII (cheaper classification); if a byte >= 0x80 shows up the masks are
@@ -771,12 +774,12 @@ struct RunEngine {
 				uint32_t seen = 0;
 #pragma unroll
 				for (int r = 0; r < kRows; r++) cm[r] = mask16_ascii(P, S.tile + S.begin + r * 512 + lane * 16, seen);
-				const uint32_t x = *reinterpret_cast<const uint32_t *>(S.tile + send + (lane & 3) * 4);
+				const uint32_t x = la_valid ? *reinterpret_cast<const uint32_t *>(S.tile + send + (lane & 3) * 4) : 0u; // no copy behind the unit's end
 				seen |= x;
 				uint32_t nib = (pack_top_nibble(class_flags_ascii(P, x)) >> 28) << ((lane & 3) * 4);
 				nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
 				nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
-				cm[kRows] = nib; // correct in lanes 0..3; only lane 0's copy is consumed (by lane 31)
+				cm[kRows] = nib & la_valid; // correct in lanes 0..3; only lane 0's copy is consumed (by lane 31)
 				if (__any_sync(0xffffffffu, (seen & kHigh) != 0)) {
 					E.n += run_tail(P, S.tile, S.gtile, S.off, S.ulen, S.begin, S.niter, prevbit, E.scratch + E.n, lane);
 					return;
@@ -785,11 +788,11 @@ struct RunEngine {
 #pragma unroll
 				for (int r = 0; r < kRows; r++) cm[r] = mask16_inner(P, S.tile + S.begin + r * 512 + lane * 16);
 				// the 16 bytes after the slice: lanes 0..3 classify one word each of the look-ahead copy
-				const uint32_t x = *reinterpret_cast<const uint32_t *>(S.tile + send + (lane & 3) * 4);
+				const uint32_t x = la_valid ? *reinterpret_cast<const uint32_t *>(S.tile + send + (lane & 3) * 4) : 0u;
 				uint32_t nib = (pack_top_nibble(class_flags(P, x)) >> 28) << ((lane & 3) * 4);
 				nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
 				nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
-				cm[kRows] = nib; // correct in lanes 0..3; only lane 0's copy is consumed (by lane 31)
+				cm[kRows] = nib & la_valid; // correct in lanes 0..3; only lane 0's copy is consumed (by lane 31)
 			}
 			const uint32_t nxt_lane = (lane + 1) & 31, prv_lane = (lane + 31) & 31;
 #pragma unroll

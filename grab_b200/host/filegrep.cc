@@ -7,6 +7,7 @@
 #include <sys/mman.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <cerrno>
 #include <chrono>
 #include <condition_variable>
@@ -16,6 +17,7 @@
 #include <deque>
 #include <iostream>
 #include <mutex>
+#include <system_error>
 #include <thread>
 
 #include "../../include/gscan.h"
@@ -144,6 +146,12 @@ int FileGrep::find(const char *path, const struct stat *st, int)
 		}
 		clen = (st->st_size - off < (off_t)d_chunk_size) ? (size_t)(st->st_size - off) : d_chunk_size;
 		void *m = mmap(nullptr, clen, PROT_READ, MAP_PRIVATE | MAP_NORESERVE, fd, off); // grab.cc:126-128,161
+		if (m == MAP_FAILED && errno == ENOMEM && (!d_queue.empty() || d_pipe)) {
+			// out of address space or mappings (vm.max_map_count) because queued windows are still mapped: the reference
+			// holds one window at a time -- print what is queued, which unmaps it, and try again
+			flush_quietly();
+			m = mmap(nullptr, clen, PROT_READ, MAP_PRIVATE | MAP_NORESERVE, fd, off);
+		}
 		if (m == MAP_FAILED) {
 			d_err = "FileGrep::find::mmap: " + std::string(strerror(errno));
 			close(fd);
@@ -158,7 +166,9 @@ int FileGrep::find(const char *path, const struct stat *st, int)
 		w.file_seq = seq;
 		d_queue.push_back(std::move(w));
 		d_queued_bytes += clen;
-		if (d_queued_bytes >= d_batch_bytes && submit() < 0) { close(fd); return -1; }
+		// a batch is cut by bytes or by windows: every queued window is a live mapping, and a tree of tiny files would
+		// otherwise run into vm.max_map_count (65530) long before 256 MiB are queued
+		if ((d_queued_bytes >= d_batch_bytes || d_queue.size() >= max_windows_per_batch()) && submit() < 0) { close(fd); return -1; }
 	}
 	close(fd);
 	return 0;
@@ -203,8 +213,8 @@ void FileGrep::format_window(const Window &w, const gscan_match_view *m, size_t 
 	}
 }
 
-// Moves the queued windows into a batch for the lanes.  Returns -1 when an earlier batch failed (why() has the
-// first failure); the queue is empty afterwards either way.
+// Moves the queued windows into a batch for the lanes.  Returns -1 only when no lane could be started; the failure of
+// an earlier batch is kept for flush() to report.  The queue is empty afterwards either way.
 int FileGrep::submit()
 {
 	if (d_queue.empty()) return 0;
@@ -217,23 +227,49 @@ int FileGrep::submit()
 	if (p.lanes.empty()) {
 		trace_ts("first batch submitted");
 		const int n = d_ndev * d_lanes_per_dev;
-		for (int i = 0; i < n; i++) p.lanes.emplace_back(&FileGrep::lane_main, this, i);
+		for (int i = 0; i < n; i++) {
+			try {
+				p.lanes.emplace_back(&FileGrep::lane_main, this, i);
+			} catch (const std::system_error &e) { // thread limit, no memory: work with the lanes that did start
+				if (p.lanes.empty()) {
+					d_err = std::string("FileGrep::find::lane: ") + e.what();
+					lk.unlock();
+					for (auto &w : b->windows) release(w);
+					delete b;
+					return -1;
+				}
+				break;
+			}
+		}
 	}
 	// bounded look-ahead: at most one waiting batch per lane keeps the mapped-but-unscanned windows small
 	p.cv_space.wait(lk, [&] { return p.jobs.size() < p.lanes.size(); });
-	if (p.failed) {
-		d_err = p.err;
-		lk.unlock();
-		for (auto &w : b->windows) release(w);
-		delete b;
-		return -1;
-	}
+	// a batch that failed earlier is reported by flush(); later batches are still scanned and printed -- the reference
+	// keeps going after a file it could not search (grab.cc:267-268)
 	b->seq = p.next_seq++;
 	p.inflight++;
 	p.jobs.push_back(b);
 	lk.unlock();
 	p.cv_job.notify_one();
 	return 0;
+}
+
+// windows per batch: all batches that can be alive at once (one being filled, one waiting and one running per lane)
+// stay well below the default vm.max_map_count of 65530
+size_t FileGrep::max_windows_per_batch() const
+{
+	const size_t lanes = (size_t)(d_ndev * d_lanes_per_dev);
+	const size_t cap = 49152 / (2 * lanes + 1);
+	return cap < 8192 ? (cap < 64 ? 64 : cap) : 8192;
+}
+
+// flush() that keeps a lane failure for the final flush() to report
+void FileGrep::flush_quietly()
+{
+	submit();
+	if (!d_pipe) return;
+	std::unique_lock<std::mutex> lk(d_pipe->mu);
+	d_pipe->cv_idle.wait(lk, [&] { return d_pipe->inflight == 0; });
 }
 
 // Submits what is queued and waits until every batch has been printed.
@@ -302,6 +338,13 @@ void FileGrep::lane_main(int lane)
 			size_t n = 0;
 			rc = gscan_scan_batch(ctx, d_pat, units.data(), units.size(), mode, &matches, &n);
 			if (rc < 0) err = std::string("FileGrep::find::scan: ") + gscan_why(ctx);
+			else {
+				gscan_stats st;
+				static std::atomic<bool> warned{false};
+				if (gscan_last_stats(ctx, &st) == 0 && st.vm_limit_hit && !warned.exchange(true))
+					std::cerr << "grab-b200: backtracking limit reached in at least one window; the search of that window stopped there "
+					             "(the reference's loop does the same when pcre_exec reports an error)\n";
+			}
 			if (trace) {
 				gscan_stats st;
 				gscan_last_stats(ctx, &st);

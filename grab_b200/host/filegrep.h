@@ -69,6 +69,8 @@ private:
 	struct Pipeline;
 	friend struct Pipeline;
 	int submit();                      // hand the queued windows to the lanes (blocks only when they are all busy)
+	void flush_quietly();              // submit + wait, leaving a lane failure for flush() to report
+	size_t max_windows_per_batch() const;
 	void lane_main(int lane);
 	void format_window(const Window &w, const struct gscan_match_view *m, size_t n, std::string &out) const;
 	static void release(Window &w);

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GSCAN_ABI_VERSION 1
+#define GSCAN_ABI_VERSION 2
 
 typedef struct gscan_ctx gscan_ctx;
 typedef struct gscan_pattern gscan_pattern;
@@ -69,7 +69,16 @@ typedef struct gscan_pattern_info {
 	int32_t n_filter_tests; /* byte-pair tests of the SWAR filter; negative: hashed engine, -(table slots) */
 	int32_t filter_anchor; /* byte of the pattern the SWAR filter is anchored on */
 	int32_t filter_delta;  /* distance to the second filter byte (0: single-byte filter) */
+	int32_t scan_kernel;   /* GSCAN_KERNEL_* below: which scan-kernel family serves the pattern */
+	int32_t reserved;
 } gscan_pattern_info;
+
+#define GSCAN_KERNEL_NONE 0
+#define GSCAN_KERNEL_PAIR 1     /* byte-pair SWAR filter (single literals: the HBM-bound kernel) */
+#define GSCAN_KERNEL_TRIPLE 2   /* byte-triple SWAR filter (masked / case-insensitive multi-alternative patterns) */
+#define GSCAN_KERNEL_BALANCED 3 /* exact byte pairs on both issue pipes + inline third-byte stage (small alternations) */
+#define GSCAN_KERNEL_HASH 4     /* perfect-hash membership of the leading bytes (large literal sets) */
+#define GSCAN_KERNEL_RUN 5      /* byte-class runs */
 
 #define GSCAN_ENGINE_FIXED 1 /* alternation of fixed-length byte-class sequences (literals, sets) */
 #define GSCAN_ENGINE_RUN 2   /* one byte class repeated {n,} (greedy) */
@@ -87,6 +96,10 @@ typedef struct gscan_stats {
 	float resolve_ms;        /* CUDA-event time of the resolve/compaction kernels */
 	float h2d_ms;            /* host->device staging (host units only; overlapped with scanning) */
 	float total_ms;          /* wall time of the call */
+	uint32_t vm_limit_hit;   /* != 0: on at least one unit the device VM ran out of backtracking stack (2048 frames) or steps;
+	                            that unit's loop stopped there, as the reference's does when pcre_exec returns an error
+	                            (grab.cc:179, quirk Q5) -- the matches before it and all other units are complete */
+	uint32_t reserved;
 } gscan_stats;
 
 /* ---- pattern: replaces FileGrep::prepare (grab.cc:101-123) ----------------------------- */

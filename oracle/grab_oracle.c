@@ -538,7 +538,7 @@ static int n_nullable(const node *n) { return n_minlen(n) == 0; }
 /* program                                                                                     */
 /* ------------------------------------------------------------------------------------------ */
 
-enum { I_SET, I_SPLIT, I_JMP, I_REP, I_ASSERT, I_MATCH };
+enum { I_SET, I_SPLIT, I_JMP, I_REP, I_ASSERT, I_MATCH, I_CAP /* a capturing group closed */ };
 
 typedef struct { uint32_t op, a, b, c, d; } inst;
 
@@ -642,7 +642,10 @@ static void gen(go_regex *re, const node *n)
 	case N_SET: emit(re, I_SET, addset(re, &n->set), 0, 0, 0); break;
 	case N_ASSERT: emit(re, I_ASSERT, (uint32_t)n->akind, 0, 0, 0); break;
 	case N_CAT: for (int i = 0; i < n->nkid; i++) gen(re, n->kid[i]); break;
-	case N_GROUP: gen(re, n->kid[0]); break;
+	case N_GROUP:
+		gen(re, n->kid[0]);
+		if (n->capturing) emit(re, I_CAP, 0, 0, 0, 0);
+		break;
 	case N_REP: gen_rep(re, n); break;
 	case N_ALT: {
 		/* split a1, L2 ; a1 ; jmp end ; L2: split a2, L3 ; ... ; an */
@@ -746,12 +749,12 @@ int go_nullable(const go_regex *re) { return re->nullable; }
 /* backtracking VM                                                                             */
 /* ------------------------------------------------------------------------------------------ */
 
-typedef struct { uint32_t pc; uint32_t kind; size_t sp, lo; } bt;
+typedef struct { uint32_t pc; uint32_t kind; size_t sp, lo; int cap; /* was a capturing group set when this choice was pushed? */ } bt;
 enum { BT_PLAIN, BT_REP_GIVEBACK, BT_REP_TAKEMORE };
 
 typedef struct { bt *v; size_t n, cap; } btstack;
 
-static int bt_push(btstack *s, uint32_t pc, uint32_t kind, size_t sp, size_t lo)
+static int bt_push(btstack *s, uint32_t pc, uint32_t kind, size_t sp, size_t lo, int cap)
 {
 	if (s->n == s->cap) {
 		size_t nc = s->cap ? s->cap * 2 : 256;
@@ -761,7 +764,7 @@ static int bt_push(btstack *s, uint32_t pc, uint32_t kind, size_t sp, size_t lo)
 		s->v = nv;
 		s->cap = nc;
 	}
-	s->v[s->n].pc = pc; s->v[s->n].kind = kind; s->v[s->n].sp = sp; s->v[s->n].lo = lo;
+	s->v[s->n].pc = pc; s->v[s->n].kind = kind; s->v[s->n].sp = sp; s->v[s->n].lo = lo; s->v[s->n].cap = cap;
 	s->n++;
 	return 0;
 }
@@ -785,7 +788,8 @@ static int check_assert(int kind, const uint8_t *s, size_t len, size_t sp)
 	return 0;
 }
 
-/* one anchored attempt at offset `at`; returns 1 and *e on success, 0 on failure, -1 on limit */
+/* one anchored attempt at offset `at`; returns 1 and *e on success (2: a capturing group was set on the successful
+ * path -- with room for a single offset pair pcre_exec then returns 0, quirk Q2), 0 on failure, -1 on limit */
 /* PCRE bounds its search (match limit, 10 million by default); so does the oracle, or a pathological pattern
  * would keep a test busy for hours.  Hitting the limit is reported (-1), never turned into an answer. */
 #define GO_MATCH_LIMIT 20000000ul
@@ -795,13 +799,15 @@ static int attempt(const go_regex *re, const uint8_t *s, size_t len, size_t at, 
 	uint32_t pc = 0;
 	size_t sp = at;
 	unsigned long steps = 0;
+	int cap = 0;
 	st->n = 0;
 	for (;;) {
 		if (++steps > GO_MATCH_LIMIT) return -1;
 		const inst *in = &re->prog[pc];
 		int fail = 0;
 		switch (in->op) {
-		case I_MATCH: *e = sp; return 1;
+		case I_MATCH: *e = sp; return cap ? 2 : 1;
+		case I_CAP: cap = 1; pc++; break;
 		case I_SET:
 			if (sp < len && bs_has(&re->sets[in->a], s[sp])) { sp++; pc++; }
 			else fail = 1;
@@ -812,7 +818,7 @@ static int attempt(const go_regex *re, const uint8_t *s, size_t len, size_t at, 
 			break;
 		case I_JMP: pc = in->a; break;
 		case I_SPLIT:
-			if (bt_push(st, in->b, BT_PLAIN, sp, 0) < 0) return -1;
+			if (bt_push(st, in->b, BT_PLAIN, sp, 0, cap) < 0) return -1;
 			pc = in->a;
 			break;
 		case I_REP: {
@@ -823,13 +829,13 @@ static int attempt(const go_regex *re, const uint8_t *s, size_t len, size_t at, 
 				while (k < mn && k < avail && bs_has(set, s[sp + k])) k++;
 				if (k < mn) { fail = 1; break; }
 				/* lo field carries how many more may be taken */
-				if (mx > mn && bt_push(st, pc, BT_REP_TAKEMORE, sp + k, mx == (size_t)-1 ? (size_t)-1 : mx - mn) < 0) return -1;
+				if (mx > mn && bt_push(st, pc, BT_REP_TAKEMORE, sp + k, mx == (size_t)-1 ? (size_t)-1 : mx - mn, cap) < 0) return -1;
 				sp += k; pc++;
 			} else {
 				size_t lim = mx < avail ? mx : avail;
 				while (k < lim && bs_has(set, s[sp + k])) k++;
 				if (k < mn) { fail = 1; break; }
-				if (in->d == Q_GREEDY && k > mn && bt_push(st, pc + 1, BT_REP_GIVEBACK, sp + k, sp + mn) < 0) return -1;
+				if (in->d == Q_GREEDY && k > mn && bt_push(st, pc + 1, BT_REP_GIVEBACK, sp + k, sp + mn, cap) < 0) return -1;
 				sp += k; pc++;
 			}
 			break;
@@ -840,6 +846,7 @@ static int attempt(const go_regex *re, const uint8_t *s, size_t len, size_t at, 
 		for (;;) {
 			if (st->n == 0) return 0;
 			bt *t = &st->v[st->n - 1];
+			cap = t->cap; /* groups closed after this choice point are undone */
 			if (t->kind == BT_PLAIN) { pc = t->pc; sp = t->sp; st->n--; break; }
 			if (t->kind == BT_REP_GIVEBACK) {
 				/* t->sp: current end of the greedy run; give back one item */
@@ -884,7 +891,7 @@ int go_exec(const go_regex *re, const uint8_t *subject, size_t length, size_t *s
 		size_t end = 0;
 		rc = attempt(re, subject, length, at, &end, &st);
 		if (rc < 0) break;
-		if (rc == 1) { *s = at; *e = end; break; }
+		if (rc >= 1) { *s = at; *e = end; break; }
 	}
 	free(st.v);
 	return rc;
@@ -927,7 +934,7 @@ int go_scan_window(const go_regex *re, const uint8_t *w, size_t clen, uint64_t b
 		size_t s = 0, e = 0;
 		int rc = go_exec(re, w + start, clen - start, &s, &e); /* grab.cc:178 */
 		if (rc < 0) return -1;                                /* oracle's own match limit: report, do not guess */
-		if (rc == 1 && strict_q2 && re->ncapture > 0) rc = 0; /* ovecsize 3 too small => rc 0 */
+		if (rc == 2) rc = strict_q2 ? 0 : 1;                  /* a group was set: ovecsize 3 too small => pcre_exec returns 0 (Q2) */
 		if (rc <= 0) break;                                   /* grab.cc:179 */
 		if (push_match(out, base_off + start + s, (uint32_t)(e - s), unit) < 0) return -1;
 		size_t a = 0;
@@ -959,7 +966,7 @@ int go_grab_buffer(const go_regex *re, const go_opts *o, const uint8_t *file, si
 			size_t s = 0, e = 0;
 			int rc = go_exec(re, w + start, clen - start, &s, &e);
 			if (rc < 0) return -1;
-			if (rc == 1 && o->strict_q2 && re->ncapture > 0) rc = 0;
+			if (rc == 2) rc = o->strict_q2 ? 0 : 1;
 			if (rc <= 0) break;
 			if (o->path_prefix) { fputs(o->path_prefix, out); fputc(':', out); } /* :182-183 */
 			if (o->print_offset)                              /* :185-186 */

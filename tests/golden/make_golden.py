@@ -107,6 +107,20 @@ KAT = [
     ("line_two_on_line", b"foo bar foo\nfoo\n", [], "foo"),
     ("line_two_on_line_O", b"foo bar foo\nfoo\n", ["-O"], "foo"),
     ("tail_nl", b"abc\nfoo", ["-O", "-l"], "foo"),
+    # Q2 in full: pcre_exec (ovecsize 3) returns 0 only for a match in which a capturing group TOOK PART -- the loop prints
+    # until the first such match and leaves the window there
+    ("q2_alt_mixed", b"foo bar foo\nfoo\n", ["-O", "-l"], "foo|(bar)"),
+    ("q2_alt_mixed_lines", b"foo x\nfoo bar foo\nfoo\n", [], "foo|(bar)"),
+    ("q2_opt_group", b"foo xfoo foo\n", ["-O", "-l"], "(x)?foo"),
+    ("q2_opt_group_lines", b"foo\nzfoo\nxfoo\nfoo\n", [], "(x)?foo"),
+    ("q2_group_in_rep", b"bc abc bc\n", ["-O", "-l"], "(?:(a)|b)+c"),
+    ("q2_group_in_rep2", b"b ab b\n", ["-O", "-l"], "(?:(a)|b)+c"),
+    ("q2_backtracked_group", b"ab ab aab ab\n", ["-O", "-l"], "(a)?ab"),
+    ("q2_star_group", b"b b ab b\n", ["-O", "-l"], "(a)*b"),
+    ("q2_always", b"bc abc bc\n", ["-O", "-l"], "(a|b)"),
+    ("q2_nested_noncap", b"xy xzy xy\n", ["-O", "-l"], "x(?:(z)|)y"),
+    ("q2_single", b"foo bar foo\n", ["-s", "-O", "-l"], "foo|(bar)"),
+    ("q2_first_is_group", b"bar foo foo\n", ["-O", "-l"], "foo|(bar)"),
     ("bigalt", b"the quick brown fox jumps over the lazy dog\n" * 3, ["-O", "-l"],
      "fox|dog|the|quick|lazy|over|jumps|brown"),
 ]

@@ -174,7 +174,7 @@ int main(int argc, char **argv)
 		for (auto &c : b) c = (uint8_t)al[rnd() % na];
 		subjects.push_back(b);
 	}
-	int n_pat = 0, n_served = 0, n_vm = 0, n_cmp = 0, n_walk = 0, n_limit = 0, bad = 0;
+	int n_pat = 0, n_served = 0, n_vm = 0, n_cmp = 0, n_walk = 0, n_limit = 0, bad = 0, n_strict = 0;
 	while (std::getline(f, pat)) {
 		if (pat.empty()) continue;
 		n_pat++;
@@ -227,8 +227,39 @@ int main(int argc, char **argv)
 				go_matches_free(&w2);
 			}
 		}
+		// Q2 in full (STRICT_REF): patterns with capturing groups -- the first match in which a group took part ends the
+		// window; the device walk kernels against the oracle with strict_q2 on
+		if (p.captures > 0) {
+			Program ps;
+			std::string e2;
+			if (compile_pattern(pat.data(), pat.size(), GSCAN_STRICT_REF, ps, e2)) {
+				n_strict++;
+				for (auto &sb : subjects) {
+					const int modes[3] = {GO_MODE_ALL, GO_MODE_FIRST, GO_MODE_LINE};
+					const uint32_t dmodes[3] = {GSCAN_MODE_ALL, GSCAN_MODE_FIRST, GSCAN_MODE_LINE};
+					for (int m = 0; m < 3; m++) {
+						go_matches w2 = {0, 0, 0};
+						if (go_scan_window(re, sb.data(), sb.size(), 0, 0, modes[m], 1, &w2) != 0) { go_matches_free(&w2); continue; }
+						std::vector<M> g2;
+						if (ps.kind != ENGINE_NONE && walk(ps, sb.data(), sb.size(), dmodes[m], g2) != 0) { go_matches_free(&w2); n_limit++; continue; }
+						bool ok = g2.size() == w2.n;
+						for (size_t i = 0; ok && i < g2.size(); i++) ok = g2[i].pos == w2.v[i].start && g2[i].len == w2.v[i].len;
+						n_walk++;
+						if (!ok) {
+							bad++;
+							printf("STRICT WALK MISMATCH %s mode %d (engine %d vm %d) on \"", pat.c_str(), m, (int)ps.kind, (int)ps.use_vm);
+							for (uint8_t c : sb) printf(c == '\n' ? "\\n" : c == '\t' ? "\\t" : "%c", c);
+							printf("\": got %zu want %zu\n", g2.size(), w2.n);
+							if (bad > 20) { go_matches_free(&w2); go_free(re); return 1; }
+						}
+						go_matches_free(&w2);
+					}
+				}
+			}
+		}
 		go_free(re);
 	}
+	printf("strict (Q2) patterns %d; ", n_strict);
 	printf("patterns %d, served %d (%d through the VM), comparisons %d + %d through the walk kernels, limit skips %d, mismatches %d\n", n_pat, n_served, n_vm, n_cmp, n_walk, n_limit, bad);
 	if (bad == 0) printf("model ok\n");
 	return bad ? 1 : 0;

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), "libgscan.so does not export %s" % name
     assert declared == set(G._PROTOS), "python prototypes out of sync with include/gscan.h"
-    assert G.lib().gscan_abi_version() == 1
+    assert G.lib().gscan_abi_version() == 2
 
 
 def test_struct_layouts():
@@ -58,6 +58,13 @@ def test_engine_selection_and_filter():
     assert i["minlen"] == 18 and i["maxlen"] == 18 and i["filter_delta"] in (1, 2, 3, 4)
     i = G.Pattern("foo|bar|baz|quux").info
     assert i["engine"] == G.ENGINE_FIXED and i["n_sequences"] == 3 and i["minlen"] == 3 and i["maxlen"] == 4  # bar|baz merge into ba[rz]
+    # three exact byte pairs (fo, ba, qu) => the balanced pair kernel, third bytes (o, [rz], u) in its inline stage 2
+    assert i["scan_kernel"] == G.KERNEL_BALANCED and i["n_filter_tests"] == 3 and i["filter_delta"] == 1
+    assert G.Pattern("foobardoesexist", literal=True).info["scan_kernel"] == G.KERNEL_PAIR
+    assert G.Pattern("[A-Za-z0-9_]{16,}").info["scan_kernel"] == G.KERNEL_RUN
+    assert G.Pattern("(?i)linus|torvalds").info["scan_kernel"] in (G.KERNEL_TRIPLE, G.KERNEL_PAIR)
+    import corpus
+    assert G.Pattern(corpus.literals100()).info["scan_kernel"] == G.KERNEL_HASH
     assert 1 <= i["n_filter_tests"] <= 4
     i = G.Pattern("[A-Za-z0-9_]{16,}").info
     assert i["engine"] == G.ENGINE_RUN and i["minlen"] == 16 and i["maxlen"] == -1

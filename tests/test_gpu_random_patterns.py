@@ -94,12 +94,10 @@ def test_random_pattern(ctx, inputs, pat):
         pytest.skip("engine rejects: " + str(e)[:60])
     assert p.minlen == o.minlen
     for mode in (G.MODE_ALL, G.MODE_FIRST, G.MODE_LINE):
-        try:
-            r = ctx.scan(p, inputs, mode=mode)
-        except G.GscanError as e:
-            # nested unbounded groups on long inputs can exhaust the device VM's backtrack stack: that is an
-            # explicit, specific error (PCRE has its match limits too), never a wrong answer
-            assert "stack or step limit" in str(e)
+        r = ctx.scan(p, inputs, mode=mode)
+        if ctx.stats()["vm_limit_hit"]:
+            # nested unbounded groups on long inputs can exhaust the device VM's backtrack stack: the unit stops there (as
+            # the reference's loop does on a pcre_exec error) and the call says so -- never a silently wrong answer
             pytest.skip("device VM limit reported")
         got = {}
         for fid, s, l in zip(r["file_id"].tolist(), r["start"].tolist(), r["match_len"].tolist()):

@@ -208,3 +208,33 @@ def test_host_pipeline_under_sanitizers(san, tmp_path):
             assert sorted(so.split(b"\n")) == sorted(plain.split(b"\n"))
         else:
             assert so == plain
+
+
+def test_host_many_tiny_files_stay_below_the_mapping_limit(tmp_path):
+    """80 000 files of 14 bytes: batches are cut by windows as well as by bytes, so the live mappings never reach
+    vm.max_map_count (65530) -- every file is searched, nothing aborts (the reference maps one window at a time)."""
+    n = 80000
+    d = tmp_path / "tiny"
+    d.mkdir()
+    for k in range(0, n, 1000):
+        sub = d / ("s%03d" % (k // 1000))
+        sub.mkdir()
+        for i in range(k, k + 1000):
+            (sub / ("f%05d" % i)).write_bytes(b"xx foo %05d\n\n" % i if i % 7 == 0 else b"nothing here.\n")
+    rc, so, se = run(["-r", "-O", "-l", "foo", "tiny"], cwd=str(tmp_path))
+    assert rc == 0 and se == b"", se[-500:]
+    lines = so.split(b"\n")
+    assert len([x for x in lines if x]) == len(range(0, n, 7))
+    assert all(x.endswith(b":Match at offset 3") for x in lines if x)
+
+
+def test_host_good_path_then_missing_path(tmp_path):
+    """`grab foo a nope`: the matches of `a` are printed before the stat error of `nope` ends the run (rc 255)."""
+    (tmp_path / "a").write_bytes(b"xx foo yy\nzz foo\n\n")
+    rc, so, se = run(["-O", "-l", "foo", "a", "nope"], cwd=str(tmp_path))
+    assert rc == 255
+    assert so == b"a:Match at offset 3\na:Match at offset 13\n"
+    assert b"FileGrep::find::stat" in se
+    if os.path.exists(REF):
+        rcr, ref_out, ref_err = run(["-O", "-l", "foo", "a", "nope"], cwd=str(tmp_path), binary=REF)
+        assert (rcr, ref_out) == (rc, so) and ref_err == se
