@@ -401,7 +401,7 @@ static int stage_pageable(gscan_ctx *ctx, const std::vector<StageJob> &jobs)
 {
 	size_t total = 0;
 	for (auto &j : jobs) total += j.len;
-	int want = 8;
+	int want = 12; // measured on the B200 box (tools/stage_sweep.py): 4 -> 33, 8 -> 35/49, 12 -> 38/50, 16 -> 38/49, 24 -> 32/39 GB/s (1 MiB / 64 MiB units)
 	if (const char *e = getenv("GSCAN_STAGE_THREADS")) want = atoi(e);
 	const int hw = (int)std::thread::hardware_concurrency();
 	if (hw > 0 && want > hw) want = hw;
@@ -760,6 +760,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		R.vm_code = ctx->vm_code;
 		R.vm_sets = ctx->vm_sets;
 		R.vm_runstart = pat->prog.vm_runstart ? 1u : 0u;
+		R.flat = (mode == GSCAN_MODE_ALL && !pat->prog.use_vm && (pat->prog.kind == ENGINE_RUN || pat->prog.disjoint)) ? 1u : 0u;
 		R.run_min = (uint32_t)pat->prog.run_min;
 		for (int i = 0; i < 8; i++) R.bitmap[i] = pat->prog.run_class.w[i];
 		R.total_cand = (uint32_t)total_cand;

@@ -253,11 +253,16 @@ __global__ void k_walk(const ResolveArgs R)
 		const uint64_t ulen = du.len;
 		const bool run = R.engine == GSCAN_ENGINE_RUN;
 		uint64_t start = 0;
-		if (!WRITE && run && R.mode == GSCAN_MODE_ALL) {
-			// runs never touch each other (a non-class byte separates them), so in ALL mode every candidate is a
-			// match and the loop guard (grab.cc:175) can only bite before the first search: count without measuring
-			// the runs -- their lengths are only needed by the write pass
+		if (!WRITE && R.flat) {
+			// ALL mode, no two matches can overlap: every candidate is a match as long as the loop guard start + minlen < ulen
+			// (grab.cc:175, Q1) holds.  Runs never touch each other (a non-class byte separates them), so for RUN it can only
+			// bite before the first search; for FIXED it can also drop the LAST candidate (the one that exactly fills what the
+			// previous match left).  Counted here in O(1); the write pass is k_write_flat, one thread per candidate.
 			n = (R.minlen < ulen) ? end - i : 0u;
+			if (!run && n >= 2u) {
+				const OutRec prev = R.ord[end - 2];
+				if (!((uint64_t)prev.pos + prev.len + R.minlen < ulen)) n--;
+			}
 		} else
 		for (;;) {
 			if (!(start + R.minlen < ulen)) break;                 // grab.cc:175 (strict '<': Q1)
@@ -292,6 +297,33 @@ __global__ void k_walk(const ResolveArgs R)
 		}
 	}
 	if (!WRITE) R.unit_out[u] = n;
+}
+
+// write pass of the flat case (ResolveArgs::flat): one thread per candidate
+__global__ void k_write_flat(const ResolveArgs R)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= R.total_cand) return;
+	const OutRec c = R.ord[i];
+	const DevUnit du = R.units[c.unit];
+	const uint64_t ulen = du.len;
+	const uint32_t first = R.unit_start[c.unit], idx = i - first;
+	if (!(R.minlen < ulen)) return;                                 // grab.cc:175 before the first search
+	uint32_t len = c.len;
+	if (R.engine == GSCAN_ENGINE_RUN) {                             // greedy: extend to the end of the run
+		const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
+		uint64_t e = (uint64_t)c.pos + R.run_min;
+		while (e < ulen && in_class(R, data[e])) e++;
+		len = (uint32_t)(e - c.pos);
+	} else if (idx >= 1u && i + 1u == R.unit_start[c.unit + 1]) {    // the unit's last candidate: the guard after its predecessor (Q1)
+		const OutRec prev = R.ord[i - 1];
+		if (!((uint64_t)prev.pos + prev.len + R.minlen < ulen)) return;
+	}
+	FinalRec r;
+	r.start = du.base_off + c.pos;
+	r.file_id = du.file_id;
+	r.len = len;
+	R.out[R.unit_out[c.unit] + idx] = r;
 }
 
 // general patterns: every match starts at a candidate (a leading-byte prefix hit).  The count pass runs the VM
@@ -428,6 +460,11 @@ cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t
 
 cudaError_t launch_resolve_write(const ResolveArgs &R, cudaStream_t st, uint32_t *launches)
 {
+	if (R.flat) {
+		k_write_flat<<<(R.total_cand + 255) / 256, 256, 0, st>>>(R);
+		if (launches) *launches = 1;
+		return cudaGetLastError();
+	}
 	if (R.engine == GSCAN_ENGINE_VM) k_walk_vm<true><<<(R.n_units + 63) / 64, 64, 0, st>>>(R);
 	else k_walk<true><<<(R.n_units + 127) / 128, 128, 0, st>>>(R);
 	if (launches) *launches = 1;

@@ -753,10 +753,67 @@ struct RunEngine {
 		return Emitter::emit_at(dst, cand, off + c0, [](uint32_t) -> uint32_t { return 0u; }, lane);
 	}
 
+	// rare: several candidates in one lane's 64 bytes -- general prefix sum, lane-major, low word first == position order
+	static __device__ __noinline__ uint32_t emit_block_multi(Cand *dst, uint32_t lane, uint32_t clo, uint32_t chi, uint32_t pos0)
+	{
+		const uint32_t cnt = __popc(clo) + __popc(chi);
+		uint32_t incl = cnt;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+			if ((int)lane >= d) incl += v;
+		}
+		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+		uint32_t idx = incl - cnt;
+		for (uint32_t t = clo; t; t &= t - 1) { Cand c; c.pos = pos0 + (__ffs(t) - 1); c.len = 0; dst[idx++] = c; }
+		for (uint32_t t = chi; t; t &= t - 1) { Cand c; c.pos = pos0 + 32 + (__ffs(t) - 1); c.len = 0; dst[idx++] = c; }
+		return total;
+	}
+	// long minimum: confirm bytes 17..n-1 of every candidate (global memory: they may lie in another warp's slice)
+	static __device__ __noinline__ uint32_t confirm_long(const RunParams &P, const uint8_t *gtile, uint32_t off, uint32_t ulen, uint32_t cand, uint32_t c0)
+	{
+		uint32_t keep = 0;
+		for (uint32_t t = cand; t; t &= t - 1) {
+			const uint32_t b = __ffs(t) - 1, p = c0 + b;
+			bool ok = (unsigned long long)off + p + P.run_min <= ulen;
+			for (uint32_t i = 17; ok && i < P.run_min; i++) ok = in_class(P, gtile[p + i]);
+			if (ok) keep |= 1u << b;
+		}
+		return keep;
+	}
+	// candidates of one 2 KiB block (64 bytes per lane: clo = bytes 0..31, chi = bytes 32..63) -> private list, in
+	// position order; returns how many.  Common case (no lane has two): rank by ballot.
+	static __device__ __forceinline__ uint32_t emit_block(const RunParams &P, const uint8_t *gtile, uint32_t off, uint32_t ulen, Cand *dst,
+	                                                   uint32_t lane, uint32_t clo, uint32_t chi, uint32_t c0)
+	{
+		if (P.run_min > 17u) {
+			clo = confirm_long(P, gtile, off, ulen, clo, c0);
+			chi = confirm_long(P, gtile, off, ulen, chi, c0 + 32);
+		}
+		const uint32_t any = clo | chi;
+		const bool one = (clo & (clo - 1)) == 0 && (chi & (chi - 1)) == 0 && (clo == 0 || chi == 0);
+		if (__all_sync(0xffffffffu, one)) {
+			const uint32_t has = __ballot_sync(0xffffffffu, any != 0);
+			if (any) {
+				Cand c;
+				c.pos = off + c0 + (clo ? __ffs(clo) - 1 : 32 + __ffs(chi) - 1);
+				c.len = 0;
+				dst[__popc(has & ((1u << lane) - 1u))] = c;
+			}
+			return __popc(has);
+		}
+		return emit_block_multi(dst, lane, clo, chi, off + c0);
+	}
+
+	// One slice.  Full slices inside their unit run 2 KiB per warp step: every lane classifies 64 CONTIGUOUS bytes (four
+	// 16-byte loads, the order rotated per lane pair so that a quarter warp still covers all 32 banks) into a 64-bit class
+	// mask -- the cross-lane stitching (two shuffles), the "n ones start here" shifts and the vote are then paid once per
+	// 64 bytes instead of once per 16.
 	template <class G>
 	static __device__ __forceinline__ void run(const RunParams &P, const Slice &S, Emitter &E, uint32_t lane)
 	{
-		constexpr int kRows = G::kSlice / 512;
+		constexpr int kRows = G::kSlice / 512, kBlocks = G::kSlice / 2048;
+		static_assert(kBlocks >= 1 && kBlocks * 2048 == G::kSlice, "RUN scans blocks of 2 KiB");
 		if (S.niter == 0) return;
 		// is the byte just before the slice in the class?  (the unit's first byte has no predecessor)
 		uint32_t prevbit = 0;
@@ -767,46 +824,63 @@ struct RunEngine {
 			// the look-ahead bytes, everything in registers ----
 			const unsigned long long after = (unsigned long long)S.ulen - S.off - send; // bytes of the unit behind the slice
 			const uint32_t la_valid = after >= 16 ? 0xffffu : ((1u << (uint32_t)after) - 1u);
-			uint32_t cm[kRows + 1];
-			if (NHI == 0) {
-				// speculate that the slice is plain ASCII (cheaper classification); if a byte >= 0x80 shows up the masks are
-				// wrong (carries between bytes) and the slice goes through the general out-of-line path instead
-				uint32_t seen = 0;
+			const uint32_t rot = (lane >> 1) & 3u; // this lane loads its pieces in the order rot, rot + 1, ... (mod 4)
+			const uint32_t sel_lo = (uint32_t)(0x5432765410763210ull >> (16 * rot)) & 0xffffu; // undo the rotation: byte selectors
+			const uint32_t sel_hi = (uint32_t)(0x1076321054327654ull >> (16 * rot)) & 0xffffu; // for the low / high mask word
+			uint32_t mlo[kBlocks], mhi[kBlocks], seen = 0;
 #pragma unroll
-				for (int r = 0; r < kRows; r++) cm[r] = mask16_ascii(P, S.tile + S.begin + r * 512 + lane * 16, seen);
+			for (int b = 0; b < kBlocks; b++) {
+				const uint8_t *base = S.tile + S.begin + b * 2048 + lane * 64;
+				uint32_t m[4];
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					const uint8_t *pp = base + 16u * ((rot + (uint32_t)k) & 3u);
+					m[k] = NHI == 0 ? mask16_ascii(P, pp, seen) : mask16_inner(P, pp);
+				}
+				const uint32_t a = __byte_perm(m[0], m[1], 0x5410), c = __byte_perm(m[2], m[3], 0x5410);
+				mlo[b] = __byte_perm(a, c, sel_lo);
+				mhi[b] = __byte_perm(a, c, sel_hi);
+			}
+			uint32_t la; // class mask of the 16 bytes after the slice: correct in lanes 0..3, consumed from lane 0 (by lane 31)
+			{
 				const uint32_t x = la_valid ? *reinterpret_cast<const uint32_t *>(S.tile + send + (lane & 3) * 4) : 0u; // no copy behind the unit's end
 				seen |= x;
-				uint32_t nib = (pack_top_nibble(class_flags_ascii(P, x)) >> 28) << ((lane & 3) * 4);
+				uint32_t nib = (pack_top_nibble(NHI == 0 ? class_flags_ascii(P, x) : class_flags(P, x)) >> 28) << ((lane & 3) * 4);
 				nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
 				nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
-				cm[kRows] = nib & la_valid; // correct in lanes 0..3; only lane 0's copy is consumed (by lane 31)
-				if (__any_sync(0xffffffffu, (seen & kHigh) != 0)) {
-					E.n += run_tail(P, S.tile, S.gtile, S.off, S.ulen, S.begin, S.niter, prevbit, E.scratch + E.n, lane);
-					return;
-				}
-			} else {
-#pragma unroll
-				for (int r = 0; r < kRows; r++) cm[r] = mask16_inner(P, S.tile + S.begin + r * 512 + lane * 16);
-				// the 16 bytes after the slice: lanes 0..3 classify one word each of the look-ahead copy
-				const uint32_t x = la_valid ? *reinterpret_cast<const uint32_t *>(S.tile + send + (lane & 3) * 4) : 0u;
-				uint32_t nib = (pack_top_nibble(class_flags(P, x)) >> 28) << ((lane & 3) * 4);
-				nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
-				nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
-				cm[kRows] = nib & la_valid; // correct in lanes 0..3; only lane 0's copy is consumed (by lane 31)
+				la = nib & la_valid;
+			}
+			if (NHI == 0 && __any_sync(0xffffffffu, (seen & kHigh) != 0)) {
+				// a byte >= 0x80: the ASCII classification is void (carries between bytes) -- general out-of-line path
+				E.n += run_tail(P, S.tile, S.gtile, S.off, S.ulen, S.begin, S.niter, prevbit, E.scratch + E.n, lane);
+				return;
 			}
 			const uint32_t nxt_lane = (lane + 1) & 31, prv_lane = (lane + 31) & 31;
 #pragma unroll
-			for (int r = 0; r < kRows; r++) {
-				// one shuffle brings the next lane's mask of this row and (for lane 31) lane 0's mask of the next row
-				const uint32_t v = __shfl_sync(0xffffffffu, cm[r] | (cm[r + 1] << 16), nxt_lane);
-				const uint32_t nx = lane == 31 ? v >> 16 : v & 0xffffu;
-				// one shuffle brings the previous lane's last bit and (for lane 0) lane 31's last bit of the previous row
-				const uint32_t below = r ? cm[r - 1] : prevbit << 15;
-				const uint32_t u = __shfl_sync(0xffffffffu, cm[r] | (below << 16), prv_lane);
-				const uint32_t pv = lane == 0 ? u >> 31 : (u >> 15) & 1u;
-				const uint32_t starts = cm[r] & ~((cm[r] << 1) | pv);
-				const uint32_t cand = starts & runs(P, cm[r] | (nx << 16)) & 0xffffu;
-				if (__any_sync(0xffffffffu, cand != 0)) E.n += emit_row(P, S.gtile, S.off, S.ulen, E.scratch + E.n, lane, cand, S.begin + r * 512 + lane * 16);
+			for (int b = 0; b < kBlocks; b++) {
+				// one shuffle brings the next lane's first 16 class bits and (for lane 31) lane 0's of the next block / the look-ahead
+				const uint32_t follow = b + 1 < kBlocks ? (mlo[b + 1 < kBlocks ? b + 1 : b] & 0xffffu) : la;
+				const uint32_t v = __shfl_sync(0xffffffffu, (mlo[b] & 0xffffu) | (follow << 16), nxt_lane);
+				uint32_t ext = lane == 31 ? v >> 16 : v & 0xffffu;
+				// one shuffle brings the previous lane's last bit and (for lane 0) lane 31's last bit of the previous block
+				const uint32_t below = b ? mhi[b ? b - 1 : 0] >> 31 : prevbit;
+				const uint32_t u = __shfl_sync(0xffffffffu, (mhi[b] >> 31) | (below << 1), prv_lane);
+				const uint32_t pv = lane == 0 ? u >> 1 : u & 1u;
+				// bits where at least min(run_min, 17) ones start, on the 80-bit window (own 64 + 16 of the follower)
+				uint32_t rlo = mlo[b], rhi = mhi[b];
+#pragma unroll
+				for (int i = 0; i < 5; i++) {
+					const uint32_t sh = P.sh[i];
+					if (sh == 0) break; // the schedule is front-packed: nothing after the first zero
+					rlo &= __funnelshift_r(rlo, rhi, sh);
+					rhi &= __funnelshift_r(rhi, ext, sh);
+					ext &= ext >> sh;
+				}
+				// run starts: class bit with the previous bit clear
+				const uint32_t clo = rlo & mlo[b] & ~((mlo[b] << 1) | pv);
+				const uint32_t chi = rhi & mhi[b] & ~__funnelshift_l(mlo[b], mhi[b], 1);
+				if (__any_sync(0xffffffffu, (clo | chi) != 0))
+					E.n += emit_block(P, S.gtile, S.off, S.ulen, E.scratch + E.n, lane, clo, chi, S.begin + b * 2048 + lane * 64);
 			}
 			return;
 		}

@@ -119,6 +119,7 @@ static void candidates(const Program &p, const uint8_t *s, size_t len, std::vect
 	}
 }
 
+static int g_flat_checks = 0;
 // count pass, slot scan (one unit: slot 0), write pass -- the device code of resolve_kernels.cu, on the host.
 // 0 ok, -1 VM limit
 static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, std::vector<M> &out)
@@ -156,6 +157,25 @@ static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, s
 	if (p.use_vm) k_walk_vm<true>(R); else k_walk<true>(R);
 	if (totals[2]) return -1;
 	for (uint32_t i = 0; i < n; i++) out.push_back(M{fin[i].start, fin[i].len});
+	// the flat write pass (one thread per candidate) wherever the engine would choose it: same records
+	if (mode == GSCAN_MODE_ALL && !p.use_vm && (p.kind == ENGINE_RUN || p.disjoint)) {
+		R.flat = 1;
+		R.total_cand = (uint32_t)ord.size();
+		R.out = nullptr;
+		unit_out[0] = 0;
+		model_threadIdx.x = 0;
+		k_walk<false>(R);
+		const uint32_t nf = unit_out[0];
+		std::vector<FinalRec> ff(nf + 1);
+		unit_out[0] = 0;
+		R.out = ff.data();
+		for (uint32_t i = 0; i < ord.size(); i++) { model_threadIdx.x = i; k_write_flat(R); }
+		model_threadIdx.x = 0;
+		bool same = nf == n;
+		for (uint32_t i = 0; same && i < n; i++) same = ff[i].start == fin[i].start && ff[i].len == fin[i].len;
+		if (!same) return -3;
+		g_flat_checks++;
+	}
 	return 0;
 }
 
@@ -213,7 +233,9 @@ int main(int argc, char **argv)
 				go_matches w2 = {0, 0, 0};
 				if (go_scan_window(re, sb.data(), sb.size(), 0, 0, modes[m], 0, &w2) != 0) { go_matches_free(&w2); continue; }
 				std::vector<M> g2;
-				if (walk(p, sb.data(), sb.size(), dmodes[m], g2) != 0) { go_matches_free(&w2); n_limit++; continue; }
+				const int wrc = walk(p, sb.data(), sb.size(), dmodes[m], g2);
+				if (wrc == -3) { printf("FLAT WALK MISMATCH %s\n", pat.c_str()); bad++; go_matches_free(&w2); continue; }
+				if (wrc != 0) { go_matches_free(&w2); n_limit++; continue; }
 				bool ok = g2.size() == w2.n;
 				for (size_t i = 0; ok && i < g2.size(); i++) ok = g2[i].pos == w2.v[i].start && g2[i].len == w2.v[i].len;
 				n_walk++;
@@ -259,7 +281,7 @@ int main(int argc, char **argv)
 		}
 		go_free(re);
 	}
-	printf("strict (Q2) patterns %d; ", n_strict);
+	printf("flat write checks %d; strict (Q2) patterns %d; ", g_flat_checks, n_strict);
 	printf("patterns %d, served %d (%d through the VM), comparisons %d + %d through the walk kernels, limit skips %d, mismatches %d\n", n_pat, n_served, n_vm, n_cmp, n_walk, n_limit, bad);
 	if (bad == 0) printf("model ok\n");
 	return bad ? 1 : 0;
