@@ -64,6 +64,8 @@ _PROTOS = {
     "gscan_scan_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32,
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
     "gscan_free_matches": (None, [ctypes.c_void_p, ctypes.c_void_p]),
+    "gscan_scan_batch_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32]),
+    "gscan_scan_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
     "gscan_batch_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "gscan_batch_scan": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32,
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
@@ -224,6 +226,24 @@ class Context:
         self._check(lib().gscan_scan_batch(self._h, pattern._h, units.ctypes.data, len(units), mode,
                                            ctypes.byref(out), ctypes.byref(n)))
         return self._take(out, n, copy)
+
+    def scan_units_async(self, pattern, units, mode=MODE_ALL):
+        """gscan_scan_batch_async: returns at once; `wait()` of the returned handle delivers the records.  The unit table and
+        the buffers are kept alive by the handle."""
+        units = np.ascontiguousarray(units, dtype=UNIT_DTYPE)
+        self._check(lib().gscan_scan_batch_async(self._h, pattern._h, units.ctypes.data, len(units), mode))
+        ctx = self
+
+        class Job:
+            def __init__(self):
+                self.keep = (units, pattern)
+
+            def wait(self):
+                out, n = ctypes.c_void_p(), ctypes.c_size_t()
+                ctx._check(lib().gscan_scan_wait(ctx._h, ctypes.byref(out), ctypes.byref(n)))
+                self.keep = None
+                return ctx._take(out, n)
+        return Job()
 
     def scan(self, pattern, bufs, mode=MODE_ALL, file_ids=None, base_offs=None):
         units, keep = self.units_from_buffers(bufs, file_ids, base_offs)

@@ -119,6 +119,12 @@ struct gscan_ctx {
 	DevBuf<uint8_t> pool_arena;
 	DevBuf<TileDesc> pool_tiles;
 	DevBuf<DevUnit> pool_units;
+	// the job of gscan_scan_batch_async (one in flight)
+	std::thread job;
+	bool job_active = false;
+	int job_rc = 0;
+	gscan_match *job_out = nullptr;
+	size_t job_n = 0;
 };
 
 static thread_local std::string g_last_error;
@@ -159,7 +165,7 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 	memset(&p->fixed, 0, sizeof(p->fixed));
 	memset(&p->run, 0, sizeof(p->run));
 	memset(&p->hash, 0, sizeof(p->hash));
-	if (pr.kind == ENGINE_FIXED) {
+	if (pr.kind == ENGINE_FIXED && !pr.vm_dense) {
 		FixedParams &F = p->fixed;
 		F.one = 1;
 		F.ntests = (uint32_t)pr.tests.size();
@@ -301,7 +307,7 @@ extern "C" int gscan_pattern_get_info(const gscan_pattern *p, gscan_pattern_info
 	o->filter_anchor = p->prog.anchor;
 	o->filter_delta = p->prog.delta;
 	o->reserved = 0;
-	if (p->prog.kind == ENGINE_NONE) o->scan_kernel = GSCAN_KERNEL_NONE;
+	if (p->prog.kind == ENGINE_NONE || (p->prog.use_vm && p->prog.vm_dense)) o->scan_kernel = GSCAN_KERNEL_NONE;
 	else if (p->prog.kind == ENGINE_RUN) o->scan_kernel = GSCAN_KERNEL_RUN;
 	else if (p->prog.use_hash) o->scan_kernel = GSCAN_KERNEL_HASH;
 	else if (p->fixed.b_engine) o->scan_kernel = GSCAN_KERNEL_BALANCED;
@@ -348,6 +354,7 @@ extern "C" gscan_ctx *gscan_open(int device)
 extern "C" void gscan_close(gscan_ctx *c)
 {
 	if (!c) return;
+	if (c->job_active) { c->job.join(); c->job_active = false; }
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->segs.release(); c->cand.release(); c->scratch.release(); c->ord.release(); c->out.release();
@@ -602,7 +609,7 @@ static int ensure_segs(gscan_ctx *ctx, uint32_t n_segs)
 static int ensure_pattern(gscan_ctx *ctx, const gscan_pattern *pat)
 {
 	if (ctx->pat_id == pat->prog.id) return 0;
-	if (pat->prog.kind == ENGINE_FIXED) {
+	if (pat->prog.kind == ENGINE_FIXED && !pat->prog.vm_dense) {
 		const size_t b_len = (pat->seq_len.size() * 2 + 15) & ~(size_t)15;
 		const size_t b_off = pat->seq_off.size() * 4, b_pos = pat->seq_pos.size() * 4, b_bm = pat->cls_bm.size() * 4;
 		const size_t total = b_len + b_off + b_pos + b_bm + 64;
@@ -705,7 +712,14 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 
 	unsigned long long *h_cursor = reinterpret_cast<unsigned long long *>(ctx->readback.p);
 	unsigned long long total_cand = 0;
-	for (int attempt = 0;; attempt++) {
+	// general patterns without a candidate filter: no scan kernel -- the VM walk tries the positions itself
+	const bool dense = pat->prog.use_vm && pat->prog.vm_dense;
+	if (dense) {
+		CK(ctx, launch_fill_u32(reinterpret_cast<uint32_t *>(ctx->cursor.p), 8, 0u, ctx->stream));
+		CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+		S.total_launches += 1;
+	}
+	for (int attempt = 0; !dense; attempt++) {
 		A.cand = ctx->cand.p;
 		A.cand_cap = (uint32_t)std::min<size_t>(ctx->cand.cap, 0xffffffffu);
 		CK(ctx, launch_fill_u32(reinterpret_cast<uint32_t *>(ctx->cursor.p), 8, 0u, ctx->stream));
@@ -733,7 +747,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	size_t n = 0;
 	gscan_match *m = nullptr;
 	static_assert(sizeof(FinalRec) == sizeof(gscan_match), "device records are gscan_match");
-	if (total_cand) {
+	if (total_cand || dense) {
 		const uint32_t nb_seg = (n_segs + 2047) / 2048, nb_u = (uint32_t)((b->n_units + 2047) / 2048);
 		CK(ctx, ctx->ord.ensure((size_t)total_cand));
 		CK(ctx, ctx->unit_start.ensure((size_t)b->n_units + 1));
@@ -762,7 +776,8 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		R.vm_runstart = pat->prog.vm_runstart ? 1u : 0u;
 		R.flat = (mode == GSCAN_MODE_ALL && !pat->prog.use_vm && (pat->prog.kind == ENGINE_RUN || pat->prog.disjoint)) ? 1u : 0u;
 		R.run_min = (uint32_t)pat->prog.run_min;
-		for (int i = 0; i < 8; i++) R.bitmap[i] = pat->prog.run_class.w[i];
+		for (int i = 0; i < 8; i++) R.bitmap[i] = dense ? pat->prog.first_set.w[i] : pat->prog.run_class.w[i];
+		R.vm_dense = dense ? 1u : 0u;
 		R.total_cand = (uint32_t)total_cand;
 		uint32_t nl = 0;
 		CK(ctx, launch_resolve_count(R, ctx->stream, &nl));
@@ -773,7 +788,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		// a unit on which the backtracking VM ran out of stack or steps stops there, like the reference's loop when
 		// pcre_exec reports a match-limit error (rc < 0 => break, grab.cc:179, quirk Q5); the other units are unaffected
 		S.vm_limit_hit = h_tot[2] ? 1u : 0u;
-		if (h_tot[0] != (uint32_t)total_cand) return fail(ctx, "gscan_batch_scan: internal: segment counts disagree with the cursor");
+		if (!dense && h_tot[0] != (uint32_t)total_cand) return fail(ctx, "gscan_batch_scan: internal: segment counts disagree with the cursor");
 		n = h_tot[1];
 		if (n) {
 			// the records are written on the device in their final form and land in a pinned buffer that is lent
@@ -831,6 +846,35 @@ extern "C" int gscan_last_device_matches(gscan_ctx *ctx, const gscan_match **dpt
 	*n = (size_t)ctx->stats.n_matches;
 	*dptr = *n ? reinterpret_cast<const gscan_match *>(ctx->out.p) : nullptr;
 	return 0;
+}
+
+extern "C" int gscan_scan_batch_async(gscan_ctx *ctx, const gscan_pattern *pat, const gscan_unit *units, size_t n_units, uint32_t mode)
+{
+	if (!ctx || !pat) return fail(ctx, "gscan_scan_batch_async: null argument");
+	if (ctx->job_active) return fail(ctx, "gscan_scan_batch_async: a job is already in flight on this context (call gscan_scan_wait)");
+	ctx->job_rc = 0;
+	ctx->job_out = nullptr;
+	ctx->job_n = 0;
+	try {
+		ctx->job = std::thread([ctx, pat, units, n_units, mode] {
+			ctx->job_rc = gscan_scan_batch(ctx, pat, units, n_units, mode, &ctx->job_out, &ctx->job_n);
+		});
+	} catch (const std::exception &e) {
+		return fail(ctx, std::string("gscan_scan_batch_async: cannot start the worker: ") + e.what());
+	}
+	ctx->job_active = true;
+	return 0;
+}
+
+extern "C" int gscan_scan_wait(gscan_ctx *ctx, gscan_match **out, size_t *n_out)
+{
+	if (!ctx || !out || !n_out) return fail(ctx, "gscan_scan_wait: null argument");
+	if (!ctx->job_active) return fail(ctx, "gscan_scan_wait: no job in flight");
+	ctx->job.join(); // the worker's writes (results, error text, statistics) happen-before this returns
+	ctx->job_active = false;
+	*out = ctx->job_out;
+	*n_out = ctx->job_n;
+	return ctx->job_rc;
 }
 
 extern "C" void gscan_free_matches(gscan_ctx *ctx, gscan_match *m)

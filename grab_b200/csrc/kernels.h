@@ -52,12 +52,14 @@ struct ResolveArgs {
 	const uint32_t *vm_code; // general patterns: VM program (3 words per instruction) and byte classes (8 words each)
 	const uint32_t *vm_sets;
 	uint32_t vm_runstart; // candidates are run starts of `bitmap`: also try the search start itself when it lies inside a run
+	uint32_t vm_dense;    // general pattern without a candidate filter: no candidate list, the walk offers every position whose byte
+	                      // is in `bitmap` (the first-byte set) to the VM
 	uint32_t flat;        // ALL mode, RUN or a FIXED pattern whose matches can never overlap, no VM: every candidate of a unit is a
 	                      // match, except that the loop guard (grab.cc:175, Q1) can drop the unit's LAST one -- no replay needed, the
 	                      // write pass runs one thread per candidate (a 1 GiB window with 10^7 candidates resolves in microseconds)
 };
 // count pass: segment scan, gather, per-unit replay that counts, slot scan; totals[1] = number of matches
-cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t *launches);
+cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t *launches); // vm_dense: no segments, no gather
 // write pass: per-unit replay that writes R.out
 cudaError_t launch_resolve_write(const ResolveArgs &R, cudaStream_t st, uint32_t *launches);
 

@@ -1028,19 +1028,27 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 			}
 		}
 		std::vector<Pref> pf;
-		if (!prefixes(root.get(), 4, pf) || pf.empty()) { err = "pattern has too many distinct leading byte sequences for the candidate filter"; return false; }
-		seqs.clear();
-		for (auto &p : pf) {
-			if (p.seq.empty()) {
-				err = "pattern can start with any byte (leading optional item or bare assertion): the device engines need at "
-				      "least one fixed leading byte class";
-				return false;
-			}
-			seqs.push_back(p.seq);
-		}
 		out.use_vm = true;
 		out.vm_code = g.code;
 		for (auto &s : g.sets) for (int i = 0; i < 8; i++) out.vm_sets.push_back(s.w[i]);
+		bool dense = !prefixes(root.get(), 4, pf) || pf.empty();
+		seqs.clear();
+		out.first_set = ByteSet();
+		for (auto &p : pf) {
+			if (p.seq.empty()) dense = true; // a match can begin with any byte (leading optional item or bare assertion)
+			else { seqs.push_back(p.seq); out.first_set.unite(p.seq[0]); }
+		}
+		if (dense) {
+			// no candidate filter at all: the walk offers every position to the VM (what pcre_exec does without a
+			// first-code-unit optimisation)
+			out.first_set = ByteSet();
+			out.first_set.invert();
+			out.vm_dense = true;
+			out.kind = ENGINE_FIXED;
+			out.seqs.clear();
+			out.maxlen = -1;
+			return true;
+		}
 	}
 	// drop exact duplicates (a later identical alternative can never win) and never-matching ones
 	std::vector<Sequence> uniq;
@@ -1120,6 +1128,10 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 		out.anchor = 0;
 		out.delta = 0;
 		out.tests.clear();
+	} else if (best_tests.empty() && out.use_vm) {
+		out.vm_dense = true; // too many distinct leading sequences for either filter: the VM walk tries the positions itself
+		out.seqs.clear();
+		return true;
 	} else if (best_tests.empty()) {
 		err = "alternation needs more than 8 distinct byte-pair filter tests and its leading bytes cannot be hashed "
 		      "(an alternative shorter than 2 bytes, or more than 4096 distinct leading byte combinations)";
@@ -1159,9 +1171,13 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 	}
 
 	if (out.use_vm && best_p > 0.30) {
-		err = "the leading bytes of the pattern are too common for the candidate filter (every match attempt runs the "
-		      "backtracking VM on the device); anchor the pattern on a rarer leading byte";
-		return false;
+		// the leading bytes are so common that the candidate list would hold every other position: skip the scan kernel and
+		// let the VM walk try the positions itself (first-byte test in registers), as pcre_exec does
+		out.vm_dense = true;
+		out.seqs.clear();
+		out.tests.clear();
+		out.triples.clear();
+		return true;
 	}
 	// a 4 KiB slice has 8 rows of 512 bytes; once more than a few percent of the rows get flagged the slow path
 	// dominates, and three filter bytes (+2 ops per word) are cheaper than visiting it

@@ -98,6 +98,9 @@ struct Program {
 	// general patterns: seqs are the leading-byte prefixes (candidate filter), matches are decided by the VM
 	bool use_vm = false;
 	bool vm_runstart = false;      // candidates are the starts of runs of run_class (pattern begins with C{n,})
+	bool vm_dense = false;         // no useful candidate filter (the match can begin with (almost) any byte): the VM walk tries every
+	                               // position whose byte is in first_set itself, no scan kernel runs -- PCRE does the same on the CPU
+	ByteSet first_set;             // vm_dense: bytes a match can start with
 	std::vector<uint32_t> vm_code; // 3 words per instruction
 	std::vector<uint32_t> vm_sets; // 8 words per byte class
 

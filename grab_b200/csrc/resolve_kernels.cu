@@ -334,11 +334,41 @@ __global__ void __launch_bounds__(64, 4) k_walk_vm(const ResolveArgs R)
 {
 	const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
 	if (u >= R.n_units) return;
-	uint32_t i = R.unit_start[u];
-	const uint32_t end = R.unit_start[u + 1];
+	uint32_t i = R.vm_dense ? 0u : R.unit_start[u];
+	const uint32_t end = R.vm_dense ? 0u : R.unit_start[u + 1];
 	uint32_t n = 0;
 	FinalRec *o = WRITE ? R.out + R.unit_out[u] : nullptr;
-	if (i != end && R.vm_runstart) {
+	if (R.vm_dense) {
+		// no candidate list: PCRE's own search loop -- one anchored attempt per position whose byte can start a match, from
+		// the moving search start; both passes replay it
+		const DevUnit du = R.units[u];
+		const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
+		const uint64_t ulen = du.len;
+		uint64_t start = 0;
+		for (;;) {
+			if (!(start + R.minlen < ulen)) break;                                      // grab.cc:175
+			uint64_t pos = start;
+			uint32_t e = 0;
+			int rc = 0;
+			for (; pos + R.minlen <= ulen; pos++) {                                     // (an attempt with fewer bytes left cannot succeed)
+				if (!in_class(R, data[pos])) continue;
+				rc = vm_exec(R, data + start, (uint32_t)(ulen - start), (uint32_t)(pos - start), &e); // grab.cc:178
+				if (rc != 0) break;
+			}
+			if (rc < 0) { atomicOr(R.totals + 2, 1u); break; }
+			if (rc != 1) break;                                                         // no match, or Q2 (rc 2)
+			uint64_t me = start + e;
+			if (WRITE) { FinalRec r; r.start = du.base_off + pos; r.file_id = du.file_id; r.len = (uint32_t)(me - pos); o[n] = r; }
+			n++;
+			if (R.mode == GSCAN_MODE_FIRST) break;
+			if (R.mode == GSCAN_MODE_LINE) {
+				uint32_t a = 0;
+				while (me + a < ulen && a < 511 && data[me + a] != '\n') a++;
+				me += a;
+			}
+			start = me;                                                                 // grab.cc:209
+		}
+	} else if (i != end && R.vm_runstart) {
 		// candidates are run starts; a match may also begin at the search start when that lies inside a run, so the
 		// outcome cannot be recorded in the candidate array: both passes replay the loop (the VM runs twice)
 		const DevUnit du = R.units[u];
@@ -442,10 +472,12 @@ __global__ void k_u32_exclusive(uint32_t *v, uint32_t n, const uint32_t *blk)
 cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t *launches)
 {
 	uint32_t nl = 0;
-	const uint32_t nb_seg = (R.n_segs + kPerBlock - 1) / kPerBlock;
-	k_seg_sums<<<nb_seg, kScanBlock, 0, st>>>(R.segs, R.n_segs, R.tag, R.blk); nl++;
-	k_scan_blk<<<1, kScanBlock, 0, st>>>(R.blk, nb_seg, R.totals, R.unit_start + R.n_units); nl++;
-	k_gather<<<nb_seg, kScanBlock, 0, st>>>(R); nl++;
+	const uint32_t nb_seg = R.vm_dense ? 0u : (R.n_segs + kPerBlock - 1) / kPerBlock;
+	if (!R.vm_dense) {
+		k_seg_sums<<<nb_seg, kScanBlock, 0, st>>>(R.segs, R.n_segs, R.tag, R.blk); nl++;
+		k_scan_blk<<<1, kScanBlock, 0, st>>>(R.blk, nb_seg, R.totals, R.unit_start + R.n_units); nl++;
+		k_gather<<<nb_seg, kScanBlock, 0, st>>>(R); nl++;
+	}
 	if (R.engine == GSCAN_ENGINE_VM) k_walk_vm<false><<<(R.n_units + 63) / 64, 64, 0, st>>>(R);
 	else k_walk<false><<<(R.n_units + 127) / 128, 128, 0, st>>>(R);
 	nl++;

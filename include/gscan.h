@@ -135,6 +135,15 @@ int gscan_scan_batch(gscan_ctx *ctx, const gscan_pattern *pat, const gscan_unit 
                      uint32_t mode, gscan_match **out, size_t *n_out);
 void gscan_free_matches(gscan_ctx *ctx, gscan_match *m);
 
+/* Asynchronous variant (SURVEY.md 8(b) "explicit async variant with a completion call"): starts the same scan on a worker
+ * owned by the context and returns at once, so the caller can stat / open / mmap the next batch meanwhile (what the
+ * FileGrep mirror's lanes do).  `units` and the host buffers they point to must stay valid and unchanged until
+ * gscan_scan_wait() has returned; the context must not be used for anything else in between (one job in flight per
+ * context).  gscan_scan_wait() blocks until the job is done and delivers what gscan_scan_batch() would have:
+ * 0 / -1 (gscan_why), *out / *n_out as above.  Calling it without a job in flight returns -1. */
+int gscan_scan_batch_async(gscan_ctx *ctx, const gscan_pattern *pat, const gscan_unit *units, size_t n_units, uint32_t mode);
+int gscan_scan_wait(gscan_ctx *ctx, gscan_match **out, size_t *n_out);
+
 /* Resident variant: plan (and for host units upload) once, scan many times / many patterns. */
 int gscan_batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units, gscan_batch **out);
 int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_batch *batch, uint32_t mode,

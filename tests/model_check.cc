@@ -86,9 +86,10 @@ static int emulate(const Program &p, const uint8_t *s, size_t len, std::vector<M
 			if (found) break;
 		}
 		if (!found) break;
-		if (p.use_vm) { // the scan kernel must have offered this position to the VM walk
+		if (p.use_vm) { // the scan kernel (dense: the first-byte test of the walk) must have offered this position to the VM walk
 			bool offered = false;
-			if (p.vm_runstart) offered = p.run_class.has(s[pos]) && (pos == start || !p.run_class.has(s[pos - 1]));
+			if (p.vm_dense) offered = p.first_set.has(s[pos]);
+			else if (p.vm_runstart) offered = p.run_class.has(s[pos]) && (pos == start || !p.run_class.has(s[pos - 1]));
 			else for (auto &q : p.seqs) offered = offered || seq_at(q, s, len, pos);
 			if (!offered) { why = "candidate filter rejects a matching position"; return -2; }
 		}
@@ -125,7 +126,7 @@ static int g_flat_checks = 0;
 static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, std::vector<M> &out)
 {
 	std::vector<OutRec> ord;
-	candidates(p, s, len, ord);
+	if (!(p.use_vm && p.vm_dense)) candidates(p, s, len, ord);
 	DevUnit du;
 	memset(&du, 0, sizeof du);
 	du.ptr = (uint64_t)(uintptr_t)s;
@@ -143,10 +144,11 @@ static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, s
 	R.minlen = (uint32_t)p.minlen;
 	R.engine = p.use_vm ? (uint32_t)GSCAN_ENGINE_VM : (uint32_t)p.kind;
 	R.run_min = (uint32_t)p.run_min;
-	for (int i = 0; i < 8; i++) R.bitmap[i] = p.run_class.w[i];
+	for (int i = 0; i < 8; i++) R.bitmap[i] = (p.use_vm && p.vm_dense) ? p.first_set.w[i] : p.run_class.w[i];
 	R.vm_code = p.vm_code.data();
 	R.vm_sets = p.vm_sets.data();
 	R.vm_runstart = p.vm_runstart ? 1u : 0u;
+	R.vm_dense = (p.use_vm && p.vm_dense) ? 1u : 0u;
 	model_threadIdx.x = 0;
 	if (p.use_vm) k_walk_vm<false>(R); else k_walk<false>(R);
 	if (totals[2]) return -1;
@@ -194,7 +196,7 @@ int main(int argc, char **argv)
 		for (auto &c : b) c = (uint8_t)al[rnd() % na];
 		subjects.push_back(b);
 	}
-	int n_pat = 0, n_served = 0, n_vm = 0, n_cmp = 0, n_walk = 0, n_limit = 0, bad = 0, n_strict = 0;
+	int n_dense = 0, n_pat = 0, n_served = 0, n_vm = 0, n_cmp = 0, n_walk = 0, n_limit = 0, bad = 0, n_strict = 0;
 	while (std::getline(f, pat)) {
 		if (pat.empty()) continue;
 		n_pat++;
@@ -208,6 +210,7 @@ int main(int argc, char **argv)
 		if (go_minlen(re) != p.minlen) { printf("MISMATCH %s: minlen %d, oracle %d\n", pat.c_str(), p.minlen, go_minlen(re)); bad++; }
 		n_served++;
 		n_vm += p.use_vm;
+		n_dense += p.use_vm && p.vm_dense;
 		for (auto &sb : subjects) {
 			go_matches want = {0, 0, 0};
 			if (go_scan_window(re, sb.data(), sb.size(), 0, 0, GO_MODE_ALL, 0, &want) != 0) { go_matches_free(&want); n_limit++; continue; }
@@ -281,6 +284,7 @@ int main(int argc, char **argv)
 		}
 		go_free(re);
 	}
+	printf("dense VM patterns %d; ", n_dense);
 	printf("flat write checks %d; strict (Q2) patterns %d; ", g_flat_checks, n_strict);
 	printf("patterns %d, served %d (%d through the VM), comparisons %d + %d through the walk kernels, limit skips %d, mismatches %d\n", n_pat, n_served, n_vm, n_cmp, n_walk, n_limit, bad);
 	if (bad == 0) printf("model ok\n");

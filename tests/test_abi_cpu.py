@@ -82,6 +82,10 @@ def test_engine_selection_and_filter():
     assert i["engine"] == G.ENGINE_VM and i["minlen"] == 7 and i["maxlen"] == -1
     assert G.Pattern("^foo").info["engine"] == G.ENGINE_VM and G.Pattern(r"\bfoo\b").info["minlen"] == 3
     assert G.Pattern(r"\w+@\w+\.com").info["engine"] == G.ENGINE_VM  # begins with a class run: run starts are the candidates
+    # a match that can begin with (almost) any byte has no candidate filter: the VM walk tries the positions itself
+    for pat in (".*foo", r"(?:\w|-)+@\w+", r"x*ab|\s?c"):
+        i = G.Pattern(pat).info
+        assert i["engine"] == G.ENGINE_VM and i["scan_kernel"] == G.KERNEL_NONE, pat
     # many alternatives: hashed engine (negative n_filter_tests = -(table slots))
     import corpus
     i = G.Pattern(corpus.literals100()).info
@@ -90,7 +94,7 @@ def test_engine_selection_and_filter():
 
 @pytest.mark.parametrize("pat,frag", [
     ("x*", "empty string"), ("", "empty string"), ("a|", "empty string"),
-    (".*foo", "too common"), (r"(?:\w|-)+@\w+", "too common"), ("a*", "empty string"), ("(?:a*)+b", "not supported"),
+    ("a*", "empty string"), ("(?:a*)+b", "not supported"),
     ("(", "missing )"), ("[a-", "missing terminating ]"), (r"\1", "back references"), ("(?=a)b", "not supported"),
     ("a{3,2}", "quantifier"),
 ])
