@@ -111,3 +111,25 @@ def test_no_cpu_fallback():
     with pytest.raises(G.GscanError) as ei:
         G.Context(0)
     assert "no CPU fallback" in str(ei.value)
+
+
+def test_shipped_sass_uses_bulk_tma_and_mbarriers():
+    """After build(): every scan-kernel family moves its slices with the 1-D bulk TMA copy (SASS UBLKCP) completing on an
+    mbarrier (SYNCS.ARRIVE.TRANS64 / SYNCS.PHASECHK...TRYWAIT), compiled for sm_100a only, and -- this path has no dense
+    contraction -- without tensor-core instructions (tools/sass_check.py, profiles/r02_sass_check.txt)."""
+    import shutil
+    import sys
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not installed")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_check
+    arch, per = sass_check.sass_counts(G.LIB_PATH)
+    assert arch == {"sm_100a"}
+    fams = [f for f in per if f.startswith("scan_kernel")]
+    assert len(fams) >= 5
+    for f in fams:
+        c = per[f]
+        assert c["UBLKCP (cp.async.bulk, 1-D TMA)"] >= c["kernels"], f
+        assert c["SYNCS.ARRIVE.TRANS64 (mbarrier arrive / expect_tx)"] >= c["kernels"], f
+        assert c["SYNCS.PHASECHK.TRANS64.TRYWAIT (mbarrier try_wait)"] >= c["kernels"], f
+        assert c["tensor-core / TMEM instructions"] == 0, f
