@@ -129,7 +129,8 @@ struct ScanArgs {
 	uint32_t n_tiles;
 	Cand *cand;
 	uint32_t cand_cap;
-	unsigned long long *cursor; // [0]: candidates reserved so far
+	unsigned long long *cursor; // [0]: candidate slots reserved so far (in chunks: an upper bound of the candidates written)
+	uint32_t chunk;             // slots a warp reserves per atomicAdd
 	SegEntry *segs;
 	Cand *scratch;  // [gridDim.x * warps][slice bytes]: one private list per warp
 	uint32_t spt_shift;  // log2(slices per tile) = batch tile_shift - log2(Geom::kSlice)

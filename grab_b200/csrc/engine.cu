@@ -722,6 +722,8 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 	for (int attempt = 0; !dense; attempt++) {
 		A.cand = ctx->cand.p;
 		A.cand_cap = (uint32_t)std::min<size_t>(ctx->cand.cap, 0xffffffffu);
+		// a warp reserves candidate slots a chunk at a time; all warps' unused tails together stay below an eighth of the buffer
+		A.chunk = (uint32_t)std::min<size_t>(std::max<size_t>(A.cand_cap / ((size_t)8 * (size_t)grid * (size_t)geom.warps), 32), 1024);
 		CK(ctx, launch_fill_u32(reinterpret_cast<uint32_t *>(ctx->cursor.p), 8, 0u, ctx->stream));
 		CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
 		if (hashed) CK(ctx, launch_scan_hash(A, ctx->pat_hash, grid, ctx->stream));
@@ -742,7 +744,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 			return fail(ctx, "gscan_batch_scan: candidate buffer overflow (pattern matches almost everywhere); split the batch");
 		CK(ctx, ctx->cand.ensure((size_t)(total_cand + total_cand / 8 + 1024)));
 	}
-	S.n_candidates = total_cand;
+	S.n_candidates = total_cand; // slots reserved; replaced by the exact count once the segments are summed
 
 	size_t n = 0;
 	gscan_match *m = nullptr;
@@ -788,7 +790,8 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		// a unit on which the backtracking VM ran out of stack or steps stops there, like the reference's loop when
 		// pcre_exec reports a match-limit error (rc < 0 => break, grab.cc:179, quirk Q5); the other units are unaffected
 		S.vm_limit_hit = h_tot[2] ? 1u : 0u;
-		if (!dense && h_tot[0] != (uint32_t)total_cand) return fail(ctx, "gscan_batch_scan: internal: segment counts disagree with the cursor");
+		if (!dense && h_tot[0] > (uint32_t)total_cand) return fail(ctx, "gscan_batch_scan: internal: more candidates in the segments than slots reserved");
+		if (!dense) { S.n_candidates = h_tot[0]; R.total_cand = h_tot[0]; }
 		n = h_tot[1];
 		if (n) {
 			// the records are written on the device in their final form and land in a pinned buffer that is lent
@@ -959,7 +962,7 @@ extern "C" int gscan_tma_probe(gscan_ctx *ctx, gscan_batch *b, int geom, float *
 	if (ctx->cand.cap == 0) CK(ctx, ctx->cand.ensure(1u << 20));
 	ScanArgs A;
 	A.tiles = b->d_tiles; A.n_tiles = b->n_tiles; A.cand = ctx->cand.p; A.cand_cap = (uint32_t)ctx->cand.cap;
-	A.cursor = ctx->cursor.p; A.segs = ctx->segs.p; A.scratch = ctx->scratch.p; A.extra_smem = 0; A.tag = ctx->seg_tag; A.spt_shift = spt_shift;
+	A.cursor = ctx->cursor.p; A.segs = ctx->segs.p; A.scratch = ctx->scratch.p; A.extra_smem = 0; A.tag = ctx->seg_tag; A.spt_shift = spt_shift; A.chunk = 64;
 	CK(ctx, launch_fill_u32(reinterpret_cast<uint32_t *>(ctx->cursor.p), 8, 0u, ctx->stream));
 	CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
 	CK(ctx, launch_scan_null(A, geom, (int)std::min<uint32_t>((uint32_t)ctx->num_sms, b->n_tiles), ctx->stream));

@@ -164,23 +164,35 @@ struct Emitter {
 		return total;
 	}
 
+	// Space in the global candidate buffer is reserved a CHUNK at a time (one atomicAdd per A.chunk candidates, not one
+	// per slice): with one reservation per slice the warp sat on the atomic's round trip in four slices out of five of a
+	// dense pattern -- 35 % of all stall samples of the RUN kernel (profiles/r02_run16_v1_ncu.txt).  What a warp leaves
+	// unused of its last chunk is wasted (the host sizes for it); candidates of one slice stay contiguous.
+	uint32_t chunk_base = 0, chunk_left = 0;
+
 	__device__ __forceinline__ void flush(const ScanArgs &A, uint32_t seg, uint32_t lane)
 	{
-		uint32_t base = 0;
 		if (n) {
-			unsigned long long b64 = 0;
-			if (lane == 0) b64 = atomicAdd(A.cursor, (unsigned long long)n);
-			b64 = __shfl_sync(0xffffffffu, b64, 0);
-			__syncwarp();
-			if (b64 + n <= (unsigned long long)A.cand_cap) {
-				base = (uint32_t)b64;
-				for (uint32_t i = lane; i < n; i += 32) A.cand[base + i] = scratch[i];
+			if (n > chunk_left) { // warp-uniform
+				const uint32_t want = n > A.chunk ? n : A.chunk;
+				unsigned long long b64 = 0;
+				if (lane == 0) b64 = atomicAdd(A.cursor, (unsigned long long)want);
+				b64 = __shfl_sync(0xffffffffu, b64, 0);
+				// past the end of the buffer: nothing is written, the host sees cursor > cand_cap, grows the buffer and re-runs
+				chunk_left = b64 + want <= (unsigned long long)A.cand_cap ? want : 0u;
+				chunk_base = (uint32_t)b64;
 			}
-			// else: the host sees cursor > cand_cap, grows the buffer and re-runs the scan
+			__syncwarp();
+			if (n <= chunk_left) {
+				const uint32_t base = chunk_base;
+				for (uint32_t i = lane; i < n; i += 32) A.cand[base + i] = scratch[i];
+				// only non-empty segments are written; the entry carries this scan's generation tag, so stale entries of
+				// earlier scans read as empty and the table never has to be cleared between scans
+				if (lane == 0) A.segs[seg] = SegEntry{base, n | (A.tag << 16)};
+				chunk_base += n;
+				chunk_left -= n;
+			}
 		}
-		// only non-empty segments are written; the entry carries this scan's generation tag, so stale entries of
-		// earlier scans read as empty and the table never has to be cleared between scans
-		if (n && lane == 0) A.segs[seg] = SegEntry{base, n | (A.tag << 16)};
 		n = 0;
 	}
 };
