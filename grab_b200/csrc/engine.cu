@@ -401,13 +401,26 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 // ---- feed path for pageable host memory ----
 // A single memcpy into a pinned bounce buffer runs at ~8 GB/s, PCIe Gen5 takes ~55 GB/s: several helper threads
 // copy disjoint 4 MiB chunks into their own pinned buffers and queue the H2D copies on their own streams.
-struct StageJob { const uint8_t *src; uint8_t *dst; size_t len; };
+struct StagePiece { const uint8_t *src; uint8_t *dst; size_t len; };
+// one bounce-buffer load: pieces [first, first + count) whose arena range [dst, dst + span) is at most kStageChunk --
+// many small units (1 MiB files) travel as ONE 4 MiB copy instead of four
+struct StageJob { size_t first, count; uint8_t *dst; size_t span; };
 constexpr size_t kStageChunk = 4u << 20;
 
-static int stage_pageable(gscan_ctx *ctx, const std::vector<StageJob> &jobs)
+static int stage_pageable(gscan_ctx *ctx, const std::vector<StagePiece> &pieces)
 {
+	// group consecutive pieces (ascending arena addresses) into bounce-buffer loads
+	std::vector<StageJob> jobs;
 	size_t total = 0;
-	for (auto &j : jobs) total += j.len;
+	for (size_t i = 0; i < pieces.size(); i++) {
+		total += pieces[i].len;
+		if (!jobs.empty()) {
+			StageJob &j = jobs.back();
+			const uint8_t *end = pieces[i].dst + pieces[i].len;
+			if (pieces[i].dst >= j.dst + j.span && (size_t)(end - j.dst) <= kStageChunk) { j.count++; j.span = (size_t)(end - j.dst); continue; }
+		}
+		jobs.push_back(StageJob{i, 1, pieces[i].dst, pieces[i].len});
+	}
 	int want = 12; // measured on the B200 box (tools/stage_sweep.py): 4 -> 33, 8 -> 35/49, 12 -> 38/50, 16 -> 38/49, 24 -> 32/39 GB/s (1 MiB / 64 MiB units)
 	if (const char *e = getenv("GSCAN_STAGE_THREADS")) want = atoi(e);
 	const int hw = (int)std::thread::hardware_concurrency();
@@ -433,8 +446,10 @@ static int stage_pageable(gscan_ctx *ctx, const std::vector<StageJob> &jobs)
 			cudaError_t e = cudaSuccess;
 			if (used[k]) e = cudaEventSynchronize(l.ev[k]);
 			if (e == cudaSuccess) {
-				memcpy(l.buf[k], jobs[j].src, jobs[j].len);
-				e = cudaMemcpyAsync(jobs[j].dst, l.buf[k], jobs[j].len, cudaMemcpyHostToDevice, l.stream);
+				const StageJob &job = jobs[j];
+				for (size_t q = job.first; q < job.first + job.count; q++) // the gaps between units (256-byte alignment) travel as they are
+					memcpy(static_cast<uint8_t *>(l.buf[k]) + (pieces[q].dst - job.dst), pieces[q].src, pieces[q].len);
+				e = cudaMemcpyAsync(job.dst, l.buf[k], job.span, cudaMemcpyHostToDevice, l.stream);
 			}
 			if (e == cudaSuccess) e = cudaEventRecord(l.ev[k], l.stream);
 			used[k] = true;
@@ -507,7 +522,7 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 	std::vector<DevUnit> dunits;
 	tiles.reserve((size_t)n_tiles64);
 	auto t0 = std::chrono::steady_clock::now();
-	std::vector<StageJob> jobs;
+	std::vector<StagePiece> jobs;
 	const uint8_t *run_src = nullptr;
 	uint8_t *run_dst = nullptr;
 	size_t run_len = 0;
@@ -544,7 +559,7 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 			} else {
 				// pageable memory (the reference's mmap windows): staged after this loop by the helper lanes
 				for (uint64_t o = 0; o < u.len; o += kStageChunk)
-					jobs.push_back(StageJob{u.ptr + o, dst + o, (size_t)std::min<uint64_t>(kStageChunk, u.len - o)});
+					jobs.push_back(StagePiece{u.ptr + o, dst + o, (size_t)std::min<uint64_t>(kStageChunk, u.len - o)});
 			}
 		}
 		DevUnit du;

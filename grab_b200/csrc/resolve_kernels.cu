@@ -128,7 +128,11 @@ __global__ void k_gather(const ResolveArgs R)
 // `subj` is the subject as the reference's pcre_exec call sees it: it begins at the moving search start
 // (grab.cc:178), so ^, \A and \b at its first byte behave exactly as there.
 constexpr int kVmStack = 2048; // entries of 12 bytes in thread-local memory (24 KiB per thread); the VM walk runs in its own low-occupancy kernel
-constexpr uint32_t kVmMaxSteps = 1u << 24;
+// PCRE bounds the work of ONE pcre_exec call -- all start offsets of one search together (match limit, 10 million by
+// default) -- and a unit additionally gets a total budget, so that a pathological pattern costs seconds, not hours, before
+// the limit is reported (gscan_stats.vm_limit_hit; the unit stops there like the reference's loop on a pcre_exec error)
+constexpr uint32_t kVmSearchSteps = 1u << 22;  // per search (from one search start to its match), plus 64 per byte of the unit
+constexpr uint32_t kVmUnitSteps = 1u << 25;    // per unit and call, plus 128 per byte of the unit
 
 __device__ __forceinline__ bool vm_in_set(const ResolveArgs &R, uint32_t set, uint32_t b) { return (R.vm_sets[set * 8 + (b >> 5)] >> (b & 31)) & 1u; }
 __device__ __forceinline__ bool vm_is_word(uint32_t b) { return (b >= '0' && b <= '9') || (b >= 'A' && b <= 'Z') || (b >= 'a' && b <= 'z') || b == '_'; }
@@ -151,14 +155,23 @@ __device__ bool vm_assert(uint32_t kind, const uint8_t *s, uint32_t len, uint32_
 
 // 1: match, *end set; 2: match in which a capturing group took part (VM_CAP on the successful path: pcre_exec with room
 // for one offset pair returns 0 for it, quirk Q2); 0: no match at `at`; -1: stack / step limit
-__device__ int vm_exec(const ResolveArgs &R, const uint8_t *s, uint32_t len, uint32_t at, uint32_t *end)
+struct VmBudget {
+	// both budgets grow with the unit (a linear scan of a big window must never trip them): + 64 steps per byte
+	unsigned long long search, unit, per_search;
+	__device__ explicit VmBudget(unsigned long long ulen) : search(kVmSearchSteps + 64ull * ulen), unit(kVmUnitSteps + 128ull * ulen), per_search(kVmSearchSteps + 64ull * ulen) {}
+	__device__ void new_search() { search = per_search; }
+};
+
+__device__ int vm_exec(const ResolveArgs &R, const uint8_t *s, uint32_t len, uint32_t at, uint32_t *end, VmBudget &budget)
 {
 	// st_pc: pc | kind << 16 (0 plain, 1 give-back, 2 take-more) | capture flag at push time << 24
 	uint32_t st_pc[kVmStack], st_sp[kVmStack], st_lo[kVmStack];
 	int top = 0;
-	uint32_t pc = 0, sp = at, steps = 0, cap = 0;
+	uint32_t pc = 0, sp = at, cap = 0;
 	for (;;) {
-		if (++steps > kVmMaxSteps) return -1;
+		if (budget.search == 0 || budget.unit == 0) return -1;
+		budget.search--;
+		budget.unit--;
 		const uint32_t w0 = R.vm_code[3 * pc], a = R.vm_code[3 * pc + 1], b = R.vm_code[3 * pc + 2];
 		const uint32_t op = w0 & 0xffu, kind = (w0 >> 8) & 0xffu, set = w0 >> 16;
 		bool fail = false;
@@ -338,6 +351,7 @@ __global__ void __launch_bounds__(64, 4) k_walk_vm(const ResolveArgs R)
 	const uint32_t end = R.vm_dense ? 0u : R.unit_start[u + 1];
 	uint32_t n = 0;
 	FinalRec *o = WRITE ? R.out + R.unit_out[u] : nullptr;
+	VmBudget budget(R.units[u].len); // the count and the write pass replay the same searches with the same budgets: same outcome
 	if (R.vm_dense) {
 		// no candidate list: PCRE's own search loop -- one anchored attempt per position whose byte can start a match, from
 		// the moving search start; both passes replay it
@@ -352,7 +366,7 @@ __global__ void __launch_bounds__(64, 4) k_walk_vm(const ResolveArgs R)
 			int rc = 0;
 			for (; pos + R.minlen <= ulen; pos++) {                                     // (an attempt with fewer bytes left cannot succeed)
 				if (!in_class(R, data[pos])) continue;
-				rc = vm_exec(R, data + start, (uint32_t)(ulen - start), (uint32_t)(pos - start), &e); // grab.cc:178
+				rc = vm_exec(R, data + start, (uint32_t)(ulen - start), (uint32_t)(pos - start), &e, budget); // grab.cc:178
 				if (rc != 0) break;
 			}
 			if (rc < 0) { atomicOr(R.totals + 2, 1u); break; }
@@ -367,6 +381,7 @@ __global__ void __launch_bounds__(64, 4) k_walk_vm(const ResolveArgs R)
 				me += a;
 			}
 			start = me;                                                                 // grab.cc:209
+			budget.new_search();
 		}
 	} else if (i != end && R.vm_runstart) {
 		// candidates are run starts; a match may also begin at the search start when that lies inside a run, so the
@@ -381,7 +396,7 @@ __global__ void __launch_bounds__(64, 4) k_walk_vm(const ResolveArgs R)
 			uint32_t e = 0;
 			bool found = false;
 			if (start > 0 && in_class(R, data[start - 1]) && in_class(R, data[start])) {
-				const int rc = vm_exec(R, data + start, (uint32_t)(ulen - start), 0u, &e);
+				const int rc = vm_exec(R, data + start, (uint32_t)(ulen - start), 0u, &e, budget);
 				if (rc < 0) { atomicOr(R.totals + 2, 1u); break; }
 				if (rc == 2) break;                                                     // Q2: pcre_exec returns 0, the loop leaves the window
 				if (rc == 1) { pos = start; found = true; }
@@ -390,7 +405,7 @@ __global__ void __launch_bounds__(64, 4) k_walk_vm(const ResolveArgs R)
 				while (i < end && R.ord[i].pos < start) i++;
 				if (i == end) break;
 				pos = R.ord[i++].pos;
-				const int rc = vm_exec(R, data + start, (uint32_t)(ulen - start), (uint32_t)(pos - start), &e); // grab.cc:178
+				const int rc = vm_exec(R, data + start, (uint32_t)(ulen - start), (uint32_t)(pos - start), &e, budget); // grab.cc:178
 				if (rc < 0) { atomicOr(R.totals + 2, 1u); i = end; break; }
 				if (rc == 2) { i = end; break; }                                        // Q2
 				found = rc == 1;
@@ -406,6 +421,7 @@ __global__ void __launch_bounds__(64, 4) k_walk_vm(const ResolveArgs R)
 				me += a;
 			}
 			start = me;                                                                 // grab.cc:209
+			budget.new_search();
 		}
 	} else 	if (i != end) {
 		const DevUnit du = R.units[u];
@@ -418,7 +434,7 @@ __global__ void __launch_bounds__(64, 4) k_walk_vm(const ResolveArgs R)
 				const uint32_t pos = R.ord[i].pos;
 				if (pos < start) continue;
 				uint32_t e = 0;
-				const int rc = vm_exec(R, data + start, (uint32_t)(ulen - start), (uint32_t)(pos - start), &e); // grab.cc:178
+				const int rc = vm_exec(R, data + start, (uint32_t)(ulen - start), (uint32_t)(pos - start), &e, budget); // grab.cc:178
 				if (rc < 0) { atomicOr(R.totals + 2, 1u); break; }                      // limit: this unit stops here (pcre_exec error => break, grab.cc:179 / Q5)
 				if (rc == 0) continue;                                                  // next start offset, like PCRE
 				if (rc == 2) break;                                                     // Q2: a group was set => rc 0 => grab.cc:179 breaks
@@ -433,6 +449,7 @@ __global__ void __launch_bounds__(64, 4) k_walk_vm(const ResolveArgs R)
 					me += a;
 				}
 				start = me;                                                             // grab.cc:209
+				budget.new_search();
 			}
 		} else {
 			for (; i < end; i++)

@@ -542,15 +542,17 @@ struct HashEngine {
 	static __device__ __noinline__ uint32_t verify(const HashParams &P, const uint8_t *tile, uint32_t off, uint32_t ulen, int p, uint32_t slot)
 	{
 		const unsigned long long qu = (unsigned long long)off + (unsigned)p;
-		const uint32_t first = P.slot_first[slot], cnt = P.slot_count[slot];
+		// the pattern tables are read-only for the whole launch: the non-coherent path keeps them in L1 (a verification is a
+		// chain of dependent loads: from L2 every link costs ~250 cycles)
+		const uint32_t first = __ldg(P.slot_first + slot), cnt = __ldg(P.slot_count + slot);
 		for (uint32_t k = 0; k < cnt; k++) {
-			const uint32_t s = P.slot_seqs[first + k];
-			const uint32_t len = P.seq_len[s];
+			const uint32_t s = __ldg(P.slot_seqs + first + k);
+			const uint32_t len = __ldg(P.seq_len + s);
 			if (qu + len > ulen) continue;
-			const uint32_t *pp = P.seq_pos + P.seq_off[s];
+			const uint32_t *pp = P.seq_pos + __ldg(P.seq_off + s);
 			uint32_t i = 0;
 			for (; i < len; i++) {
-				const uint32_t e = pp[i];
+				const uint32_t e = __ldg(pp + i);
 				const uint32_t b = tile[p + (int)i];
 				const uint32_t cls = e >> 16;
 				bool ok;
@@ -601,14 +603,21 @@ struct HashEngine {
 			hits |= (probe<false>(P, tbl, window(w[b >> 2], w[(b >> 2) + 1], b & 3)) == 0u ? 1u : 0u) << b;
 		// the slot at position b for a run-time b (rolled loops below: the slow path stays small)
 		auto slot_rt = [&](int b) -> uint32_t { return slot_of(P, __funnelshift_r(w[b >> 2], w[(b >> 2) + 1], 8 * (b & 3)) * P.mulsh); };
+		uint32_t len_a = 0, len_b = 0, bit_a = 32, bit_b = 32; // lengths of the lane's first two matches (a third one verifies again)
 		while (hits) { // verify() is out of line: one copy, the kernel stays instruction-cache resident
 			const int b = __ffs(hits) - 1;
 			hits &= hits - 1;
 			const int p = (int)c0 + b;
-			if (p < (int)tile_len && verify(P, gtile, off, ulen, p, slot_rt(b))) mm |= 1u << b;
+			const uint32_t len = p < (int)tile_len ? verify(P, gtile, off, ulen, p, slot_rt(b)) : 0u;
+			if (len) {
+				mm |= 1u << b;
+				if (bit_a == 32) { bit_a = (uint32_t)b; len_a = len; }
+				else if (bit_b == 32) { bit_b = (uint32_t)b; len_b = len; }
+			}
 		}
 		return Emitter::emit_at(dst, mm, off + c0, [&](uint32_t b) -> uint32_t {
-			if (P.uniform_len) return P.uniform_len;
+			if (b == bit_a) return len_a;
+			if (b == bit_b) return len_b;
 			return verify(P, gtile, off, ulen, (int)(c0 + b), slot_rt((int)b));
 		}, lane);
 	}

@@ -69,10 +69,11 @@ static int emulate(const Program &p, const uint8_t *s, size_t len, std::vector<M
 	while (start + (size_t)p.minlen < len) { // grab.cc:175
 		bool found = false;
 		size_t pos = start, mend = 0;
+		VmBudget budget(len);
 		for (; pos < len; pos++) {
 			if (p.use_vm) {
 				uint32_t e = 0;
-				const int rc = vm_exec(R, s + start, (uint32_t)(len - start), (uint32_t)(pos - start), &e);
+				const int rc = vm_exec(R, s + start, (uint32_t)(len - start), (uint32_t)(pos - start), &e, budget);
 				if (rc < 0) return -1;
 				if (rc == 1) { found = true; mend = start + e; }
 			} else if (p.kind == ENGINE_RUN) {
