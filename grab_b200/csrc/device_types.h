@@ -95,6 +95,7 @@ struct HashParams {
 	uint32_t nslots;     //   slot = umulhi(h, nslots): IMADs only, nothing on the ALU pipe
 	uint32_t stride;     // bytes between slots in shared memory: 128 when the table is replicated per bank, else 4
 	uint32_t neg1;       // == 0xffffffff, opaque to the compiler: h * neg1 + entry is an IMAD (FMA pipe) where a XOR would be ALU
+	uint32_t pow2_shift, pow2_mask; // power-of-two replicated table: row offset = (h >> pow2_shift) & pow2_mask (0: not a power of two)
 	const uint32_t *table;      // [nslots] h of the slot's key, or 0xffffffff (copied to shared memory at kernel start)
 	const uint32_t *slot_first; // [nslots] first index into slot_seqs
 	const uint32_t *slot_count; // [nslots]

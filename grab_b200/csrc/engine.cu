@@ -244,6 +244,13 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 			H.nslots = pr.hash_slots;
 			H.stride = hash_table_copies(pr.hash_slots) * 4u;
 			H.neg1 = 0xffffffffu;
+			H.pow2_shift = H.pow2_mask = 0;
+			if (H.stride == 128u && (H.nslots & (H.nslots - 1u)) == 0u && H.nslots >= 2u) {
+				uint32_t lg = 0;
+				while ((1u << lg) < H.nslots) lg++;
+				H.pow2_shift = 32u - lg - 7u;          // slot = h >> (32 - lg); row offset = slot * 128
+				H.pow2_mask = (H.nslots - 1u) << 7;
+			}
 			H.uniform_len = F.uniform_len;
 			H.maxlen = F.maxlen;
 		}

@@ -526,6 +526,9 @@ struct FixedBEngine {
 #ifndef GS_HASH_SUB
 #define GS_HASH_SUB 2
 #endif
+#ifndef GS_HASH_POW2
+#define GS_HASH_POW2 0
+#endif
 struct HashEngine {
 	typedef HashParams Params;
 	static constexpr bool kLookBehind = false, kLookAhead = true;
@@ -568,6 +571,15 @@ struct HashEngine {
 	// the 32-bit window at byte k of the word pair; the bytes beyond the key fall off the top of window * mulsh
 	static __device__ __forceinline__ uint32_t window(uint32_t lo, uint32_t hi, int k) { return k ? __funnelshift_r(lo, hi, 8 * k) : lo; }
 	static __device__ __forceinline__ uint32_t slot_of(const HashParams &P, uint32_t h) { return __umulhi(h, P.nslots); }
+	// byte offset of the slot's row in the replicated table.  GS_HASH_POW2 (tuning): for a power-of-two table the offset is
+	// a shift and a mask on the ALU pipe instead of IMAD.HI + IMAD on the FMA pipe
+	static __device__ __forceinline__ uint32_t row_of(const HashParams &P, uint32_t h)
+	{
+#if GS_HASH_POW2
+		if (P.pow2_shift) return (h >> P.pow2_shift) & P.pow2_mask;
+#endif
+		return slot_of(P, h) * P.stride;
+	}
 	// tbl: the table in shared memory, for a replicated table already advanced to this lane's bank (+ lane * 4).
 	// Hash, slot and address are three IMADs (FMA pipe); zero <=> the position holds a key of the set.  SUB: the
 	// comparison as entry - h on the FMA pipe instead of entry ^ h on the ALU pipe (GS_HASH_SUB of every 4 positions).
@@ -575,32 +587,34 @@ struct HashEngine {
 	static __device__ __forceinline__ uint32_t probe(const HashParams &P, const uint8_t *tbl, uint32_t y)
 	{
 		const uint32_t h = y * P.mulsh;
-		const uint32_t e = *reinterpret_cast<const uint32_t *>(tbl + slot_of(P, h) * P.stride);
+		const uint32_t e = *reinterpret_cast<const uint32_t *>(tbl + row_of(P, h));
 		return SUB ? h * P.neg1 + e : e ^ h;
 	}
 
-	// min over the 16 positions of (table[slot(h)] ^ h), two positions per 3-input minimum
-	static __device__ __forceinline__ uint32_t row_min(const HashParams &P, const uint8_t *tbl, const uint32_t (&w)[5])
+	// min over the 16 positions of (table[slot(h)] ^ h), two positions per 3-input minimum; d[] keeps the 16 words for the
+	// rare row that has a hit (its positions then cost a compare each instead of a second round of lookups)
+	static __device__ __forceinline__ uint32_t row_min(const HashParams &P, const uint8_t *tbl, const uint32_t (&w)[5], uint32_t (&d)[16])
 	{
 		uint32_t mn = 0xffffffffu;
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
-			mn = __vimin3_u32(mn, probe<(GS_HASH_SUB > 0)>(P, tbl, window(w[j], w[j + 1], 0)), probe<(GS_HASH_SUB > 1)>(P, tbl, window(w[j], w[j + 1], 1)));
-			mn = __vimin3_u32(mn, probe<(GS_HASH_SUB > 2)>(P, tbl, window(w[j], w[j + 1], 2)), probe<(GS_HASH_SUB > 3)>(P, tbl, window(w[j], w[j + 1], 3)));
+			d[4 * j + 0] = probe<(GS_HASH_SUB > 0)>(P, tbl, window(w[j], w[j + 1], 0));
+			d[4 * j + 1] = probe<(GS_HASH_SUB > 1)>(P, tbl, window(w[j], w[j + 1], 1));
+			d[4 * j + 2] = probe<(GS_HASH_SUB > 2)>(P, tbl, window(w[j], w[j + 1], 2));
+			d[4 * j + 3] = probe<(GS_HASH_SUB > 3)>(P, tbl, window(w[j], w[j + 1], 3));
+			mn = __vimin3_u32(mn, d[4 * j + 0], d[4 * j + 1]);
+			mn = __vimin3_u32(mn, d[4 * j + 2], d[4 * j + 3]);
 		}
 		return mn;
 	}
 
 	static __device__ __noinline__ uint32_t slow_row(const HashParams &P, const uint8_t *tbl, const uint8_t *gtile, uint32_t off,
 	                                                 uint32_t ulen, uint32_t tile_len, Cand *dst, uint32_t lane, uint32_t c0,
-	                                                 uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4)
+	                                                 uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t hits)
 	{
+		// hits: positions whose leading bytes are a key of the set (from the comparison words the fast path kept)
 		const uint32_t w[5] = {w0, w1, w2, w3, w4};
 		uint32_t mm = 0;
-		uint32_t hits = 0; // positions whose leading bytes are a key of the set (unrolled: straight-line, no divergence yet)
-#pragma unroll
-		for (int b = 0; b < 16; b++)
-			hits |= (probe<false>(P, tbl, window(w[b >> 2], w[(b >> 2) + 1], b & 3)) == 0u ? 1u : 0u) << b;
 		// the slot at position b for a run-time b (rolled loops below: the slow path stays small)
 		auto slot_rt = [&](int b) -> uint32_t { return slot_of(P, __funnelshift_r(w[b >> 2], w[(b >> 2) + 1], 8 * (b & 3)) * P.mulsh); };
 		uint32_t len_a = 0, len_b = 0, bit_a = 32, bit_b = 32; // lengths of the lane's first two matches (a third one verifies again)
@@ -633,9 +647,14 @@ struct HashEngine {
 			const uint4 a = *reinterpret_cast<const uint4 *>(S.tile + c0);
 			w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
 			w[4] = *reinterpret_cast<const uint32_t *>(S.tile + c0 + 16);
-			const uint32_t mn = row_min(P, tbl, w);
-			if (__any_sync(0xffffffffu, mn == 0))
-				E.n += slow_row(P, tbl, S.gtile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, c0, w[0], w[1], w[2], w[3], w[4]);
+			uint32_t d[16];
+			const uint32_t mn = row_min(P, tbl, w, d);
+			if (__any_sync(0xffffffffu, mn == 0)) {
+				uint32_t hits = 0;
+#pragma unroll
+				for (int b = 0; b < 16; b++) hits |= (d[b] == 0u ? 1u : 0u) << b;
+				E.n += slow_row(P, tbl, S.gtile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, c0, w[0], w[1], w[2], w[3], w[4], hits);
+			}
 		}
 	}
 };
