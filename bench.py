@@ -463,8 +463,8 @@ def main():
 
     def make_resident(cfg):
         """Device corpus of a config: files [rank * n, (rank + 1) * n) of its seeded corpus (weak scaling, reference main.cc:94)."""
-        key = (cfg["seed"], cfg["file_len"], cfg["needle"])
         n, first_id = cfg["n_files"], rank * cfg["n_files"]
+        key = (cfg["seed"], cfg["file_len"], cfg["needle"], first_id)  # rank r's shard starts at file r * n: part of the identity
         if resident["key"] != key or resident.get("n", 0) < n:
             ctx.synth_corpus(dptr, cfg["seed"], first_id, n, cfg["file_len"],
                              needle=cfg["needle"].encode() if cfg["needle"] else None, needle_every=NEEDLE_EVERY if cfg["needle"] else 0)

@@ -85,17 +85,19 @@ struct Node;
 typedef std::unique_ptr<Node> NodeP;
 
 struct Node {
-	enum Kind { SET, CAT, ALT, REP, GROUP, ASSERT, EMPTY } kind;
+	enum Kind { SET, CAT, ALT, REP, GROUP, ASSERT, EMPTY, LOOK /* (?=) (?!) (?<=) (?<!) */, ATOMIC /* (?>...), possessive groups */ } kind;
 	ByteSet set;
 	std::vector<NodeP> kids;
 	uint32_t rmin = 0, rmax = 0; // rmax == UINT32_MAX: unbounded
 	bool lazy = false, possessive = false;
 	bool capturing = false;
+	bool ahead = false, neg = false; // LOOK
 	int akind = 0; // ASSERT: one of VM_A_*
 	explicit Node(Kind k) : kind(k) {}
 };
 
 constexpr uint32_t kInf = UINT32_MAX;
+const Node *peel_noncapturing(const Node *n);
 
 struct Flags { bool icase = false, dotall = false, multiline = false, ungreedy = false, extended = false; };
 
@@ -329,8 +331,26 @@ private:
 					p_++;
 					flag_only = true;
 					return nullptr;
-				} else if (strchr("=!<>|R(&C+0123456789", (int)*p_)) {
-					fail("lookaround / atomic / recursive / conditional groups are not supported by the device engines");
+				} else if (*p_ == '=' || *p_ == '!' || *p_ == '>' || (*p_ == '<' && p_ + 1 < end_ && (p_[1] == '=' || p_[1] == '!'))) {
+					// lookahead (?= (?!, lookbehind (?<= (?<!, atomic group (?> -- none of them captures
+					int kind = 0; // 0 ahead, 1 behind, 2 atomic
+					bool neg = false;
+					if (*p_ == '>') { kind = 2; p_++; }
+					else if (*p_ == '<') { kind = 1; neg = p_[1] == '!'; p_ += 2; }
+					else { neg = *p_ == '!'; p_++; }
+					if (++depth_ > 200) { fail("parentheses nested too deeply"); return nullptr; }
+					NodeP body = alternation(inner);
+					depth_--;
+					if (!ok_) return nullptr;
+					if (!more() || *p_ != ')') { fail("missing )"); return nullptr; }
+					p_++;
+					NodeP g(new Node(kind == 2 ? Node::ATOMIC : Node::LOOK));
+					g->ahead = kind == 0;
+					g->neg = neg;
+					g->kids.push_back(std::move(body));
+					return g;
+				} else if (strchr("<|R(&C+0123456789", (int)*p_)) {
+					fail("recursive / conditional groups are not supported by the device engines");
 					return nullptr;
 				} else {
 					bool on = true;
@@ -453,9 +473,16 @@ private:
 					r->lazy = f.ungreedy;
 					if (more() && *p_ == '?') { r->lazy = !f.ungreedy; p_++; }
 					else if (more() && *p_ == '+') { r->possessive = true; r->lazy = false; p_++; }
-					if (a->kind == Node::ASSERT) { fail("quantified assertion"); break; }
+					if (a->kind == Node::ASSERT || a->kind == Node::LOOK) { fail("quantified assertion"); break; }
 					r->kids.push_back(std::move(a));
 					a = std::move(r);
+					if (a->possessive && peel_noncapturing(a->kids[0].get())->kind != Node::SET) {
+						// X*+ on anything but a single byte class is the atomic group (?>X*)
+						a->possessive = false;
+						NodeP at(new Node(Node::ATOMIC));
+						at->kids.push_back(std::move(a));
+						a = std::move(at);
+					}
 				}
 			}
 			cat->kids.push_back(std::move(a));
@@ -494,14 +521,41 @@ uint64_t min_length(const Node *n)
 		for (auto &k : n->kids) m = std::min(m, min_length(k.get()));
 		return m;
 	case Node::REP: return (uint64_t)n->rmin * min_length(n->kids[0].get());
-	case Node::GROUP: return min_length(n->kids[0].get());
+	case Node::GROUP: case Node::ATOMIC: return min_length(n->kids[0].get());
+	case Node::LOOK: return 0;
 	}
 	return 0;
 }
 
+// every match of n has the same length (what a lookbehind branch must have)
+bool fixed_length(const Node *n, uint64_t &len)
+{
+	uint64_t a = 0, b = 0;
+	switch (n->kind) {
+	case Node::EMPTY: case Node::ASSERT: case Node::LOOK: len = 0; return true;
+	case Node::SET: len = 1; return true;
+	case Node::CAT:
+		for (auto &k : n->kids) { if (!fixed_length(k.get(), b)) return false; a += b; }
+		len = a;
+		return true;
+	case Node::ALT:
+		if (n->kids.empty() || !fixed_length(n->kids[0].get(), a)) return false;
+		for (size_t i = 1; i < n->kids.size(); i++) if (!fixed_length(n->kids[i].get(), b) || b != a) return false;
+		len = a;
+		return true;
+	case Node::REP:
+		if (n->rmin != n->rmax || !fixed_length(n->kids[0].get(), a)) return false;
+		len = a * n->rmin;
+		return true;
+	case Node::GROUP: case Node::ATOMIC: return fixed_length(n->kids[0].get(), len);
+	}
+	return false;
+}
+
+// assertions, look-arounds and atomic groups: only the VM serves them
 bool has_assert(const Node *n)
 {
-	if (n->kind == Node::ASSERT) return true;
+	if (n->kind == Node::ASSERT || n->kind == Node::LOOK || n->kind == Node::ATOMIC) return true;
 	for (auto &k : n->kids) if (has_assert(k.get())) return true;
 	return false;
 }
@@ -531,7 +585,8 @@ const Node *peel_noncapturing(const Node *n)
 bool always_captures(const Node *n)
 {
 	switch (n->kind) {
-	case Node::SET: case Node::EMPTY: case Node::ASSERT: return false;
+	case Node::SET: case Node::EMPTY: case Node::ASSERT: case Node::LOOK: return false;
+	case Node::ATOMIC: return always_captures(n->kids[0].get());
 	case Node::GROUP: return n->capturing || always_captures(n->kids[0].get());
 	case Node::CAT: for (auto &k : n->kids) if (always_captures(k.get())) return true; return false;
 	case Node::ALT: for (auto &k : n->kids) if (!always_captures(k.get())) return false; return !n->kids.empty();
@@ -599,7 +654,7 @@ struct Expander {
 		if (overflow) return out;
 		switch (n->kind) {
 		case Node::EMPTY: out.push_back(Sequence()); return out;
-		case Node::ASSERT: overflow = true; general = true; return out;
+		case Node::ASSERT: case Node::LOOK: case Node::ATOMIC: overflow = true; general = true; return out;
 		case Node::SET:
 			if (n->set.empty()) return out; // can never match: contributes no alternative
 			out.push_back(Sequence(1, n->set));
@@ -710,6 +765,48 @@ struct VmGen {
 			gen(n->kids[0].get());
 			if (track_caps && n->capturing) emit(VM_CAP, 0, 0, 0, 0);
 			return;
+		case Node::ATOMIC: {
+			const uint32_t l = emit(VM_LOOK, VM_LK_ATOMIC, 0, 0, 0);
+			gen(n->kids[0].get());
+			emit(VM_LOOKEND, 0, 0, 0, 0);
+			if (!failed) code[3 * l + 1] = (uint32_t)(code.size() / 3);
+			return;
+		}
+		case Node::LOOK: {
+			if (n->ahead) {
+				const uint32_t l = emit(VM_LOOK, n->neg ? VM_LK_AHEAD_NEG : VM_LK_AHEAD, 0, 0, 0);
+				gen(n->kids[0].get());
+				emit(VM_LOOKEND, 0, 0, 0, 0);
+				if (!failed) code[3 * l + 1] = (uint32_t)(code.size() / 3);
+				return;
+			}
+			// lookbehind: every top-level branch has its own fixed length (PCRE's rule): (?<=a|bc) is (?:(?<=a)|(?<=bc)),
+			// (?<!a|bc) is (?<!a)(?<!bc)
+			const Node *body = peel_noncapturing(n->kids[0].get());
+			std::vector<const Node *> branches;
+			if (body->kind == Node::ALT) for (auto &k : body->kids) branches.push_back(k.get());
+			else branches.push_back(body);
+			std::vector<uint32_t> jmps;
+			for (size_t i = 0; i < branches.size() && !failed; i++) {
+				uint64_t len = 0;
+				if (!fixed_length(branches[i], len) || len > 65535) { failed = true; why = "lookbehind assertion is not fixed length"; return; }
+				uint32_t split = 0;
+				const bool more_branches = !n->neg && i + 1 < branches.size();
+				if (more_branches) split = emit(VM_SPLIT, 0, 0, 0, 0);
+				const uint32_t l = emit(VM_LOOK, n->neg ? VM_LK_BEHIND_NEG : VM_LK_BEHIND, 0, 0, (uint32_t)len);
+				gen(branches[i]);
+				emit(VM_LOOKEND, 0, 0, 0, 0);
+				if (failed) return;
+				code[3 * l + 1] = (uint32_t)(code.size() / 3);
+				if (more_branches) {
+					jmps.push_back(emit(VM_JMP, 0, 0, 0, 0));
+					code[3 * split + 1] = split + 1;
+					code[3 * split + 2] = (uint32_t)(code.size() / 3);
+				}
+			}
+			for (uint32_t j : jmps) code[3 * j + 1] = (uint32_t)(code.size() / 3);
+			return;
+		}
 		case Node::CAT: for (auto &k : n->kids) gen(k.get()); return;
 		case Node::ALT: {
 			std::vector<uint32_t> jmps;
@@ -770,7 +867,8 @@ bool prefixes(const Node *n, size_t L, std::vector<Pref> &out)
 {
 	out.clear();
 	switch (n->kind) {
-	case Node::EMPTY: case Node::ASSERT: out.push_back(Pref{Sequence(), true}); return true;
+	case Node::EMPTY: case Node::ASSERT: case Node::LOOK: out.push_back(Pref{Sequence(), true}); return true;
+	case Node::ATOMIC: return prefixes(n->kids[0].get(), L, out);
 	case Node::SET:
 		if (n->set.empty()) return true; // can never match: no prefix at all
 		out.push_back(Pref{Sequence(1, n->set), true});

@@ -54,7 +54,9 @@ struct FilterTest {
 enum EngineKind { ENGINE_FIXED = 1, ENGINE_RUN = 2, ENGINE_NONE = 3 };
 
 // device VM (resolve_kernels.cu) instruction set
-enum { VM_SET = 0, VM_SPLIT = 1, VM_JMP = 2, VM_REP = 3, VM_ASSERT = 4, VM_MATCH = 5, VM_CAP = 6 /* a capturing group closed (Q2) */ };
+enum { VM_SET = 0, VM_SPLIT = 1, VM_JMP = 2, VM_REP = 3, VM_ASSERT = 4, VM_MATCH = 5, VM_CAP = 6 /* a capturing group closed (Q2) */,
+       VM_LOOK = 7 /* kind: VM_LK_*, a: pc behind the construct, b: bytes to step back (lookbehind) */, VM_LOOKEND = 8 };
+enum { VM_LK_AHEAD = 0, VM_LK_AHEAD_NEG = 1, VM_LK_BEHIND = 2, VM_LK_BEHIND_NEG = 3, VM_LK_ATOMIC = 4 };
 enum { VM_Q_GREEDY = 0, VM_Q_LAZY = 1, VM_Q_POSSESSIVE = 2 };
 enum { VM_A_BOL = 0, VM_A_EOL = 1, VM_A_SOS = 2, VM_A_EOS = 3, VM_A_EOSNL = 4, VM_A_WORDB = 5, VM_A_NWORDB = 6, VM_A_MBOL = 7, VM_A_MEOL = 8 };
 

@@ -185,6 +185,31 @@ __device__ int vm_exec(const ResolveArgs &R, const uint8_t *s, uint32_t len, uin
 			if (vm_assert(kind, s, len, sp)) pc++; else fail = true;
 			break;
 		case VM_JMP: pc = a; break;
+		case VM_LOOK: { // kind: VM_LK_*, a: pc behind the construct, b: bytes to step back (lookbehind)
+			const bool behind = kind == VM_LK_BEHIND || kind == VM_LK_BEHIND_NEG;
+			if (behind && sp < b) {
+				// fewer bytes before sp than the branch needs (the subject begins at the moving search start): it cannot match
+				if (kind == VM_LK_BEHIND) fail = true; else pc = a;
+				break;
+			}
+			if (top == kVmStack) return -1;
+			st_pc[top] = a | (3u << 16) | cap; st_sp[top] = sp; st_lo[top] = kind; top++;
+			if (behind) sp -= b;
+			pc++;
+			break;
+		}
+		case VM_LOOKEND: {
+			// the body matched: the choice points it left are dropped (an assertion / atomic group is never re-entered)
+			int L = top;
+			while (L > 0 && ((st_pc[L - 1] >> 16) & 0xffu) != 3u) L--;
+			if (L == 0) return -1; // cannot happen: every LOOKEND has its frame
+			const uint32_t fk = st_lo[L - 1], fsp = st_sp[L - 1], fcap = st_pc[L - 1] & (1u << 24);
+			top = L - 1;
+			if (fk == VM_LK_AHEAD_NEG || fk == VM_LK_BEHIND_NEG) { cap = fcap; fail = true; break; } // the negative assertion is false
+			if (fk != VM_LK_ATOMIC) sp = fsp; // assertions consume nothing
+			pc++;
+			break;
+		}
 		case VM_SPLIT:
 			if (top == kVmStack) return -1;
 			st_pc[top] = b | cap; st_sp[top] = sp; st_lo[top] = 0; top++;
@@ -219,6 +244,14 @@ __device__ int vm_exec(const ResolveArgs &R, const uint8_t *s, uint32_t len, uin
 			const uint32_t e = st_pc[top - 1], ek = (e >> 16) & 0xffu;
 			cap = e & (1u << 24); // whatever closed after this choice point is undone
 			if (ek == 0) { pc = e & 0xffffu; sp = st_sp[top - 1]; top--; break; }
+			if (ek == 3) { // the body of an assertion / atomic group failed for good
+				const uint32_t fk = st_lo[top - 1];
+				const uint32_t back_to = st_sp[top - 1];
+				top--;
+				if (fk != VM_LK_AHEAD_NEG && fk != VM_LK_BEHIND_NEG) continue; // positive assertion / atomic group: the failure goes on
+				pc = e & 0xffffu; sp = back_to;                                 // the negative assertion holds: go on behind it
+				break;
+			}
 			if (ek == 1) { // greedy repeat gives one item back
 				if (st_sp[top - 1] > st_lo[top - 1]) {
 					sp = --st_sp[top - 1];

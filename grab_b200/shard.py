@@ -100,7 +100,7 @@ class _DevRecords:
     """__cuda_array_interface__ over the engine's device records, so torch can wrap them without a copy."""
 
     def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, True), "version": 2}
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "strides": None, "version": 2}
 
 
 class PendingMatches:
@@ -143,11 +143,16 @@ def gather_matches_start(local, dst=0, group=None, device_records=None):
         buf = torch.empty(cap, dtype=torch.uint8, device=dev)
         nb = n_local * MATCH_DTYPE.itemsize
         if nb:
+            src = None
             if device_records is not None:
-                buf[:nb].copy_(torch.as_tensor(_DevRecords(int(device_records[0]), nb), device=dev))
-            else:
+                try:
+                    src = torch.as_tensor(_DevRecords(int(device_records[0]), nb), device=dev)
+                except Exception:  # noqa: BLE001 -- a torch build without __cuda_array_interface__ import: go through the host
+                    src = None
+            if src is None:
                 local = np.ascontiguousarray(local, dtype=MATCH_DTYPE)
-                buf[:nb].copy_(torch.from_numpy(local.view(np.uint8).reshape(-1)), non_blocking=False)
+                src = torch.from_numpy(local.view(np.uint8).reshape(-1).copy())
+            buf[:nb].copy_(src)
         out = torch.empty(world * cap, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(out, buf, group=group)  # enqueued on `side` (NCCL orders it after the copies above)
         host = None

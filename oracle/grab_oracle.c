@@ -68,7 +68,7 @@ static void bs_caseless(bset *s)
 /* AST                                                                                         */
 /* ------------------------------------------------------------------------------------------ */
 
-enum { N_EMPTY, N_SET, N_CAT, N_ALT, N_REP, N_GROUP, N_ASSERT };
+enum { N_EMPTY, N_SET, N_CAT, N_ALT, N_REP, N_GROUP, N_ASSERT, N_LOOK /* (?=) (?!) (?<=) (?<!) */, N_ATOMIC /* (?>...) and possessive groups */ };
 enum { A_BOL, A_EOL, A_SOS, A_EOS, A_EOSNL, A_WORDB, A_NWORDB, A_MBOL, A_MEOL };
 enum { Q_GREEDY, Q_LAZY, Q_POSSESSIVE };
 
@@ -81,6 +81,7 @@ typedef struct node {
 	int qkind;           /* N_REP */
 	int capturing;       /* N_GROUP */
 	int akind;           /* N_ASSERT */
+	int ahead, neg;      /* N_LOOK */
 } node;
 
 #define INF UINT32_MAX
@@ -354,10 +355,29 @@ static node *parse_atom(parser *P, pflags *f, int *is_flag_change)
 				P->p++;
 				*is_flag_change = 1;
 				return NULL;
-			} else if (*P->p == '=' || *P->p == '!' || *P->p == '<' || *P->p == '>' || *P->p == '|' ||
+			} else if (*P->p == '=' || *P->p == '!' || *P->p == '>' ||
+			           (*P->p == '<' && P->p + 1 < P->end && (P->p[1] == '=' || P->p[1] == '!'))) {
+				/* lookahead (?= (?!, lookbehind (?<= (?<!, atomic group (?> : none of them captures */
+				int kind = 0; /* 0 ahead, 1 behind, 2 atomic */
+				int neg = 0;
+				if (*P->p == '>') { kind = 2; P->p++; }
+				else if (*P->p == '<') { kind = 1; neg = P->p[1] == '!'; P->p += 2; }
+				else { neg = *P->p == '!'; P->p++; }
+				if (++P->depth > 200) { perr(P, "nesting too deep"); return NULL; }
+				node *body = parse_alt(P, inner);
+				P->depth--;
+				if (P->failed) { nfree(body); return NULL; }
+				if (P->p >= P->end || *P->p != ')') { perr(P, "missing )"); nfree(body); return NULL; }
+				P->p++;
+				node *g = nnew(kind == 2 ? N_ATOMIC : N_LOOK);
+				g->ahead = kind == 0;
+				g->neg = neg;
+				nadd(g, body);
+				return g;
+			} else if (*P->p == '<' || *P->p == '|' ||
 			           *P->p == 'R' || *P->p == '(' || c_isdigit(*P->p) || *P->p == '&' ||
 			           *P->p == 'C' || *P->p == '+') {
-				perr(P, "group construct not modelled (lookaround/atomic/recursion/conditional)");
+				perr(P, "group construct not modelled (recursion/conditional)");
 				return NULL;
 			} else {
 				/* inline options: (?i) (?-i) (?is-m) (?i:...) */
@@ -478,11 +498,22 @@ static node *parse_concat(parser *P, pflags *f)
 			int kind = f->ungreedy ? Q_LAZY : Q_GREEDY;
 			if (P->p < P->end && *P->p == '?') { kind = f->ungreedy ? Q_GREEDY : Q_LAZY; P->p++; }
 			else if (P->p < P->end && *P->p == '+') { kind = Q_POSSESSIVE; P->p++; }
-			if (a->type == N_ASSERT) { perr(P, "quantified assertion not modelled"); nfree(a); a = NULL; break; }
+			if (a->type == N_ASSERT || a->type == N_LOOK) { perr(P, "quantified assertion not modelled"); nfree(a); a = NULL; break; }
 			node *r = nnew(N_REP);
 			r->rmin = mn; r->rmax = mx; r->qkind = kind;
 			nadd(r, a);
 			a = r;
+			{ /* X*+ on anything but a single byte class is the atomic group (?>X*) */
+				const node *in = r->kid[0];
+				while (in->type == N_GROUP && !in->capturing) in = in->kid[0];
+				while ((in->type == N_CAT || in->type == N_ALT) && in->nkid == 1) in = in->kid[0];
+				if (kind == Q_POSSESSIVE && in->type != N_SET) {
+					r->qkind = Q_GREEDY;
+					node *at = nnew(N_ATOMIC);
+					nadd(at, r);
+					a = at;
+				}
+			}
 			break; /* "a{2}{3}" style stacking is not modelled: next loop iteration would see it as literal/err */
 		}
 		if (!a) break;
@@ -527,18 +558,47 @@ static uint64_t n_minlen(const node *n)
 		for (int i = 0; i < n->nkid; i++) { t = n_minlen(n->kid[i]); if (t < m) m = t; }
 		return m;
 	case N_REP: return (uint64_t)n->rmin * n_minlen(n->kid[0]);
-	case N_GROUP: return n_minlen(n->kid[0]);
+	case N_GROUP: case N_ATOMIC: return n_minlen(n->kid[0]);
+	case N_LOOK: return 0;
 	}
 	return 0;
 }
 
 static int n_nullable(const node *n) { return n_minlen(n) == 0; }
 
+/* 1 and *len if every match of n has the same length (what a lookbehind branch must have) */
+static int n_fixedlen(const node *n, uint64_t *len)
+{
+	uint64_t a, b;
+	switch (n->type) {
+	case N_EMPTY: case N_ASSERT: case N_LOOK: *len = 0; return 1;
+	case N_SET: *len = 1; return 1;
+	case N_CAT:
+		a = 0;
+		for (int i = 0; i < n->nkid; i++) { if (!n_fixedlen(n->kid[i], &b)) return 0; a += b; }
+		*len = a;
+		return 1;
+	case N_ALT:
+		if (!n_fixedlen(n->kid[0], &a)) return 0;
+		for (int i = 1; i < n->nkid; i++) if (!n_fixedlen(n->kid[i], &b) || b != a) return 0;
+		*len = a;
+		return 1;
+	case N_REP:
+		if (n->rmin != n->rmax || !n_fixedlen(n->kid[0], &a)) return 0;
+		*len = a * n->rmin;
+		return 1;
+	case N_GROUP: case N_ATOMIC: return n_fixedlen(n->kid[0], len);
+	}
+	return 0;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* program                                                                                     */
 /* ------------------------------------------------------------------------------------------ */
 
-enum { I_SET, I_SPLIT, I_JMP, I_REP, I_ASSERT, I_MATCH, I_CAP /* a capturing group closed */ };
+enum { I_SET, I_SPLIT, I_JMP, I_REP, I_ASSERT, I_MATCH, I_CAP /* a capturing group closed */,
+       I_LOOK /* a: LK_*, b: bytes to step back (lookbehind), c: pc behind the construct */, I_LOOKEND };
+enum { LK_AHEAD, LK_AHEAD_NEG, LK_BEHIND, LK_BEHIND_NEG, LK_ATOMIC };
 
 typedef struct { uint32_t op, a, b, c, d; } inst;
 
@@ -646,6 +706,52 @@ static void gen(go_regex *re, const node *n)
 		gen(re, n->kid[0]);
 		if (n->capturing) emit(re, I_CAP, 0, 0, 0, 0);
 		break;
+	case N_ATOMIC: {
+		uint32_t l = emit(re, I_LOOK, LK_ATOMIC, 0, 0, 0);
+		gen(re, n->kid[0]);
+		emit(re, I_LOOKEND, 0, 0, 0, 0);
+		if (!re->failed) re->prog[l].c = (uint32_t)re->nprog;
+		break;
+	}
+	case N_LOOK: {
+		if (n->ahead) {
+			uint32_t l = emit(re, I_LOOK, n->neg ? LK_AHEAD_NEG : LK_AHEAD, 0, 0, 0);
+			gen(re, n->kid[0]);
+			emit(re, I_LOOKEND, 0, 0, 0, 0);
+			if (!re->failed) re->prog[l].c = (uint32_t)re->nprog;
+			break;
+		}
+		/* lookbehind: every top-level branch has its own fixed length (PCRE's rule); (?<=a|bc) is (?:(?<=a)|(?<=bc)),
+		 * (?<!a|bc) is (?<!a)(?<!bc) */
+		const node *body = n->kid[0];
+		while (body->type == N_GROUP && !body->capturing) body = body->kid[0];
+		int nb = body->type == N_ALT ? body->nkid : 1;
+		uint32_t *jmps = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)nb);
+		for (int i = 0; i < nb && !re->failed; i++) {
+			const node *br = body->type == N_ALT ? body->kid[i] : body;
+			uint64_t len = 0;
+			if (!n_fixedlen(br, &len) || len > 65535) {
+				if (!re->failed && re->err) snprintf(re->err, re->errlen, "lookbehind assertion is not fixed length");
+				re->failed = 1;
+				break;
+			}
+			uint32_t split = 0;
+			if (!n->neg && i + 1 < nb) split = emit(re, I_SPLIT, 0, 0, 0, 0);
+			uint32_t l = emit(re, I_LOOK, n->neg ? LK_BEHIND_NEG : LK_BEHIND, (uint32_t)len, 0, 0);
+			gen(re, br);
+			emit(re, I_LOOKEND, 0, 0, 0, 0);
+			if (re->failed) break;
+			re->prog[l].c = (uint32_t)re->nprog;
+			if (!n->neg && i + 1 < nb) {
+				jmps[i] = emit(re, I_JMP, 0, 0, 0, 0);
+				re->prog[split].a = split + 1;
+				re->prog[split].b = (uint32_t)re->nprog;
+			}
+		}
+		if (!n->neg) for (int i = 0; i + 1 < nb && !re->failed; i++) re->prog[jmps[i]].a = (uint32_t)re->nprog;
+		free(jmps);
+		break;
+	}
 	case N_REP: gen_rep(re, n); break;
 	case N_ALT: {
 		/* split a1, L2 ; a1 ; jmp end ; L2: split a2, L3 ; ... ; an */
@@ -674,7 +780,8 @@ static int n_first(const node *n, bset *out, int *unknown)
 {
 	switch (n->type) {
 	case N_EMPTY: return 1;
-	case N_ASSERT: *unknown = 1; return 1; /* keep it simple: assertions disable the skip table */
+	case N_ASSERT: case N_LOOK: *unknown = 1; return 1; /* keep it simple: assertions disable the skip table */
+	case N_ATOMIC: return n_first(n->kid[0], out, unknown);
 	case N_SET: bs_or(out, &n->set); return 0;
 	case N_GROUP: return n_first(n->kid[0], out, unknown);
 	case N_CAT:
@@ -750,7 +857,7 @@ int go_nullable(const go_regex *re) { return re->nullable; }
 /* ------------------------------------------------------------------------------------------ */
 
 typedef struct { uint32_t pc; uint32_t kind; size_t sp, lo; int cap; /* was a capturing group set when this choice was pushed? */ } bt;
-enum { BT_PLAIN, BT_REP_GIVEBACK, BT_REP_TAKEMORE };
+enum { BT_PLAIN, BT_REP_GIVEBACK, BT_REP_TAKEMORE, BT_LOOK /* lo: LK_* kind, sp: position to return to, pc: behind the construct */ };
 
 typedef struct { bt *v; size_t n, cap; } btstack;
 
@@ -817,6 +924,30 @@ static int attempt(const go_regex *re, const uint8_t *s, size_t len, size_t at, 
 			else fail = 1;
 			break;
 		case I_JMP: pc = in->a; break;
+		case I_LOOK: {
+			size_t back = in->b;
+			if ((in->a == LK_BEHIND || in->a == LK_BEHIND_NEG) && sp < back) {
+				/* fewer bytes before sp than the branch needs (the subject begins at the moving search start): it cannot match */
+				if (in->a == LK_BEHIND) fail = 1; else pc = in->c;
+				break;
+			}
+			if (bt_push(st, in->c, BT_LOOK, sp, in->a, cap) < 0) return -1;
+			sp -= (in->a == LK_BEHIND || in->a == LK_BEHIND_NEG) ? back : 0;
+			pc++;
+			break;
+		}
+		case I_LOOKEND: {
+			/* the body matched: the choice points it left are dropped (an assertion / atomic group is never re-entered) */
+			size_t L = st->n;
+			while (L > 0 && st->v[L - 1].kind != BT_LOOK) L--;
+			if (L == 0) return -1; /* cannot happen: every LOOKEND has its frame */
+			bt fr = st->v[L - 1];
+			st->n = L - 1;
+			if (fr.lo == LK_AHEAD_NEG || fr.lo == LK_BEHIND_NEG) { cap = fr.cap; fail = 1; break; } /* negative assertion is false */
+			if (fr.lo != LK_ATOMIC) sp = fr.sp;                  /* assertions consume nothing */
+			pc++;
+			break;
+		}
 		case I_SPLIT:
 			if (bt_push(st, in->b, BT_PLAIN, sp, 0, cap) < 0) return -1;
 			pc = in->a;
@@ -847,6 +978,16 @@ static int attempt(const go_regex *re, const uint8_t *s, size_t len, size_t at, 
 			if (st->n == 0) return 0;
 			bt *t = &st->v[st->n - 1];
 			cap = t->cap; /* groups closed after this choice point are undone */
+			if (t->kind == BT_LOOK) {
+				/* the body of an assertion / atomic group failed for good */
+				int negative = t->lo == LK_AHEAD_NEG || t->lo == LK_BEHIND_NEG;
+				uint32_t cont = t->pc;
+				size_t back_to = t->sp;
+				st->n--;
+				if (!negative) continue;          /* positive assertion / atomic group: the failure goes on */
+				pc = cont; sp = back_to;           /* negative assertion holds: go on behind it */
+				break;
+			}
 			if (t->kind == BT_PLAIN) { pc = t->pc; sp = t->sp; st->n--; break; }
 			if (t->kind == BT_REP_GIVEBACK) {
 				/* t->sp: current end of the greedy run; give back one item */

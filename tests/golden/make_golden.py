@@ -121,6 +121,28 @@ KAT = [
     ("q2_nested_noncap", b"xy xzy xy\n", ["-O", "-l"], "x(?:(z)|)y"),
     ("q2_single", b"foo bar foo\n", ["-s", "-O", "-l"], "foo|(bar)"),
     ("q2_first_is_group", b"bar foo foo\n", ["-O", "-l"], "foo|(bar)"),
+    # look-arounds, atomic groups, possessive quantifiers (round 2: served by the device VM)
+    ("look_behind", b"foobar xbar foobar\n", ["-O", "-l"], "(?<=foo)bar"),
+    ("look_ahead", b"foobar foobaz foobar\n", ["-O", "-l"], "foo(?=bar)"),
+    ("look_ahead_neg", b"foobar foobaz foo\n", ["-O", "-l"], "foo(?!bar)"),
+    ("look_behind_neg", b"xbar bar ybar\n", ["-O", "-l"], "(?<!x)bar"),
+    ("look_behind_neg_lines", b"xbar bar\nybar\nbar\n", [], "(?<!x)bar"),
+    ("atomic", b"aaab aaa ab\n", ["-O", "-l"], "(?>a+)b"),
+    ("atomic_nomatch", b"aaab ab\n", ["-O", "-l"], "(?>a+)ab"),
+    ("possessive_set", b"aaab ab b\n", ["-O", "-l"], "a++b"),
+    ("possessive_group", b"ababc abab abc\n", ["-O", "-l"], "(?:ab)++c"),
+    ("possessive_group2", b"ababab\n", ["-O", "-l"], "(?:ab)*+ab"),
+    ("look_behind_alt", b"ad bcd cd xd\n", ["-O", "-l"], "(?<=a|bc)d"),
+    ("look_behind_neg_alt", b"ad bcd cd xd d\n", ["-O", "-l"], "(?<!a|bc)d"),
+    ("look_ahead_word", b"one three two four\n", ["-O", "-l"], r"\b(?=\w{3}\b)\w+"),
+    ("look_ahead_line", b"abcz\nabc\nazz\n", ["-O", "-l"], r"(?=.*z)a\w+"),
+    ("look_ahead_neg_line", b"xab y\nxab\n", ["-O", "-l"], r"x(?!.*y)\w*"),
+    ("look_behind_bol", b"ab,cd,ef\ngh\n", ["-O", "-l"], r"(?<=^|,)\w+"),
+    ("look_behind_icase", b"fooBAR FOObar\n", ["-O", "-l"], "(?i)(?<=FOO)bar"),
+    ("look_behind_digits", b"123-456 12-34 1234-5\n", ["-O", "-l"], r"(?<=\d{3})-\d+"),
+    ("q2_group_in_lookahead", b"foobar foobaz\n", ["-O", "-l"], "foo(?=(bar))"),
+    ("q2_group_in_neg_lookahead", b"ab b\n", ["-O", "-l"], "(?!(a))b"),
+    ("look_at_window_start", b"barfoobar\n", ["-O", "-l"], "(?<=foo)bar|bar"),
     ("bigalt", b"the quick brown fox jumps over the lazy dog\n" * 3, ["-O", "-l"],
      "fox|dog|the|quick|lazy|over|jumps|brown"),
 ]

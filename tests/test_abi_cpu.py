@@ -95,7 +95,7 @@ def test_engine_selection_and_filter():
 @pytest.mark.parametrize("pat,frag", [
     ("x*", "empty string"), ("", "empty string"), ("a|", "empty string"),
     ("a*", "empty string"), ("(?:a*)+b", "not supported"),
-    ("(", "missing )"), ("[a-", "missing terminating ]"), (r"\1", "back references"), ("(?=a)b", "not supported"),
+    ("(", "missing )"), ("[a-", "missing terminating ]"), (r"\1", "back references"), (r"(?<=\d+)x", "not fixed length"), ("(?(1)a|b)", "not supported"),
     ("a{3,2}", "quantifier"),
 ])
 def test_rejections_are_loud(pat, frag):

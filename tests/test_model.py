@@ -24,6 +24,8 @@ def test_compiled_programs_match_the_oracle(tmp_path):
         "(?U)a+b", "(?U)a+?b", "(?U)a{2,}", "(?U)\\w+ ", "(?U:a+)b", "(?U)a*b", "(?U)(?:ab)+c", "a(?U)b+c?", "(?x) a b c", "(?x)a +b",
         "(?xi)A B", "(?x)a b | b c", "a(?x) b c", "(?x)a{2} b", "(?x) [ab] {2} c", "a(?#hello)b", "(?#c)a|b(?#d)c", "a(?#x)+b",
         "foo|(bar)", "(x)?foo", "(?:(a)|b)+c", "(a)?ab", "(a)*b", "(a|b)", "x(?:(z)|)y", "a(b)?c", "(ab|a)c|b", "(?:a(b))?c", "((a)|b)x|c", "a(?:b|(c))+",
+        "(?<=a)b", "a(?=b)", "a(?!b)", "(?<!a)b", "(?>a+)b", "(?>a+)ab", "a++b", "(?:ab)++c", "(?:ab)*+ab", "(?<=a|bc)x", "(?<!a|bc)x",
+        "\\b(?=\\w{3}\\b)\\w+", "(?=.*c)a\\w+", "x(?!.*b)\\w*", "(?<=^|c)[ab]+", "(?i)(?<=AB)c", "a(?=(b))", "(?!(a))b", "(?<=ab)c|c", "(?>a|ab)c",
         "a+b+", "(?:a|b)+c", "^a.*c$", "\\bab\\b", "a.*?c", "[ab]+?c", "x*ab", "(?:ab)*c", "ab|abc|a", "a(?:b|bc)c"]
     import json
     kat = json.load(open(os.path.join(HERE, "golden", "kat.json")))
