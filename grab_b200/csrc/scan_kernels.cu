@@ -261,7 +261,7 @@ static __device__ __noinline__ uint32_t fixed_slow_row(const FixedParams &P, con
 template <int D, int K, bool EX>
 struct FixedEngine {
 	typedef FixedParams Params;
-	static constexpr bool kLookBehind = false, kLookAhead = D != 0;
+	static constexpr bool kLookBehind = false, kLookAhead = D != 0, kMergeCopies = false;
 	static __device__ __forceinline__ void prologue(const FixedParams &, uint8_t *) {}
 
 	// first sequence (in preference order) matching with its anchor byte at tile position p; 0: none
@@ -379,7 +379,7 @@ struct FixedEngine {
 template <int K, bool EX>
 struct Fixed3Engine {
 	typedef FixedParams Params;
-	static constexpr bool kLookBehind = false, kLookAhead = true;
+	static constexpr bool kLookBehind = false, kLookAhead = true, kMergeCopies = true;
 	static __device__ __forceinline__ void prologue(const FixedParams &, uint8_t *) {}
 
 	static __device__ __forceinline__ uint32_t word_flags(const FixedParams &P, uint32_t w, uint32_t s1, uint32_t s2)
@@ -442,7 +442,7 @@ struct Fixed3Engine {
 template <int D, int K, bool ALIGNED>
 struct FixedBEngine {
 	typedef FixedParams Params;
-	static constexpr bool kLookBehind = false, kLookAhead = true;
+	static constexpr bool kLookBehind = false, kLookAhead = true, kMergeCopies = true;
 	static constexpr int kA = GS_FB_A < K ? GS_FB_A : K; // tests [0, kA) in XOR form, [kA, K) in subtract form
 	static __device__ __forceinline__ void prologue(const FixedParams &, uint8_t *) {}
 
@@ -531,7 +531,7 @@ struct FixedBEngine {
 #endif
 struct HashEngine {
 	typedef HashParams Params;
-	static constexpr bool kLookBehind = false, kLookAhead = true;
+	static constexpr bool kLookBehind = false, kLookAhead = true, kMergeCopies = true;
 
 	static __device__ __forceinline__ void prologue(const HashParams &P, uint8_t *extra)
 	{
@@ -665,7 +665,7 @@ struct HashEngine {
 template <int NLO, int NHI, int NFO>
 struct RunEngine {
 	typedef RunParams Params;
-	static constexpr bool kLookBehind = true, kLookAhead = true;
+	static constexpr bool kLookBehind = true, kLookAhead = true, kMergeCopies = true;
 	static __device__ __forceinline__ void prologue(const RunParams &, uint8_t *) {}
 
 	static __device__ __forceinline__ uint32_t class_flags(const RunParams &P, uint32_t x)
@@ -972,7 +972,7 @@ struct RunEngine {
 struct NullParams { uint32_t unused; };
 struct NullEngine {
 	typedef NullParams Params;
-	static constexpr bool kLookBehind = false, kLookAhead = false;
+	static constexpr bool kLookBehind = false, kLookAhead = false, kMergeCopies = false;
 	static __device__ __forceinline__ void prologue(const NullParams &, uint8_t *) {}
 	template <class G>
 	static __device__ __forceinline__ void run(const NullParams &, const Slice &S, Emitter &E, uint32_t lane)
@@ -1040,9 +1040,17 @@ scan_kernel(const __grid_constant__ ScanArgs A, const __grid_constant__ typename
 		const bool ahead = Eng::kLookAhead && rest >= niter * 512u + kHalo;
 		uint8_t *dst = my + (size_t)slot * slot_bytes + kPre;
 		mbar_arrive_expect_tx(&c->full, bytes + (behind ? kHalo : 0u) + (ahead ? kHalo : 0u));
-		tma_load_1d(dst, reinterpret_cast<const void *>(d.src + begin), bytes, &c->full, policy);
-		if (behind) tma_load_1d(dst - kHalo, reinterpret_cast<const void *>(d.src + begin - kHalo), kHalo, &c->full, policy);
-		if (ahead) tma_load_1d(dst + niter * 512u, reinterpret_cast<const void *>(d.src + begin + niter * 512u), kHalo, &c->full, policy);
+		if constexpr (Eng::kMergeCopies) {
+			// the bytes before / after the slice are contiguous with it on both sides: ONE bulk copy.  (The issue-bound engines
+			// save ~20 instructions per extra copy; the HBM-bound pair filter keeps its 512-byte aligned slice copy -- an
+			// unaligned one re-reads the boundary sectors, measured +4 % DRAM traffic in round 1.)
+			const uint32_t pre = behind ? kHalo : 0u;
+			tma_load_1d(dst - pre, reinterpret_cast<const void *>(d.src + begin - pre), bytes + pre + (ahead ? kHalo : 0u), &c->full, policy);
+		} else {
+			tma_load_1d(dst, reinterpret_cast<const void *>(d.src + begin), bytes, &c->full, policy);
+			if (behind) tma_load_1d(dst - kHalo, reinterpret_cast<const void *>(d.src + begin - kHalo), kHalo, &c->full, policy);
+			if (ahead) tma_load_1d(dst + niter * 512u, reinterpret_cast<const void *>(d.src + begin + niter * 512u), kHalo, &c->full, policy);
+		}
 	};
 
 	if (lane == 0) {
