@@ -101,7 +101,7 @@ struct gscan_ctx {
 	// pinned result buffers handed to the caller (gscan_match arrays), recycled by gscan_free_matches
 	struct ResultBuf { void *p; size_t cap; bool lent; };
 	std::vector<ResultBuf> results;
-	DevBuf<uint32_t> unit_start, unit_out, blk;
+	DevBuf<uint32_t> unit_start, unit_out, blk, chain;
 	DevBuf<unsigned long long> cursor; // [0] cursor, then 2 x u32 totals behind it
 	DevBuf<uint8_t> pat_tables, hash_tables, vm_tables;
 	const uint32_t *vm_code = nullptr, *vm_sets = nullptr;
@@ -365,7 +365,7 @@ extern "C" void gscan_close(gscan_ctx *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->segs.release(); c->cand.release(); c->scratch.release(); c->ord.release(); c->out.release();
-	c->unit_start.release(); c->unit_out.release(); c->blk.release(); c->cursor.release(); c->pat_tables.release(); c->hash_tables.release(); c->vm_tables.release();
+	c->unit_start.release(); c->unit_out.release(); c->blk.release(); c->chain.release(); c->cursor.release(); c->pat_tables.release(); c->hash_tables.release(); c->vm_tables.release();
 	c->probe_sum.release(); c->needle.release();
 	c->pool_arena.release(); c->pool_tiles.release(); c->pool_units.release();
 	c->readback.release();
@@ -776,7 +776,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		CK(ctx, ctx->ord.ensure((size_t)total_cand));
 		CK(ctx, ctx->unit_start.ensure((size_t)b->n_units + 1));
 		CK(ctx, ctx->unit_out.ensure((size_t)b->n_units + 1));
-		CK(ctx, ctx->blk.ensure((size_t)nb_seg + nb_u + 4));
+		CK(ctx, ctx->blk.ensure((size_t)nb_seg + nb_u + (size_t)(total_cand / 2048 + 2) + 8));
 		ResolveArgs R;
 		R.tiles = b->d_tiles;
 		R.segs = ctx->segs.p;
@@ -799,6 +799,21 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		R.vm_sets = ctx->vm_sets;
 		R.vm_runstart = pat->prog.vm_runstart ? 1u : 0u;
 		R.flat = (mode == GSCAN_MODE_ALL && !pat->prog.use_vm && (pat->prog.kind == ENGINE_RUN || pat->prog.disjoint)) ? 1u : 0u;
+		// chain path: FIXED patterns whose replay is sequential (overlapping matches, or LINE mode) with many candidates per
+		// unit -- one thread per unit would walk them alone (a 1 GiB window of a log file with a million hits: seconds)
+		R.chain = 0; R.chain_levels = 0; R.chain_cap = 0; R.chain_buf = nullptr;
+		{
+			bool want = !R.flat && !dense && !pat->prog.use_vm && pat->prog.kind == ENGINE_FIXED && (mode == GSCAN_MODE_ALL || mode == GSCAN_MODE_LINE) &&
+			            total_cand >= 65536 && total_cand / std::max<uint64_t>(b->n_units, 1) >= 1024;
+			if (const char *e = getenv("GSCAN_CHAIN")) // tests: force the path on small inputs / switch it off
+				want = !R.flat && !dense && !pat->prog.use_vm && pat->prog.kind == ENGINE_FIXED && (mode == GSCAN_MODE_ALL || mode == GSCAN_MODE_LINE) && *e == '1' && total_cand > 0;
+			uint32_t levels = 1;
+			while ((1ull << levels) < total_cand) levels++;
+			if (want && (uint64_t)(levels + 2) * total_cand * 4 <= (4ull << 30)) {
+				CK(ctx, ctx->chain.ensure((size_t)(levels + 2) * (size_t)total_cand));
+				R.chain = 1; R.chain_levels = levels; R.chain_cap = (uint32_t)total_cand; R.chain_buf = ctx->chain.p;
+			}
+		}
 		R.run_min = (uint32_t)pat->prog.run_min;
 		for (int i = 0; i < 8; i++) R.bitmap[i] = dense ? pat->prog.first_set.w[i] : pat->prog.run_class.w[i];
 		R.vm_dense = dense ? 1u : 0u;

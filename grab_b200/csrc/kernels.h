@@ -52,6 +52,12 @@ struct ResolveArgs {
 	const uint32_t *vm_code; // general patterns: VM program (3 words per instruction) and byte classes (8 words each)
 	const uint32_t *vm_sets;
 	uint32_t vm_runstart; // candidates are run starts of `bitmap`: also try the search start itself when it lies inside a run
+	// chain path (FIXED patterns whose matches can overlap, or LINE mode, with many candidates per unit): the selected
+	// matches of a unit are the chain c0 -> next(c0) -> ..., next(i) = first candidate at or after where the search resumes
+	// behind i.  Pointer doubling marks every chain member in O(log n) passes over all candidates instead of one thread
+	// walking a huge unit alone.  chain_buf: chain_levels x chain_cap jump tables, then the mark and rank arrays.
+	uint32_t chain, chain_levels, chain_cap;
+	uint32_t *chain_buf;
 	uint32_t vm_dense;    // general pattern without a candidate filter: no candidate list, the walk offers every position whose byte
 	                      // is in `bitmap` (the first-byte set) to the VM
 	uint32_t flat;        // ALL mode, RUN or a FIXED pattern whose matches can never overlap, no VM: every candidate of a unit is a

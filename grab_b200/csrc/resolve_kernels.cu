@@ -372,6 +372,96 @@ __global__ void k_write_flat(const ResolveArgs R)
 	R.out[R.unit_out[c.unit] + idx] = r;
 }
 
+// ---- chain path: the per-unit replay as pointer doubling over all candidates (ResolveArgs::chain) ----
+constexpr uint32_t kChainEnd = 0xffffffffu;
+__device__ __forceinline__ uint32_t *chain_level(const ResolveArgs &R, uint32_t k) { return R.chain_buf + (size_t)k * R.chain_cap; }
+__device__ __forceinline__ uint32_t *chain_mark(const ResolveArgs &R) { return R.chain_buf + (size_t)R.chain_levels * R.chain_cap; }
+__device__ __forceinline__ uint32_t *chain_rank(const ResolveArgs &R) { return R.chain_buf + (size_t)(R.chain_levels + 1) * R.chain_cap; }
+
+// next(i): where the loop resumes behind match i (grab.cc:209; LINE mode: behind the line remainder, <= 511 bytes,
+// grab.cc:194-196), the guard of the next iteration (grab.cc:175), then the first candidate of the unit at or after it
+__global__ void k_chain_next(const ResolveArgs R)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= R.totals[0]) return;
+	const OutRec c = R.ord[i];
+	const DevUnit du = R.units[c.unit];
+	const uint64_t ulen = du.len;
+	uint64_t stop = (uint64_t)c.pos + c.len;
+	if (R.mode == GSCAN_MODE_LINE) {
+		const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
+		uint32_t a = 0;
+		while (stop + a < ulen && a < 511 && data[stop + a] != '\n') a++;
+		stop += a;
+	}
+	uint32_t nx = kChainEnd;
+	if (stop + R.minlen < ulen) {
+		uint32_t lo = i + 1, hi = R.unit_start[c.unit + 1]; // candidates are ordered by position inside the unit
+		while (lo < hi) {
+			const uint32_t mid = lo + ((hi - lo) >> 1);
+			if (R.ord[mid].pos < stop) lo = mid + 1; else hi = mid;
+		}
+		if (lo < R.unit_start[c.unit + 1]) nx = lo;
+	}
+	chain_level(R, 0)[i] = nx;
+}
+
+// level k: jump 2^k matches ahead
+__global__ void k_chain_double(const ResolveArgs R, uint32_t k)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= R.totals[0]) return;
+	const uint32_t *prev = chain_level(R, k - 1);
+	const uint32_t j = prev[i];
+	chain_level(R, k)[i] = j == kChainEnd ? kChainEnd : prev[j];
+}
+
+// the first candidate of every unit starts its chain (the guard before the first search: grab.cc:175)
+__global__ void k_chain_heads(const ResolveArgs R)
+{
+	const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= R.n_units) return;
+	const uint32_t first = R.unit_start[u];
+	if (first != R.unit_start[u + 1] && R.minlen < (uint64_t)R.units[u].len) chain_mark(R)[first] = 1u;
+}
+
+// descending levels: after level k every chain member whose distance from the head has no bit below k is marked.
+// Marks set by other threads of the same pass are harmless (whatever a marked candidate jumps to is on the chain too).
+__global__ void k_chain_spread(const ResolveArgs R, uint32_t k)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= R.totals[0]) return;
+	if (!chain_mark(R)[i]) return;
+	const uint32_t j = chain_level(R, k)[i];
+	if (j != kChainEnd) chain_mark(R)[j] = 1u;
+}
+
+// matches per unit from the exclusive scan of the marks (rank)
+__global__ void k_chain_count(const ResolveArgs R)
+{
+	const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= R.n_units) return;
+	const uint32_t first = R.unit_start[u], end = R.unit_start[u + 1];
+	uint32_t n = 0;
+	if (first != end) n = chain_rank(R)[end - 1] + chain_mark(R)[end - 1] - chain_rank(R)[first];
+	R.unit_out[u] = n;
+}
+
+__global__ void k_chain_write(const ResolveArgs R)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= R.total_cand) return;
+	if (!chain_mark(R)[i]) return;
+	const OutRec c = R.ord[i];
+	const DevUnit du = R.units[c.unit];
+	const uint32_t k = chain_rank(R)[i] - chain_rank(R)[R.unit_start[c.unit]];
+	FinalRec r;
+	r.start = du.base_off + c.pos;
+	r.file_id = du.file_id;
+	r.len = c.len;
+	R.out[R.unit_out[c.unit] + k] = r;
+}
+
 // general patterns: every match starts at a candidate (a leading-byte prefix hit).  The count pass runs the VM
 // and records the outcome in the candidate array, the write pass only copies.  Own kernel: the VM's backtrack
 // stack is thread-local memory, so occupancy is capped to keep the reservation small.
@@ -519,6 +609,14 @@ __global__ void k_u32_exclusive(uint32_t *v, uint32_t n, const uint32_t *blk)
 		if (base + i < n) { v[base + i] = p; p += x[i]; }
 }
 
+__global__ void k_fill_zero(uint32_t *p, uint32_t n)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) p[i] = 0u;
+	if (i + gridDim.x * blockDim.x < n) p[i + gridDim.x * blockDim.x] = 0u;
+}
+static uint32_t *chain_mark_host(const ResolveArgs &R) { return R.chain_buf + (size_t)R.chain_levels * R.chain_cap; }
+
 cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t *launches)
 {
 	uint32_t nl = 0;
@@ -528,11 +626,27 @@ cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t
 		k_scan_blk<<<1, kScanBlock, 0, st>>>(R.blk, nb_seg, R.totals, R.unit_start + R.n_units); nl++;
 		k_gather<<<nb_seg, kScanBlock, 0, st>>>(R); nl++;
 	}
-	if (R.engine == GSCAN_ENGINE_VM) k_walk_vm<false><<<(R.n_units + 63) / 64, 64, 0, st>>>(R);
-	else k_walk<false><<<(R.n_units + 127) / 128, 128, 0, st>>>(R);
-	nl++;
 	const uint32_t nb_u = (R.n_units + kPerBlock - 1) / kPerBlock;
 	uint32_t *blk2 = R.blk + nb_seg + 1; // block sums of the per-unit counts live behind the segment block sums
+	if (R.chain) {
+		// grids cover the reserved candidate slots; the kernels stop at the exact count (totals[0], on the device by now)
+		const uint32_t nb_c = (R.chain_cap + 255) / 256, nb_cs = (R.chain_cap + kPerBlock - 1) / kPerBlock;
+		uint32_t *blk3 = blk2 + nb_u + 1;
+		k_fill_zero<<<nb_c, 256, 0, st>>>(chain_mark_host(R), 2u * R.chain_cap); nl++; // marks and ranks
+		k_chain_next<<<nb_c, 256, 0, st>>>(R); nl++;
+		for (uint32_t k = 1; k < R.chain_levels; k++) { k_chain_double<<<nb_c, 256, 0, st>>>(R, k); nl++; }
+		k_chain_heads<<<(R.n_units + 255) / 256, 256, 0, st>>>(R); nl++;
+		for (uint32_t k = R.chain_levels; k-- > 0;) { k_chain_spread<<<nb_c, 256, 0, st>>>(R, k); nl++; }
+		cudaMemcpyAsync(chain_mark_host(R) + R.chain_cap, chain_mark_host(R), (size_t)R.chain_cap * 4, cudaMemcpyDeviceToDevice, st);
+		k_u32_sums<<<nb_cs, kScanBlock, 0, st>>>(chain_mark_host(R) + R.chain_cap, R.chain_cap, blk3); nl++;
+		k_scan_blk<<<1, kScanBlock, 0, st>>>(blk3, nb_cs, R.totals + 3, nullptr); nl++;
+		k_u32_exclusive<<<nb_cs, kScanBlock, 0, st>>>(chain_mark_host(R) + R.chain_cap, R.chain_cap, blk3); nl++;
+		k_chain_count<<<(R.n_units + 255) / 256, 256, 0, st>>>(R); nl++;
+	} else {
+		if (R.engine == GSCAN_ENGINE_VM) k_walk_vm<false><<<(R.n_units + 63) / 64, 64, 0, st>>>(R);
+		else k_walk<false><<<(R.n_units + 127) / 128, 128, 0, st>>>(R);
+		nl++;
+	}
 	k_u32_sums<<<nb_u, kScanBlock, 0, st>>>(R.unit_out, R.n_units, blk2); nl++;
 	k_scan_blk<<<1, kScanBlock, 0, st>>>(blk2, nb_u, R.totals + 1, nullptr); nl++;
 	k_u32_exclusive<<<nb_u, kScanBlock, 0, st>>>(R.unit_out, R.n_units, blk2); nl++;
@@ -542,6 +656,11 @@ cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t
 
 cudaError_t launch_resolve_write(const ResolveArgs &R, cudaStream_t st, uint32_t *launches)
 {
+	if (R.chain) {
+		k_chain_write<<<(R.total_cand + 255) / 256, 256, 0, st>>>(R);
+		if (launches) *launches = 1;
+		return cudaGetLastError();
+	}
 	if (R.flat) {
 		k_write_flat<<<(R.total_cand + 255) / 256, 256, 0, st>>>(R);
 		if (launches) *launches = 1;

@@ -121,7 +121,7 @@ static void candidates(const Program &p, const uint8_t *s, size_t len, std::vect
 	}
 }
 
-static int g_flat_checks = 0;
+static int g_flat_checks = 0, g_chain_checks = 0;
 // count pass, slot scan (one unit: slot 0), write pass -- the device code of resolve_kernels.cu, on the host.
 // 0 ok, -1 VM limit
 static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, std::vector<M> &out)
@@ -178,6 +178,37 @@ static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, s
 		for (uint32_t i = 0; same && i < n; i++) same = ff[i].start == fin[i].start && ff[i].len == fin[i].len;
 		if (!same) return -3;
 		g_flat_checks++;
+	}
+	// the chain path (pointer doubling over the candidates) wherever it applies: same records as the serial replay
+	if (!p.use_vm && p.kind == ENGINE_FIXED && (mode == GSCAN_MODE_ALL || mode == GSCAN_MODE_LINE) && !ord.empty()) {
+		const uint32_t cap = (uint32_t)ord.size();
+		uint32_t levels = 1;
+		while ((1u << levels) < cap) levels++;
+		std::vector<uint32_t> buf((size_t)(levels + 2) * cap, 0u);
+		R.flat = 0;
+		R.chain = 1; R.chain_levels = levels; R.chain_cap = cap; R.chain_buf = buf.data();
+		totals[0] = cap;
+		R.out = nullptr;
+		auto each = [&](auto fn) { for (uint32_t i = 0; i < cap; i++) { model_threadIdx.x = i; fn(); } model_threadIdx.x = 0; };
+		each([&] { k_chain_next(R); });
+		for (uint32_t k = 1; k < levels; k++) each([&] { k_chain_double(R, k); });
+		model_threadIdx.x = 0;
+		k_chain_heads(R);
+		for (uint32_t k = levels; k-- > 0;) each([&] { k_chain_spread(R, k); });
+		uint32_t *mark = buf.data() + (size_t)levels * cap, *rank = mark + cap;
+		uint32_t acc = 0;
+		for (uint32_t i = 0; i < cap; i++) { rank[i] = acc; acc += mark[i]; } // the device uses its block-scan kernels here
+		k_chain_count(R);
+		const uint32_t nc = unit_out[0];
+		unit_out[0] = 0;
+		std::vector<FinalRec> fc(nc + 1);
+		R.out = fc.data();
+		R.total_cand = cap;
+		each([&] { k_chain_write(R); });
+		bool same = nc == n;
+		for (uint32_t i = 0; same && i < n; i++) same = fc[i].start == fin[i].start && fc[i].len == fin[i].len;
+		if (!same) return -4;
+		g_chain_checks++;
 	}
 	return 0;
 }
@@ -239,6 +270,7 @@ int main(int argc, char **argv)
 				std::vector<M> g2;
 				const int wrc = walk(p, sb.data(), sb.size(), dmodes[m], g2);
 				if (wrc == -3) { printf("FLAT WALK MISMATCH %s\n", pat.c_str()); bad++; go_matches_free(&w2); continue; }
+				if (wrc == -4) { printf("CHAIN WALK MISMATCH %s mode %d\n", pat.c_str(), m); bad++; go_matches_free(&w2); continue; }
 				if (wrc != 0) { go_matches_free(&w2); n_limit++; continue; }
 				bool ok = g2.size() == w2.n;
 				for (size_t i = 0; ok && i < g2.size(); i++) ok = g2[i].pos == w2.v[i].start && g2[i].len == w2.v[i].len;
@@ -285,7 +317,7 @@ int main(int argc, char **argv)
 		}
 		go_free(re);
 	}
-	printf("dense VM patterns %d; ", n_dense);
+	printf("chain checks %d; dense VM patterns %d; ", g_chain_checks, n_dense);
 	printf("flat write checks %d; strict (Q2) patterns %d; ", g_flat_checks, n_strict);
 	printf("patterns %d, served %d (%d through the VM), comparisons %d + %d through the walk kernels, limit skips %d, mismatches %d\n", n_pat, n_served, n_vm, n_cmp, n_walk, n_limit, bad);
 	if (bad == 0) printf("model ok\n");
