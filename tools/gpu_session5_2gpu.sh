@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 O=gpurun_out/s5
 mkdir -p $O
 nvidia-smi -L > $O/gpus.txt 2>&1
-timeout 600 python -m pytest tests/test_gpu_nccl.py tests/test_cli.py -m gpu -x -q > $O/pytest_nccl.txt 2>&1; echo "pytest rc=$?" >> $O/pytest_nccl.txt; tail -4 $O/pytest_nccl.txt
+timeout 900 python -m pytest tests/test_gpu_nccl.py tests/test_cli.py tests/test_gpu_shapes.py -m gpu -x -q -k 'nccl or cli or chain or async' > $O/pytest_nccl.txt 2>&1; echo "pytest rc=$?" >> $O/pytest_nccl.txt; tail -4 $O/pytest_nccl.txt
 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > $O/bench_n2.json 2> $O/bench_n2.err; echo "bench n2 rc=$?"; tail -8 $O/bench_n2.err
 python - <<'PY'
 import json
