@@ -401,6 +401,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if a.impl == "reference":
         return run_reference(a, rank, world)
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner ignores NCCL_DEBUG_FILE)
+    # goes to stderr instead -- the real stdout is kept aside for the line
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import multiprocessing as mp
     pool = mp.get_context("spawn").Pool(min(32, max(2, usable_cores() // max(world, 1))))  # before CUDA is touched: parity workers
@@ -715,7 +720,7 @@ def main():
         line["invalid"] = "parity gate failed: %s -- no value reported" % line["parity"]
         line["value"] = None
     if rank == 0:
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if bad:
         sys.exit(3)
 
