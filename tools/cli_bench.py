@@ -14,7 +14,7 @@ import bench  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 ngpu = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-d = bench.materialise_sample(n)
+d = bench.materialise(bench.baseline_configs()[1], n)
 
 
 def timed(name, cmd, nbytes, env=None, reps=3):

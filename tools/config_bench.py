@@ -35,7 +35,7 @@ hunits = np.zeros(e_files, dtype=G.UNIT_DTYPE)
 hunits["ptr"] = hptr + np.arange(e_files, dtype=np.uint64) * np.uint64(FILE_LEN)
 hunits["len"] = FILE_LEN
 hunits["file_id"] = np.arange(e_files, dtype=np.uint32)
-sample = bench.materialise_sample(cpu_files, from_device=(ctx, d))
+sample = bench.materialise(bench.baseline_configs()[1], cpu_files, from_device=(ctx, d))
 cores = bench.reference_cores()
 try:
     for name, pat, literal in (("configs[1] literal", bench.PATTERN, True), ("configs[2] alternation (non-capturing spelling)", "foo|bar|baz|quux", False),
