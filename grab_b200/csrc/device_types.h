@@ -33,7 +33,10 @@ typedef Geom<16, 3, 4096> GeomStream;  // memory-bound: the FIXED filters
 typedef Geom<GS_BAL_W, GS_BAL_R, GS_BAL_S> GeomBalanced;
 // hashed engine: issue-bound, wants warps (20 = 5 per scheduler measured best; 16, 18 and 22 were 8-10 % slower) and
 // long slices (fewer ring refills per byte): 2 x 4 KiB per warp, which leaves 32 KiB for the table
-typedef Geom<20, 2, 4096> GeomHash;
+#ifndef GS_HASH_W
+#define GS_HASH_W 20
+#endif
+typedef Geom<GS_HASH_W, 2, 4096> GeomHash;
 // balanced pair filter (FixedBEngine): issue-bound like the hashed engine
 #ifndef GS_PAIR_W
 #define GS_PAIR_W 20
@@ -96,6 +99,17 @@ struct HashParams {
 	uint32_t stride;     // bytes between slots in shared memory: 128 when the table is replicated per bank, else 4
 	uint32_t neg1;       // == 0xffffffff, opaque to the compiler: h * neg1 + entry is an IMAD (FMA pipe) where a XOR would be ALU
 	uint32_t pow2_shift, pow2_mask; // power-of-two replicated table: row offset = (h >> pow2_shift) & pow2_mask (0: not a power of two)
+	// class prefilter (sparse path): every key byte lies in [pre_lo, pre_hi] (one range inside 0x01-0x7d); a position can
+	// only hold a key when its hash_len bytes all pass x in [pre_lo, pre_hi + 1] -- tested SWAR, the table is then probed
+	// at the surviving positions only.  pre_enable == 0: no usable range, every position is probed (dense path).
+	uint32_t one;        // == 1, opaque: x * one + c issues as IMAD
+	uint32_t hash_len;   // key bytes (2 or 3)
+	uint32_t pre_enable;
+	uint32_t pre_ge, pre_gt;  // (0x80 - lo) x4, (0x7e - hi) x4: bit 7 of x + pre_ge set and of x + pre_gt clear <=> lo <= x <= hi + 1
+	uint32_t pre_mul[7];      // 1 << (25 + k): umulhi(flags, pre_mul[k]) == flags >> (7 - k) on the FMA pipe
+	const uint4 *tail;        // [nslots] {mask_lo, val_lo, mask_hi, val_hi}: bytes 0..7 behind a key position must satisfy
+	                          // ((y_lo ^ val_lo) & mask_lo) | ((y_hi ^ val_hi) & mask_hi) == 0 for ANY alternative of the key to
+	                          // match (all-zero masks: no cheap statement) -- drops most key hits before the verification
 	const uint32_t *table;      // [nslots] h of the slot's key, or 0xffffffff (copied to shared memory at kernel start)
 	const uint32_t *slot_first; // [nslots] first index into slot_seqs
 	const uint32_t *slot_count; // [nslots]
@@ -112,7 +126,10 @@ constexpr int kHashMaxSlots = 8192;
 // 16 lookups per 512-byte row that alone caps the kernel near 4 TB/s).  512 slots x 128 bytes = 64 KiB, beside a 20-warp ring
 // of 2 x 4 KiB slots
 constexpr uint32_t kHashReplicatedSlots = 512;
-static inline uint32_t hash_table_copies(uint32_t nslots) { return nslots <= kHashReplicatedSlots ? 32u : 1u; }
+#ifndef GS_HASH_COPIES
+#define GS_HASH_COPIES 32
+#endif
+static inline uint32_t hash_table_copies(uint32_t nslots) { return nslots <= kHashReplicatedSlots ? (uint32_t)GS_HASH_COPIES : 1u; }
 
 struct RunParams {
 	uint32_t one;         // == 1, opaque (see FixedParams)

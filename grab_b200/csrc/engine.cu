@@ -253,6 +253,24 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 			}
 			H.uniform_len = F.uniform_len;
 			H.maxlen = F.maxlen;
+			// class prefilter of the sparse path: one byte range that holds every key byte
+			H.one = 1;
+			H.hash_len = (uint32_t)pr.hash_len;
+			uint32_t lo = 255, hi = 0;
+			for (uint32_t k : pr.hash_table) {
+				if (k == 0xffffffffu) continue;
+				for (int i = 0; i < pr.hash_len; i++) {
+					const uint32_t b = (k >> (8 * i)) & 0xffu;
+					lo = std::min(lo, b);
+					hi = std::max(hi, b);
+				}
+			}
+			const char *pre_off = getenv("GSCAN_HASH_PRE");
+			H.pre_enable = lo >= 1 && hi <= 0x7d && hi - lo < 48 && !(pre_off && *pre_off == '0');
+			H.pre_ge = (0x80u - lo) * 0x01010101u;
+			H.pre_gt = (0x7eu - hi) * 0x01010101u;
+			for (int k = 0; k < 7; k++) H.pre_mul[k] = 1u << (25 + k);
+			H.tail = nullptr;
 		}
 	} else if (pr.kind == ENGINE_RUN) {
 		RunParams &R = p->run;
@@ -650,7 +668,8 @@ static int ensure_pattern(gscan_ctx *ctx, const gscan_pattern *pat)
 		if (pat->prog.use_hash) {
 			const Program &pr = pat->prog;
 			const size_t nt = pr.hash_table.size() * 4, ns = pr.slot_seqs.size() * 4;
-			CK(ctx, ctx->hash_tables.ensure(3 * nt + ns + 64));
+			const size_t ns16 = (ns + 15) & ~(size_t)15; // the tail table behind it is read as uint4
+			CK(ctx, ctx->hash_tables.ensure(3 * nt + ns16 + 4 * nt + 64));
 			uint8_t *h = ctx->hash_tables.p;
 			std::vector<uint32_t> hashed(pr.hash_table.size()); // the device table holds the hash of the slot's key
 			for (size_t i = 0; i < hashed.size(); i++)
@@ -659,8 +678,40 @@ static int ensure_pattern(gscan_ctx *ctx, const gscan_pattern *pat)
 			CK(ctx, cudaMemcpyAsync(h + nt, pr.slot_first.data(), nt, cudaMemcpyHostToDevice, ctx->stream));
 			CK(ctx, cudaMemcpyAsync(h + 2 * nt, pr.slot_count.data(), nt, cudaMemcpyHostToDevice, ctx->stream));
 			if (ns) CK(ctx, cudaMemcpyAsync(h + 3 * nt, pr.slot_seqs.data(), ns, cudaMemcpyHostToDevice, ctx->stream));
+			// tail table: what the 7 bytes at a key position must look like for ANY alternative of the key to match -- byte i is
+			// pinned when every alternative of the slot has an exact byte there and they agree (i below their shortest length)
+			std::vector<uint32_t> tail(pr.hash_table.size() * 4, 0u);
+			for (size_t sl = 0; sl < pr.hash_table.size(); sl++) {
+				if (pr.hash_table[sl] == 0xffffffffu || pr.slot_count[sl] == 0) continue;
+				uint64_t mask = 0, val = 0;
+				for (int i = 0; i < 7; i++) { // byte 7 is never pinned: its val byte carries the length flag below
+					int byte = -1;
+					bool pinned = true;
+					for (uint32_t k = 0; k < pr.slot_count[sl] && pinned; k++) {
+						const Sequence &sq = pr.seqs[pr.slot_seqs[pr.slot_first[sl] + k]];
+						if ((size_t)i >= sq.size() || sq[i].count() != 1) { pinned = false; break; }
+						int b = 0;
+						while (!sq[i].has((unsigned)b)) b++;
+						if (byte >= 0 && byte != b) pinned = false;
+						byte = b;
+					}
+					if (pinned && byte >= 0) { mask |= 0xffull << (8 * i); val |= (uint64_t)byte << (8 * i); }
+				}
+				// the slot's only alternative, all literal, at most 7 bytes: the entry is the whole verification; byte 7 of val
+				// (never compared: its mask byte is 0) then carries the length
+				if (pr.slot_count[sl] == 1) {
+					const Sequence &sq = pr.seqs[pr.slot_seqs[pr.slot_first[sl]]];
+					bool lit = sq.size() <= 7;
+					for (size_t i = 0; lit && i < sq.size(); i++) lit = sq[i].count() == 1;
+					if (lit) val |= (uint64_t)sq.size() << 56;
+				}
+				tail[4 * sl + 0] = (uint32_t)mask; tail[4 * sl + 1] = (uint32_t)val;
+				tail[4 * sl + 2] = (uint32_t)(mask >> 32); tail[4 * sl + 3] = (uint32_t)(val >> 32);
+			}
+			CK(ctx, cudaMemcpyAsync(h + 3 * nt + ns16, tail.data(), 4 * nt, cudaMemcpyHostToDevice, ctx->stream));
 			CK(ctx, cudaStreamSynchronize(ctx->stream));
 			ctx->pat_hash = pat->hash;
+			ctx->pat_hash.tail = reinterpret_cast<const uint4 *>(h + 3 * nt + ns16);
 			ctx->pat_hash.table = reinterpret_cast<const uint32_t *>(h);
 			ctx->pat_hash.slot_first = reinterpret_cast<const uint32_t *>(h + nt);
 			ctx->pat_hash.slot_count = reinterpret_cast<const uint32_t *>(h + 2 * nt);

@@ -169,6 +169,7 @@ struct Emitter {
 	// dense pattern -- 35 % of all stall samples of the RUN kernel (profiles/r02_run16_v1_ncu.txt).  What a warp leaves
 	// unused of its last chunk is wasted (the host sizes for it); candidates of one slice stay contiguous.
 	uint32_t chunk_base = 0, chunk_left = 0;
+	uint32_t aux0 = 0, aux1 = 0; // engine-private state that lives across a warp's slices (hashed engine: dense-path back-off)
 
 	__device__ __forceinline__ void flush(const ScanArgs &A, uint32_t seg, uint32_t lane)
 	{
@@ -517,6 +518,9 @@ struct FixedBEngine {
 // are looked up in a perfect-hash table in shared memory -- exact membership, one multiply (FMA pipe),
 // one LDS and four ALU ops per position, independent of how many alternatives there are.  Only true
 // key hits are verified, against the alternatives that share the key, in preference order.
+// Two paths per 1 KiB block: DENSE (every position probed: 6.25 issue slots each) and, when all key bytes lie in one
+// narrow byte range, SPARSE (a SWAR class test first, the table probed only where three class bytes in a row leave a
+// key possible -- ~2 % of printable text); the kernel picks per block, see "sparse path" below.
 //
 // Small tables are replicated across the shared-memory banks: 32 copies (stride 128 B, lane l reads bank l: one
 // wavefront per lookup) up to 256 slots, 16 copies (two lanes per bank: two wavefronts) up to 512.  With a single
@@ -636,26 +640,194 @@ struct HashEngine {
 		}, lane);
 	}
 
+	// ---- sparse path ----------------------------------------------------------------------------------------------
+	// Probing every position costs ~6 issue slots each (155 instructions per 512-byte row measured, issue-bound at 0.45 of
+	// the HBM roofline).  When all key bytes lie in one narrow range (a set of lowercase words) most positions cannot hold
+	// a key at all: a SWAR class test -- 3 instructions per word, carry-tolerant, a superset -- leaves ~2 % of the positions of
+	// printable text, and only those are hashed and looked up, two per lane and round.  Text that passes the class test
+	// nearly everywhere (prose against lowercase keys) is noticed per block: the warp then runs the dense path for a
+	// while (8 .. 64 blocks, doubling) before it tries the class test again.
+	// A block is 1 KiB: every lane owns 32 CONTIGUOUS bytes (8 words + the word behind them).
+
+	// bit 7 of a byte set where lo <= byte <= hi + 1 may hold; never clear for a byte in [lo, hi] whatever its neighbours
+	// are (a carry out of a byte >= 0x80 below adds one to both sums: the upper bound is one too wide for that reason)
+	static __device__ __forceinline__ uint32_t pre_flags(const HashParams &P, uint32_t x)
+	{
+		return lop3<0x20>(x * P.one + P.pre_ge, x * P.one + P.pre_gt, kHigh); // a & ~b & 0x80808080
+	}
+	static __device__ __forceinline__ uint32_t bfind(uint32_t x) // index of the highest set bit, 0xffffffff for 0 (one FLO)
+	{
+		uint32_t r;
+		asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+		return r;
+	}
+	static __device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t n) // x << n, 0 for n >= 32
+	{
+		uint32_t r;
+		asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+		return r;
+	}
+	// Positions of a lane's 32 bytes whose hash_len bytes all pass the class test, INTERLEAVED: position 4k + j (word k,
+	// byte j) at bit 8j + k.  The flag words of the 8 text words only have to be shifted by 7 - k and added (IMAD.HI, FMA
+	// pipe), and "the flag of the next position at this position's bit" is one funnel shift for all 32 positions.
+	static __device__ __forceinline__ uint32_t pre_block(const HashParams &P, const uint32_t (&w)[9])
+	{
+		uint32_t c = pre_flags(P, w[7]);
+#pragma unroll
+		for (int k = 0; k < 7; k++) c = __umulhi(pre_flags(P, w[k]), P.pre_mul[k]) + c; // flags >> (7 - k): disjoint bits
+		const uint32_t r8 = pre_flags(P, w[8]); // bit 7: position 32, bit 15: position 33
+		// next(): bits 8j + k, j < 3 take bit 8(j + 1) + k; bit 24 + k takes bit k + 1, bit 31 the first position behind the lane
+		const uint32_t n1 = __funnelshift_r(c, lop3<0xCA>(0x7fu, c >> 1, r8), 8);
+		uint32_t f = c & n1;
+		if (P.hash_len == 3) f &= __funnelshift_r(n1, lop3<0xCA>(0x7fu, n1 >> 1, r8 >> 8), 8);
+		return f;
+	}
+#ifndef GS_HASH_PREMAX
+#define GS_HASH_PREMAX 12
+#endif
+	static constexpr uint32_t kPreMax = GS_HASH_PREMAX; // more flagged positions than this in one lane (of 32): the dense path is cheaper
+
+	// Rare (a key of the set really is in the block, one 1 KiB block in eight on printable noise): decide the lanes' key
+	// hits and append the matches in position order.  A key hit is first held against the slot's TAIL entry -- what the 8
+	// bytes at the position must look like for any alternative of that key to match: one 16-byte table load and the text
+	// from shared memory, against a chain of dependent global loads in verify() (the out-of-line verification used to be
+	// 40 % of the kernel's time).  For a slot with a single all-literal alternative of up to 7 bytes the tail entry IS the
+	// verification and carries the length; only other slots' survivors visit verify().
+	// hc: key hits in the interleaved layout of pre_block
+	static __device__ __noinline__ uint32_t slow_block(const HashParams &P, const uint8_t *tile, const uint8_t *gtile, uint32_t off,
+	                                                   uint32_t ulen, uint32_t tile_len, Cand *dst, uint32_t lane, uint32_t c0, uint32_t hc)
+	{
+		const uint8_t *lb = tile + c0; // the lane's 32 bytes in shared memory
+		// length of the match at linear position b of the lane's bytes (a key position), 0: none
+		auto len_at = [&](uint32_t b) -> uint32_t {
+			const uint8_t *wp = lb + (b & ~3u);
+			const uint32_t x0 = *reinterpret_cast<const uint32_t *>(wp), x1 = *reinterpret_cast<const uint32_t *>(wp + 4),
+			               x2 = *reinterpret_cast<const uint32_t *>(wp + 8);
+			const uint32_t sh = 8u * (b & 3u);
+			const uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh);
+			const uint32_t slot = slot_of(P, y0 * P.mulsh);
+			const uint4 te = __ldg(P.tail + slot);
+			if (((y0 ^ te.y) & te.x) | ((y1 ^ te.w) & te.z)) return 0u; // no alternative of this key matches here
+			const int p = (int)(c0 + b);
+			if (p >= (int)tile_len) return 0u;
+			const uint32_t simple = te.w >> 24; // the slot's only alternative, all literal: its length (the bytes just compared)
+			if (simple) return (unsigned long long)off + (unsigned)p + simple <= ulen ? simple : 0u;
+			return verify(P, gtile, off, ulen, p, slot);
+		};
+		uint32_t mm = 0, len_a = 0, bit_a = 32; // length of the lane's first match (a second one is decided again when emitted)
+		while (hc) {
+			const uint32_t t = bfind(hc);
+			hc ^= 1u << t;
+			const uint32_t b = (t & 7u) * 4u + (t >> 3);
+			const uint32_t len = len_at(b);
+			if (len) {
+				mm |= 1u << b;
+				if (b < bit_a) { bit_a = b; len_a = len; }
+			}
+		}
+		if (!__any_sync(0xffffffffu, mm != 0)) return 0;
+		return Emitter::emit_at(dst, mm, off + c0, [&](uint32_t b) -> uint32_t { return b == bit_a ? len_a : len_at(b); }, lane);
+	}
+
+	static __device__ __forceinline__ void load_row(const Slice &S, uint32_t c0, uint32_t (&w)[5])
+	{
+		const uint4 a = *reinterpret_cast<const uint4 *>(S.tile + c0);
+		w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+		w[4] = *reinterpret_cast<const uint32_t *>(S.tile + c0 + 16);
+	}
+
+	// every position probed (the path for sets without a usable byte range and for text the class test cannot thin out)
+	static __device__ __forceinline__ void dense_row(const HashParams &P, const uint8_t *tbl, const Slice &S, Emitter &E, uint32_t lane,
+	                                                 uint32_t c0)
+	{
+		uint32_t w[5], d[16];
+		load_row(S, c0, w);
+		const uint32_t mn = row_min(P, tbl, w, d);
+		if (__any_sync(0xffffffffu, mn == 0)) {
+			uint32_t hits = 0;
+#pragma unroll
+			for (int b = 0; b < 16; b++) hits |= (d[b] == 0u ? 1u : 0u) << b;
+			E.n += slow_row(P, tbl, S.gtile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, c0, w[0], w[1], w[2], w[3], w[4], hits);
+		}
+	}
+
+	// two 32-bit shared-memory loads at a and a + 4, executed only where on != 0 (the lanes that have no flagged position left
+	// in a probe round would otherwise all read word 7 of their 32 bytes: lanes l, l + 4, l + 8, ... on one bank, 8-way
+	// conflicts -- the shared-memory pipe was 85 % busy and the top stall reason, profiles/r02_lits100_sparse_v1_ncu.txt)
+	static __device__ __forceinline__ void lds2_if(uint32_t a, uint32_t on, uint32_t &x0, uint32_t &x1)
+	{
+		asm volatile(
+		    "{\n"
+		    ".reg .pred q;\n"
+		    "setp.ne.u32 q, %3, 0;\n"
+		    "@q ld.shared.u32 %0, [%2];\n"
+		    "@q ld.shared.u32 %1, [%2+4];\n"
+		    "}\n"
+		    : "=r"(x0), "=r"(x1) // left as they were where on == 0: the caller ignores what such a lane computes
+		    : "r"(a), "r"(on));
+	}
+
 	template <class G>
 	static __device__ __forceinline__ void run(const HashParams &P, const Slice &S, Emitter &E, uint32_t lane)
 	{
 		const uint8_t *tbl = S.extra + ((lane * 4u) & (P.stride - 1u)); // this lane's copy of the table
-		const uint32_t base = S.begin + lane * 16;
-		for (uint32_t it = 0; it < S.niter; it++) {
-			const uint32_t c0 = base + it * 512;
-			uint32_t w[5];
-			const uint4 a = *reinterpret_cast<const uint4 *>(S.tile + c0);
-			w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-			w[4] = *reinterpret_cast<const uint32_t *>(S.tile + c0 + 16);
-			uint32_t d[16];
-			const uint32_t mn = row_min(P, tbl, w, d);
-			if (__any_sync(0xffffffffu, mn == 0)) {
-				uint32_t hits = 0;
-#pragma unroll
-				for (int b = 0; b < 16; b++) hits |= (d[b] == 0u ? 1u : 0u) << b;
-				E.n += slow_row(P, tbl, S.gtile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, c0, w[0], w[1], w[2], w[3], w[4], hits);
+		uint32_t it = 0;
+		// E.aux0: blocks still to run dense before the class test is tried again, E.aux1: how many the last give-up asked for
+		// (doubling, 8 .. 64: prose against lowercase keys pays one wasted class test per 64 blocks, text that changes its
+		// character is re-probed within 8)
+		if (P.pre_enable) {
+			// the probe loop's constants in vector registers (as kernel parameters the compiler reloads them from the constant
+			// bank every round: issue slots).  z is zero in every lane, but the compiler cannot know (P.one is opaque)
+			const uint32_t z = (P.one - 1u) * lane;
+			const uint32_t mulsh = P.mulsh + z, nslots = P.nslots + z, stride = P.stride + z, k1 = P.one + z, k4 = k1 << 2;
+			while (it + 2 <= S.niter) {
+				if (E.aux0) { // warp-uniform
+					E.aux0--;
+					dense_row(P, tbl, S, E, lane, S.begin + it * 512 + lane * 16);
+					dense_row(P, tbl, S, E, lane, S.begin + (it + 1) * 512 + lane * 16);
+					it += 2;
+					continue;
+				}
+				const uint32_t c0 = S.begin + it * 512 + lane * 32;
+				const uint8_t *lb = S.tile + c0;
+				uint32_t w[9];
+				{
+					const uint4 a = *reinterpret_cast<const uint4 *>(lb), b = *reinterpret_cast<const uint4 *>(lb + 16);
+					w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+					w[8] = *reinterpret_cast<const uint32_t *>(lb + 32);
+				}
+				uint32_t c = pre_block(P, w);
+				if (__any_sync(0xffffffffu, __popc(c) > (int)kPreMax)) {
+					E.aux1 = E.aux1 ? (E.aux1 < 64u ? E.aux1 * 2u : 64u) : 8u;
+					E.aux0 = E.aux1;
+					continue; // this block and the next aux1 - 1 run dense
+				}
+				E.aux1 = 0;
+				it += 2;
+				uint32_t hc = 0;
+				const uint32_t lbr = smem_u32(lb) + z; // the block's shared-memory address in one register
+#pragma unroll 1
+				for (uint32_t round = 0; round < (kPreMax + 1) / 2; round++) {
+					// two flagged positions per lane and round: two independent chains of FLO -> LDS -> hash -> LDS in flight, one
+					// vote for both (a lane that has none left keeps what its registers held and hashes that: m is 0 for it)
+					const uint32_t on0 = c, t0 = bfind(c), m0 = shl_clamp(k1, t0);
+					c ^= m0;
+					const uint32_t on1 = c, t1 = bfind(c), m1 = shl_clamp(k1, t1);
+					c ^= m1;
+					uint32_t x0, x1, y0, y1;
+					lds2_if((t0 & 7u) * k4 + lbr, on0, x0, x1); // LOP3 + IMAD
+					lds2_if((t1 & 7u) * k4 + lbr, on1, y0, y1);
+					const uint32_t h0 = __funnelshift_r(x0, x1, t0 & 0x18u) * mulsh, h1 = __funnelshift_r(y0, y1, t1 & 0x18u) * mulsh;
+					const uint32_t e0 = *reinterpret_cast<const uint32_t *>(tbl + __umulhi(h0, nslots) * stride); // own bank: conflict free
+					const uint32_t e1 = *reinterpret_cast<const uint32_t *>(tbl + __umulhi(h1, nslots) * stride);
+					hc |= (e0 == h0 ? m0 : 0u) | (e1 == h1 ? m1 : 0u);
+					if (!__any_sync(0xffffffffu, c != 0)) break; // no lane has more than kPreMax: the loop bound is never the exit
+				}
+				if (__any_sync(0xffffffffu, hc != 0))
+					E.n += slow_block(P, S.tile, S.gtile, S.off, S.ulen, S.tile_len, E.scratch + E.n, lane, c0, hc);
 			}
 		}
+		for (; it < S.niter; it++) dense_row(P, tbl, S, E, lane, S.begin + it * 512 + lane * 16);
 	}
 };
 

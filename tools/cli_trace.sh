@@ -5,7 +5,7 @@ python - <<PY
 import sys,os
 sys.path.insert(0,os.getcwd())
 import bench
-d=bench.materialise_sample($N)
+d=bench.materialise(bench.baseline_configs()[1], $N)
 open('/tmp/cli_dir','w').write(d)
 PY
 D=$(cat /tmp/cli_dir)
