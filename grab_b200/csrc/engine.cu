@@ -6,6 +6,9 @@
 // device buffers and its last error string (FileGrep::why, grab.h:61-64).  Errors never throw
 // across the ABI and never abort: int 0 / -1 + message.
 #include <cuda_runtime.h>
+#include <unistd.h>
+
+#include <cerrno>
 
 #include <algorithm>
 #include <chrono>
@@ -426,7 +429,9 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 // ---- feed path for pageable host memory ----
 // A single memcpy into a pinned bounce buffer runs at ~8 GB/s, PCIe Gen5 takes ~55 GB/s: several helper threads
 // copy disjoint 4 MiB chunks into their own pinned buffers and queue the H2D copies on their own streams.
-struct StagePiece { const uint8_t *src; uint8_t *dst; size_t len; };
+// fd >= 0: the bytes are the `len` bytes at offset `foff` of that descriptor (GSCAN_UNIT_FD), read with pread() straight
+// into the bounce buffer: no mapping, no page faults in the helper threads, no munmap under mmap_lock afterwards
+struct StagePiece { const uint8_t *src; uint8_t *dst; size_t len; int fd; uint64_t foff; };
 // one bounce-buffer load: pieces [first, first + count) whose arena range [dst, dst + span) is at most kStageChunk --
 // many small units (1 MiB files) travel as ONE 4 MiB copy instead of four
 struct StageJob { size_t first, count; uint8_t *dst; size_t span; };
@@ -462,18 +467,32 @@ static int stage_pageable(gscan_ctx *ctx, const std::vector<StagePiece> &pieces)
 		ctx->lanes.push_back(l);
 	}
 	std::atomic<int> err{(int)cudaSuccess};
+	std::atomic<int> io_errno{0}; // first pread failure (GSCAN_UNIT_FD units); -1: the file ended early
 	auto work = [&](int t) {
 		cudaSetDevice(ctx->device);
 		gscan_ctx::StageLane &l = ctx->lanes[t];
 		bool used[2] = {false, false};
 		int k = 0;
-		for (size_t j = (size_t)t; j < jobs.size() && err.load() == (int)cudaSuccess; j += (size_t)want, k ^= 1) {
+		for (size_t j = (size_t)t; j < jobs.size() && err.load() == (int)cudaSuccess && !io_errno.load(); j += (size_t)want, k ^= 1) {
 			cudaError_t e = cudaSuccess;
 			if (used[k]) e = cudaEventSynchronize(l.ev[k]);
 			if (e == cudaSuccess) {
 				const StageJob &job = jobs[j];
-				for (size_t q = job.first; q < job.first + job.count; q++) // the gaps between units (256-byte alignment) travel as they are
-					memcpy(static_cast<uint8_t *>(l.buf[k]) + (pieces[q].dst - job.dst), pieces[q].src, pieces[q].len);
+				for (size_t q = job.first; q < job.first + job.count; q++) { // the gaps between units (256-byte alignment) travel as they are
+					uint8_t *to = static_cast<uint8_t *>(l.buf[k]) + (pieces[q].dst - job.dst);
+					if (pieces[q].fd < 0) { memcpy(to, pieces[q].src, pieces[q].len); continue; }
+					for (size_t done = 0; done < pieces[q].len;) {
+						const ssize_t r = pread(pieces[q].fd, to + done, pieces[q].len - done, (off_t)(pieces[q].foff + done));
+						if (r < 0 && errno == EINTR) continue;
+						if (r <= 0) {
+							int want_no = 0;
+							io_errno.compare_exchange_strong(want_no, r < 0 ? errno : -1);
+							break;
+						}
+						done += (size_t)r;
+					}
+				}
+				if (io_errno.load()) break;
 				e = cudaMemcpyAsync(job.dst, l.buf[k], job.span, cudaMemcpyHostToDevice, l.stream);
 			}
 			if (e == cudaSuccess) e = cudaEventRecord(l.ev[k], l.stream);
@@ -489,6 +508,8 @@ static int stage_pageable(gscan_ctx *ctx, const std::vector<StagePiece> &pieces)
 	for (auto &x : th) x.join();
 	if (err.load() != (int)cudaSuccess)
 		return fail(ctx, std::string("gscan: staging host memory: ") + cudaGetErrorString((cudaError_t)err.load()));
+	if (io_errno.load())
+		return fail(ctx, std::string("gscan: reading a descriptor unit: ") + (io_errno.load() < 0 ? "file shorter than the unit" : strerror(io_errno.load())));
 	return 0;
 }
 
@@ -527,7 +548,9 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 		const gscan_unit &u = units[i];
 		if (u.len == 0) continue;
 		if (u.len > (1ull << 31)) return fail(ctx, "gscan_batch_create: unit longer than 2 GiB (the reference's chunks are <= 1 GiB, grab.h:48)");
-		if (!u.ptr) return fail(ctx, "gscan_batch_create: unit with null pointer");
+		if (!u.ptr && !(u.flags & GSCAN_UNIT_FD)) return fail(ctx, "gscan_batch_create: unit with null pointer");
+		if ((u.flags & GSCAN_UNIT_FD) && ((u.flags & GSCAN_UNIT_DEVICE) || (intptr_t)u.ptr < 0 || (intptr_t)u.ptr > 0x7fffffff))
+			return fail(ctx, "gscan_batch_create: descriptor unit with a bad descriptor");
 		if (u.flags & GSCAN_UNIT_DEVICE) {
 			if ((uintptr_t)u.ptr & 15u) return fail(ctx, "gscan_batch_create: device unit pointer must be 16-byte aligned");
 		} else {
@@ -565,7 +588,9 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 			// pinned unit ended is taken to be pinned too (one driver query per contiguous run, not per unit; a
 			// wrong guess only costs speed: cudaMemcpyAsync stages pageable memory itself)
 			bool pinned;
-			if (prev_pinned_end && u.ptr == prev_pinned_end) {
+			if (u.flags & GSCAN_UNIT_FD) {
+				pinned = false;
+			} else if (prev_pinned_end && u.ptr == prev_pinned_end) {
 				pinned = true;
 			} else {
 				cudaPointerAttributes attr;
@@ -583,8 +608,10 @@ static int batch_create(gscan_ctx *ctx, const gscan_unit *units, size_t n_units,
 				}
 			} else {
 				// pageable memory (the reference's mmap windows): staged after this loop by the helper lanes
+				const bool is_fd = (u.flags & GSCAN_UNIT_FD) != 0;
 				for (uint64_t o = 0; o < u.len; o += kStageChunk)
-					jobs.push_back(StagePiece{u.ptr + o, dst + o, (size_t)std::min<uint64_t>(kStageChunk, u.len - o)});
+					jobs.push_back(StagePiece{is_fd ? nullptr : u.ptr + o, dst + o, (size_t)std::min<uint64_t>(kStageChunk, u.len - o),
+					                          is_fd ? (int)(intptr_t)u.ptr : -1, u.base_off + o});
 			}
 		}
 		DevUnit du;

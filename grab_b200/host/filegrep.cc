@@ -99,6 +99,8 @@ void FileGrep::config(const std::map<std::string, size_t> &config)
 	if (it != config.end() && it->second >= 1) d_ndev = (int)it->second;
 	it = config.find("lanes");
 	if (it != config.end() && it->second >= 1) d_lanes_per_dev = (int)it->second;
+	it = config.find("fd_budget");
+	if (it != config.end()) d_fd_budget = it->second;
 }
 
 int FileGrep::prepare(const std::string &regex)
@@ -119,6 +121,8 @@ void FileGrep::release(Window &w)
 {
 	if (w.map) munmap(w.map, w.clen); // grab.cc:215
 	w.map = nullptr;
+	if (w.fd >= 0) close(w.fd);
+	w.fd = -1;
 }
 
 int FileGrep::find(const char *path, const struct stat *st, int)
@@ -131,12 +135,22 @@ int FileGrep::find(const char *path, const struct stat *st, int)
 #ifdef __linux__
 	if (st->st_uid == d_my_uid || d_my_uid == 0) flags |= O_NOATIME; // grab.cc:139-143
 #endif
-	if ((fd = open(path, flags)) < 0) {
+	fd = open(path, flags);
+	if (fd < 0 && (errno == EMFILE || errno == ENFILE) && (!d_queue.empty() || d_pipe)) {
+		flush_quietly(); // queued descriptor windows are what holds the descriptors: print them and try again
+		fd = open(path, flags);
+	}
+	if (fd < 0) {
 		d_err = "FileGrep::find::open: " + std::string(strerror(errno));
 		return -1;
 	}
 	const off_t overlap = 0x1000; // grab.cc:151
 	const uint32_t seq = d_file_seq++;
+	// Without line output nothing on the host ever looks at the window's bytes: the window is queued as a descriptor
+	// and the engine's staging threads pread() it straight into their pinned buffers (GSCAN_UNIT_FD) -- no mapping, no
+	// page faults on it, no munmap.  With line output (the bytes around a match are printed) the window is mapped
+	// like the reference's (grab.cc:161).
+	const bool by_fd = !d_print_line && d_fd_budget >= 3 * 64;
 	for (off_t off = 0; off < st->st_size; off += ((off_t)d_chunk_size - overlap)) { // grab.cc:154
 		// -s: the reference stops reading a file once one of its windows printed (grab.cc:232-233).  The sequencer
 		// suppresses later windows anyway; not queueing them only saves the work when an earlier batch is already out
@@ -145,32 +159,53 @@ int FileGrep::find(const char *path, const struct stat *st, int)
 			if (d_pipe->have_done && d_pipe->done_seq == seq) break;
 		}
 		clen = (st->st_size - off < (off_t)d_chunk_size) ? (size_t)(st->st_size - off) : d_chunk_size;
-		void *m = mmap(nullptr, clen, PROT_READ, MAP_PRIVATE | MAP_NORESERVE, fd, off); // grab.cc:126-128,161
-		if (m == MAP_FAILED && errno == ENOMEM && (!d_queue.empty() || d_pipe)) {
-			// out of address space or mappings (vm.max_map_count) because queued windows are still mapped: the reference
-			// holds one window at a time -- print what is queued, which unmaps it, and try again
-			flush_quietly();
-			m = mmap(nullptr, clen, PROT_READ, MAP_PRIVATE | MAP_NORESERVE, fd, off);
-		}
-		if (m == MAP_FAILED) {
-			d_err = "FileGrep::find::mmap: " + std::string(strerror(errno));
-			close(fd);
-			return -1;
-		}
-		if (clen > 4 * 0x1000 && !d_single_match) posix_madvise(m, clen, POSIX_MADV_SEQUENTIAL); // grab.cc:168-169
 		Window w;
+		if (by_fd) {
+			const bool last = off + ((off_t)d_chunk_size - overlap) >= st->st_size;
+			w.fd = last ? fd : dup(fd); // the file's last window takes the descriptor along
+			if (w.fd < 0 && (errno == EMFILE || errno == ENFILE) && (!d_queue.empty() || d_pipe)) {
+				flush_quietly(); // queued windows hold descriptors: print them, which closes theirs, and try again
+				w.fd = dup(fd);
+			}
+			if (w.fd < 0) {
+				d_err = "FileGrep::find::dup: " + std::string(strerror(errno));
+				close(fd);
+				return -1;
+			}
+			if (last) fd = -1;
+#ifdef POSIX_FADV_WILLNEED
+			if (clen > 4 * 0x1000) posix_fadvise(w.fd, off, (off_t)clen, POSIX_FADV_WILLNEED); // start the read-ahead now (a no-op on tmpfs)
+#endif
+		} else {
+			void *m = mmap(nullptr, clen, PROT_READ, MAP_PRIVATE | MAP_NORESERVE, fd, off); // grab.cc:126-128,161
+			if (m == MAP_FAILED && errno == ENOMEM && (!d_queue.empty() || d_pipe)) {
+				// out of address space or mappings (vm.max_map_count) because queued windows are still mapped: the reference
+				// holds one window at a time -- print what is queued, which unmaps it, and try again
+				flush_quietly();
+				m = mmap(nullptr, clen, PROT_READ, MAP_PRIVATE | MAP_NORESERVE, fd, off);
+			}
+			if (m == MAP_FAILED) {
+				d_err = "FileGrep::find::mmap: " + std::string(strerror(errno));
+				close(fd);
+				return -1;
+			}
+			if (clen > 4 * 0x1000 && !d_single_match) posix_madvise(m, clen, POSIX_MADV_SEQUENTIAL); // grab.cc:168-169
+			w.map = static_cast<uint8_t *>(m);
+		}
 		w.path = path;
-		w.map = static_cast<uint8_t *>(m);
 		w.clen = clen;
 		w.off = (uint64_t)off;
 		w.file_seq = seq;
 		d_queue.push_back(std::move(w));
 		d_queued_bytes += clen;
-		// a batch is cut by bytes or by windows: every queued window is a live mapping, and a tree of tiny files would
-		// otherwise run into vm.max_map_count (65530) long before 256 MiB are queued
-		if ((d_queued_bytes >= d_batch_bytes || d_queue.size() >= max_windows_per_batch()) && submit() < 0) { close(fd); return -1; }
+		// a batch is cut by bytes or by windows: every queued window is a live mapping (or an open descriptor), and a tree of
+		// tiny files would otherwise run into vm.max_map_count (65530) long before 256 MiB are queued
+		if ((d_queued_bytes >= d_batch_bytes || d_queue.size() >= max_windows_per_batch()) && submit() < 0) {
+			if (fd >= 0) close(fd);
+			return -1;
+		}
 	}
-	close(fd);
+	if (fd >= 0) close(fd);
 	return 0;
 }
 
@@ -259,7 +294,8 @@ int FileGrep::submit()
 size_t FileGrep::max_windows_per_batch() const
 {
 	const size_t lanes = (size_t)(d_ndev * d_lanes_per_dev);
-	const size_t cap = 49152 / (2 * lanes + 1);
+	size_t cap = 49152 / (2 * lanes + 1);
+	if (!d_print_line && d_fd_budget >= 3 * 64 && d_fd_budget / (2 * lanes + 1) < cap) cap = d_fd_budget / (2 * lanes + 1); // descriptor windows
 	return cap < 8192 ? (cap < 64 ? 64 : cap) : 8192;
 }
 
@@ -324,11 +360,12 @@ void FileGrep::lane_main(int lane)
 		if (rc == 0) {
 			units.resize(b->windows.size());
 			for (size_t i = 0; i < units.size(); i++) {
-				units[i].ptr = b->windows[i].map;
+				const bool by_fd = b->windows[i].fd >= 0;
+				units[i].ptr = by_fd ? reinterpret_cast<const uint8_t *>((intptr_t)b->windows[i].fd) : b->windows[i].map;
 				units[i].len = b->windows[i].clen;
 				units[i].base_off = b->windows[i].off;
 				units[i].file_id = (uint32_t)i; // index of the window in this batch
-				units[i].flags = 0;
+				units[i].flags = by_fd ? GSCAN_UNIT_FD : 0u;
 			}
 			uint32_t mode = GSCAN_MODE_ALL;
 			if (d_print_line) mode = GSCAN_MODE_LINE;                 // resume after the printed line (grab.cc:188-209)
@@ -349,8 +386,10 @@ void FileGrep::lane_main(int lane)
 				gscan_stats st;
 				gscan_last_stats(ctx, &st);
 				char line[256];
-				snprintf(line, sizeof line, "gpu %d batch %llu: %zu windows, %.1f MiB, staging+h2d %.2f ms, scan kernel %.3f ms, resolve %.3f ms, call %.2f ms, %zu matches",
-				         device, (unsigned long long)b->seq, units.size(), (double)st.bytes_scanned / 1048576.0, st.h2d_ms,
+				size_t nfd = 0;
+				for (const Window &w : b->windows) nfd += w.fd >= 0 ? 1 : 0;
+				snprintf(line, sizeof line, "gpu %d batch %llu: %zu windows (%zu as descriptors), %.1f MiB, staging+h2d %.2f ms, scan kernel %.3f ms, resolve %.3f ms, call %.2f ms, %zu matches",
+				         device, (unsigned long long)b->seq, units.size(), nfd, (double)st.bytes_scanned / 1048576.0, st.h2d_ms,
 				         st.scan_kernel_ms, st.resolve_ms, st.total_ms, n);
 				trace_ts(line, lane);
 			}

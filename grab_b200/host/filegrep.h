@@ -54,12 +54,15 @@ public:
 	void batch_bytes(size_t n) { d_batch_bytes = n; }
 	void devices(int first, int count) { d_device = first; d_ndev = count < 1 ? 1 : count; } // lanes go to first..first+count-1
 	void lanes_per_device(int n) { d_lanes_per_dev = n < 1 ? 1 : n; }
+	// descriptors this object may keep open at once (queued descriptor windows); 0: map the windows like the reference
+	void fd_budget(size_t n) { d_fd_budget = n; }
 	int minlen() const { return d_minlen; }
 
 private:
 	struct Window {
 		std::string path;
-		uint8_t *map = nullptr;   // mmap'd window (grab.cc:161)
+		uint8_t *map = nullptr;   // mmap'd window (grab.cc:161); null for a descriptor window
+		int fd = -1;              // descriptor window: read by the engine's staging threads (GSCAN_UNIT_FD), closed in release()
 		size_t clen = 0;          // window length
 		uint64_t off = 0;         // file offset of the window
 		uint32_t file_seq = 0;    // which find() call the window belongs to (for -s early exit)
@@ -87,6 +90,7 @@ private:
 	std::vector<Window> d_queue;
 	size_t d_queued_bytes = 0;
 	size_t d_batch_bytes = (size_t)256 << 20;
+	size_t d_fd_budget = 0;
 	uint32_t d_file_seq = 0;
 };
 

@@ -18,6 +18,7 @@
 #include <fcntl.h>
 #include <pthread.h>
 #include <sched.h>
+#include <sys/resource.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -304,12 +305,33 @@ int run_single(Invocation &inv)
 	return status;
 }
 
+
+// Descriptor feed (no line output: windows are read by the engine's staging threads, not mapped): every queued window
+// holds a descriptor, so the soft limit is raised to the hard one and shared out over the scanners.
+// GRAB_B200_FEED=mmap keeps the reference's mappings.
+size_t descriptor_budget(int scanners)
+{
+	const char *feed = getenv("GRAB_B200_FEED");
+	if (feed && strcmp(feed, "mmap") == 0) return 0;
+	struct rlimit rl;
+	if (getrlimit(RLIMIT_NOFILE, &rl) != 0) return 0;
+	const rlim_t want = rl.rlim_max == RLIM_INFINITY || rl.rlim_max > 65536 ? 65536 : rl.rlim_max;
+	if (rl.rlim_cur < want) {
+		struct rlimit up = rl;
+		up.rlim_cur = want;
+		if (setrlimit(RLIMIT_NOFILE, &up) == 0) rl.rlim_cur = want;
+	}
+	if (rl.rlim_cur == RLIM_INFINITY) rl.rlim_cur = 65536;
+	return rl.rlim_cur > 128 ? (size_t)(rl.rlim_cur - 128) / (size_t)(scanners < 1 ? 1 : scanners) : 0;
+}
+
 } // namespace
 
 int main(int argc, char **argv)
 {
 	Invocation inv = parse(argc, argv);
 	inv.settings["chunk_size"] = inv.chunk;
+	inv.settings["fd_budget"] = descriptor_budget(inv.workers);
 	if (inv.workers > 1) return run_crew(inv);
 	return run_single(inv);
 }

@@ -43,10 +43,16 @@ typedef struct gscan_batch gscan_batch;
 /* ---- unit flags ------------------------------------------------------------------------ */
 #define GSCAN_UNIT_DEVICE 1u /* ptr is a device pointer on the context's GPU (16-byte aligned,
                                 readable up to the next 16-byte boundary past ptr+len) */
+#define GSCAN_UNIT_FD 2u     /* ptr carries an open file descriptor ((intptr_t)ptr); the window is the `len` bytes at file
+                                offset `base_off` of it.  Replaces the mmap of grab.cc:126-128,161 for callers that do not
+                                need the bytes themselves (no line output): the engine's staging threads pread() straight
+                                into their pinned bounce buffers -- no mapping, no page faults, no munmap (grab.cc:215)
+                                under mmap_lock.  The descriptor stays the caller's (not closed); a read error or a file
+                                shorter than base_off + len fails the call (the reference would take a SIGBUS) */
 
 /* One scan unit == one mmap window of grab.cc:154-169: `content`, `clen`, `off`. */
 typedef struct gscan_unit {
-	const uint8_t *ptr; /* window bytes (host, or device with GSCAN_UNIT_DEVICE)  grab.cc:161 */
+	const uint8_t *ptr; /* window bytes (host, or device with GSCAN_UNIT_DEVICE; a descriptor with GSCAN_UNIT_FD)  grab.cc:161 */
 	uint64_t len;       /* clen                                                  grab.cc:156-159 */
 	uint64_t base_off;  /* off: file offset of the window                        grab.cc:154 */
 	uint32_t file_id;   /* caller's id of the file the window belongs to */

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "../../include/gscan.h"
 #include "../../oracle/grab_oracle.h"
@@ -61,7 +62,24 @@ int gscan_scan_batch(gscan_ctx *ctx, const gscan_pattern *pat, const gscan_unit 
 	if (fail && atoi(fail) == ctx->device) { snprintf(ctx->err, sizeof ctx->err, "injected failure on device %d", ctx->device); return -1; }
 	for (size_t i = 0; i < n_units; i++) {
 		bytes += units[i].len;
-		if (go_scan_window(pat->re, units[i].ptr, units[i].len, units[i].base_off, units[i].file_id, (int)mode, pat->strict, &m) != 0) {
+		const uint8_t *ptr = units[i].ptr;
+		uint8_t *tmp = NULL;
+		if (units[i].flags & GSCAN_UNIT_FD) { /* descriptor unit: the window is read, not mapped */
+			ptr = tmp = malloc(units[i].len ? units[i].len : 1);
+			for (uint64_t done = 0; done < units[i].len;) {
+				ssize_t r = pread((int)(intptr_t)units[i].ptr, tmp + done, units[i].len - done, (off_t)(units[i].base_off + done));
+				if (r <= 0) {
+					snprintf(ctx->err, sizeof ctx->err, "gscan: reading a descriptor unit: %s", r < 0 ? "error" : "file shorter than the unit");
+					free(tmp);
+					go_matches_free(&m);
+					return -1;
+				}
+				done += (uint64_t)r;
+			}
+		}
+		const int src = go_scan_window(pat->re, ptr, units[i].len, units[i].base_off, units[i].file_id, (int)mode, pat->strict, &m);
+		free(tmp);
+		if (src != 0) {
 			snprintf(ctx->err, sizeof ctx->err, "oracle limit");
 			go_matches_free(&m);
 			return -1;

@@ -238,3 +238,40 @@ def test_host_good_path_then_missing_path(tmp_path):
     if os.path.exists(REF):
         rcr, ref_out, ref_err = run(["-O", "-l", "foo", "a", "nope"], cwd=str(tmp_path), binary=REF)
         assert (rcr, ref_out) == (rc, so) and ref_err == se
+
+
+@pytest.mark.parametrize("flags", [["-r", "-O", "-l"], ["-r", "-l"], ["-r", "-s", "-O", "-l"]], ids=lambda f: "".join(f))
+def test_host_descriptor_feed_equals_mapped_feed(flags, tmp_path):
+    """Without line output the windows travel as descriptors (GSCAN_UNIT_FD: read by the engine's staging threads, never
+    mapped); GRAB_B200_FEED=mmap keeps the reference's mappings.  Same bytes on stdout either way, also with a descriptor
+    limit so tight that batches are cut by descriptors (ulimit -n 400: about 90 windows per batch) and with one so tight
+    that the feed falls back to mappings (ulimit -n 200)."""
+    _tree(tmp_path)
+    pat = "foo|bar|baz|quux"
+    rc, mapped, se = run(flags + [pat, "tree"], cwd=str(tmp_path), env=dict(GRAB_B200_FEED="mmap"))
+    assert rc == 0, se
+    rc, by_fd, se = run(flags + [pat, "tree"], cwd=str(tmp_path), env=dict(GRAB_B200_TRACE="1"))
+    assert rc == 0 and by_fd == mapped, se
+    assert b"as descriptors)" in se and b"(0 as descriptors)" not in se
+    assert b"(0 as descriptors)" in run(flags + [pat, "tree"], cwd=str(tmp_path), env=dict(GRAB_B200_TRACE="1", GRAB_B200_FEED="mmap"))[2]
+    assert b"(0 as descriptors)" in run(["-r", "-O", pat, "tree"], cwd=str(tmp_path), env=dict(GRAB_B200_TRACE="1"))[2]  # line output: mapped
+    for limit in ("400", "200"):
+        sh = "ulimit -Hn %s; exec %s %s '%s' tree" % (limit, BIN, " ".join(flags), pat)
+        e = {k: v for k, v in os.environ.items() if not k.startswith("GRAB_B200_")}
+        p = subprocess.run(["bash", "-c", sh], stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=str(tmp_path), env=e, timeout=300)
+        assert p.returncode == 0 and p.stdout == mapped, (limit, p.stderr[-500:])
+
+
+def test_host_descriptor_feed_one_file_many_windows(tmp_path):
+    """One file cut into windows (chunk 32 MiB): every window of a descriptor feed holds its own descriptor (dup), the
+    last one the file's; stdout equals the mapped feed's and the oracle's FileGrep::find restatement (Q3 duplicates)."""
+    C = 1 << 25
+    size = 2 * C + 999
+    fn = str(tmp_path / "big.bin")
+    img = _big_file(fn, size, [1000, C - 4096 + 100, C - 3, size - 6])
+    args = ["-L"] * 5 + ["-O", "-l", "NEEDLE", fn]
+    rc, so, se = run(args)
+    assert rc == 0, se
+    assert so == O.Regex("NEEDLE").grab(img.tobytes(), offsets=True, line=False, single=False, chunk_size=C)
+    rc, mapped, se = run(args, env=dict(GRAB_B200_FEED="mmap"))
+    assert rc == 0 and mapped == so

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Times the two command lines on the same tmpfs tree: grab-b200 (GPU) and the unmodified reference (host cores),
 then on ONE file of the same bytes (the reference has a single thread there; grab-b200 spreads the file's windows
-over lanes / GPUs).  Usage: python tools/cli_bench.py [n_files] [n_gpus]"""
+over lanes / GPUs), then -- `patterns` given -- the other BASELINE patterns over the tree (the literal is the reference's
+best case: its PCRE2-JIT search is a memchr; alternations, class runs and literal sets are where its cores are busy).
+Usage: python tools/cli_bench.py [n_files] [n_gpus] [patterns]"""
 import os
 import shutil
 import subprocess
@@ -27,7 +29,7 @@ def timed(name, cmd, nbytes, env=None, reps=3):
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
         out = p.stdout
-    print("%-34s %7.3f s  %6.2f GB/s  rc=%d  lines=%d  sorted-md5=%s" % (
+    print("%-58s %7.3f s  %6.2f GB/s  rc=%d  lines=%d  sorted-md5=%s" % (
         name, best, nbytes / best / 1e9, p.returncode, out.count(b"\n"),
         __import__("hashlib").md5(b"\n".join(sorted(out.split(b"\n")))).hexdigest()[:12]), flush=True)
 
@@ -60,5 +62,14 @@ try:
     if ngpu > 1:
         timed("one file: grab-b200 (%d gpus)" % ngpu, [ours] + one, nbytes, dict(GRAB_B200_NDEV=str(ngpu)))
     timed("one file: grab_ref", [bench.REF_BIN] + one, nbytes, reps=1)
+    os.unlink(big)
+    if len(sys.argv) > 3:
+        for cfg in bench.baseline_configs()[2:]:
+            pat = cfg["pattern"]
+            args = ["-r", "-O", "-l", pat, d]
+            tag = cfg["key"] + " " + (pat if len(pat) < 24 else pat[:16] + "...")
+            timed(tag + ": grab-b200 (2 lanes)", [ours] + args, nbytes, dict(GRAB_B200_LANES="2"), reps=2)
+            timed(tag + ": grab_ref -n 32", [bench.REF_BIN, "-n", "32"] + args, nbytes, reps=1)
+            timed(tag + ": grab_ref -n 128", [bench.REF_BIN, "-n", "128"] + args, nbytes, reps=1)
 finally:
     shutil.rmtree(d, ignore_errors=True)
