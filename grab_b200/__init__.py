@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("GSCAN_LIB") or os.path.join(_HERE, "libgscan.so")  # 
 MODE_ALL, MODE_FIRST, MODE_LINE = 0, 1, 2
 LITERAL, STRICT_REF = 1, 2
 UNIT_DEVICE = 1
+UNIT_FD = 2  # ptr carries an open descriptor, the window is [base_off, base_off + len) of it (pread by the engine)
 ENGINE_FIXED, ENGINE_RUN, ENGINE_NONE, ENGINE_VM = 1, 2, 3, 4
 KERNEL_NONE, KERNEL_PAIR, KERNEL_TRIPLE, KERNEL_BALANCED, KERNEL_HASH, KERNEL_RUN = 0, 1, 2, 3, 4, 5
 
@@ -190,6 +191,19 @@ class Context:
             arr[i]["base_off"] = base_offs[i] if base_offs is not None else 0
             arr[i]["file_id"] = file_ids[i] if file_ids is not None else i
         return arr, keep
+
+    @staticmethod
+    def fd_units(windows, file_ids=None):
+        """windows: list of (descriptor, file offset, length): descriptor windows (GSCAN_UNIT_FD), read by the engine's
+        staging threads with pread() -- the descriptors stay the caller's and must stay open until the scan returns."""
+        arr = np.zeros(len(windows), dtype=UNIT_DTYPE)
+        for i, (fd, off, n) in enumerate(windows):
+            arr[i]["ptr"] = fd
+            arr[i]["len"] = n
+            arr[i]["base_off"] = off
+            arr[i]["file_id"] = file_ids[i] if file_ids is not None else i
+            arr[i]["flags"] = UNIT_FD
+        return arr
 
     @staticmethod
     def device_units(dptr, n_files, file_len, stride=None, first_file_id=0):

@@ -348,8 +348,18 @@ extern "C" int gscan_pattern_get_info(const gscan_pattern *p, gscan_pattern_info
 // ------------------------------------------------------------------------------------------
 extern "C" gscan_ctx *gscan_open(int device)
 {
+	// GSCAN_TRACE_OPEN=1: where the start-up time goes (driver initialisation / primary context / the rest), on stderr
+	const bool trace = getenv("GSCAN_TRACE_OPEN") != nullptr;
+	auto t0 = std::chrono::steady_clock::now();
+	auto lap = [&](const char *what) {
+		if (!trace) return;
+		const auto t1 = std::chrono::steady_clock::now();
+		fprintf(stderr, "[gscan_open] %-44s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		t0 = t1;
+	};
 	int n = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
+	lap("cudaGetDeviceCount (driver initialisation)");
 	if (e != cudaSuccess || n == 0) {
 		g_last_error = std::string("gscan_open: no CUDA device (") + cudaGetErrorString(e) +
 		               "): the scan has no CPU fallback";
@@ -360,22 +370,29 @@ extern "C" gscan_ctx *gscan_open(int device)
 	if (!c) { g_last_error = "gscan_open: out of memory"; return nullptr; }
 	c->device = device;
 	memset(&c->stats, 0, sizeof(c->stats));
-	cudaDeviceProp prop;
-	if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
-	    (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+	int major = 0, minor = 0, sms = 0;
+	if ((e = cudaSetDevice(device)) == cudaSuccess) e = cudaFree(nullptr); // creates the primary context
+	lap("cudaSetDevice + cudaFree(0) (primary context)");
+	// three attributes, not cudaGetDeviceProperties (which queries every property of the device)
+	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+	if (e != cudaSuccess) {
 		g_last_error = std::string("gscan_open: ") + cudaGetErrorString(e);
 		delete c;
 		return nullptr;
 	}
-	if (prop.major != 10) {
+	if (major != 10) {
 		g_last_error = "gscan_open: this library is built for sm_100a (B200) only; device is sm_" +
-		               std::to_string(prop.major) + std::to_string(prop.minor);
+		               std::to_string(major) + std::to_string(minor);
 		cudaStreamDestroy(c->stream);
 		delete c;
 		return nullptr;
 	}
-	c->num_sms = prop.multiProcessorCount;
+	c->num_sms = sms;
 	for (auto &ev : c->ev) cudaEventCreate(&ev);
+	lap("attributes, stream, events");
 	return c;
 }
 
