@@ -104,7 +104,8 @@ struct gscan_ctx {
 	// pinned result buffers handed to the caller (gscan_match arrays), recycled by gscan_free_matches
 	struct ResultBuf { void *p; size_t cap; bool lent; };
 	std::vector<ResultBuf> results;
-	DevBuf<uint32_t> unit_start, unit_out, blk, chain;
+	DevBuf<uint32_t> unit_start, unit_out, blk, chain, vm_flag, vm_unit_start;
+	DevBuf<OutRec> vm_ord;
 	DevBuf<unsigned long long> cursor; // [0] cursor, then 2 x u32 totals behind it
 	DevBuf<uint8_t> pat_tables, hash_tables, vm_tables;
 	const uint32_t *vm_code = nullptr, *vm_sets = nullptr;
@@ -403,7 +404,7 @@ extern "C" void gscan_close(gscan_ctx *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->segs.release(); c->cand.release(); c->scratch.release(); c->ord.release(); c->out.release();
-	c->unit_start.release(); c->unit_out.release(); c->blk.release(); c->chain.release(); c->cursor.release(); c->pat_tables.release(); c->hash_tables.release(); c->vm_tables.release();
+	c->unit_start.release(); c->unit_out.release(); c->blk.release(); c->chain.release(); c->vm_flag.release(); c->vm_unit_start.release(); c->vm_ord.release(); c->cursor.release(); c->pat_tables.release(); c->hash_tables.release(); c->vm_tables.release();
 	c->probe_sum.release(); c->needle.release();
 	c->pool_arena.release(); c->pool_tiles.release(); c->pool_units.release();
 	c->readback.release();
@@ -897,16 +898,30 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		// chain path: FIXED patterns whose replay is sequential (overlapping matches, or LINE mode) with many candidates per
 		// unit -- one thread per unit would walk them alone (a 1 GiB window of a log file with a million hits: seconds)
 		R.chain = 0; R.chain_levels = 0; R.chain_cap = 0; R.chain_buf = nullptr;
+		R.vm_par = 0; R.vm_ord = nullptr; R.vm_unit_start = nullptr; R.vm_flag = nullptr;
 		{
-			bool want = !R.flat && !dense && !pat->prog.use_vm && pat->prog.kind == ENGINE_FIXED && (mode == GSCAN_MODE_ALL || mode == GSCAN_MODE_LINE) &&
-			            total_cand >= 65536 && total_cand / std::max<uint64_t>(b->n_units, 1) >= 1024;
+			// general patterns take the same path when their attempts do not depend on the search start (vm_start_free) and
+			// the candidates come from a leading-sequence filter: one VM attempt per candidate, all at once, then the chain
+			// over the candidates that matched (any mode) -- instead of one thread replaying a huge unit's attempts alone
+			// RUN in LINE mode too: the search resumes behind a line remainder, possibly inside a run (chain_entry)
+			const bool fixed_ok = !pat->prog.use_vm && ((pat->prog.kind == ENGINE_FIXED && (mode == GSCAN_MODE_ALL || mode == GSCAN_MODE_LINE)) ||
+			                                            (pat->prog.kind == ENGINE_RUN && mode == GSCAN_MODE_LINE));
+			const bool vm_ok = pat->prog.use_vm && !pat->prog.vm_runstart && pat->prog.vm_start_free;
+			const bool eligible = !R.flat && !dense && (fixed_ok || vm_ok) && total_cand > 0;
+			bool want = eligible && total_cand >= 65536 && total_cand / std::max<uint64_t>(b->n_units, 1) >= 1024;
 			if (const char *e = getenv("GSCAN_CHAIN")) // tests: force the path on small inputs / switch it off
-				want = !R.flat && !dense && !pat->prog.use_vm && pat->prog.kind == ENGINE_FIXED && (mode == GSCAN_MODE_ALL || mode == GSCAN_MODE_LINE) && *e == '1' && total_cand > 0;
-			uint32_t levels = 1;
+				want = eligible && *e == '1';
+			uint32_t levels = 2; // at least two tables: the second one doubles as the RUN entry positions
 			while ((1ull << levels) < total_cand) levels++;
 			if (want && (uint64_t)(levels + 2) * total_cand * 4 <= (4ull << 30)) {
 				CK(ctx, ctx->chain.ensure((size_t)(levels + 2) * (size_t)total_cand));
 				R.chain = 1; R.chain_levels = levels; R.chain_cap = (uint32_t)total_cand; R.chain_buf = ctx->chain.p;
+				if (vm_ok) {
+					CK(ctx, ctx->vm_ord.ensure((size_t)total_cand));
+					CK(ctx, ctx->vm_flag.ensure((size_t)total_cand));
+					CK(ctx, ctx->vm_unit_start.ensure((size_t)b->n_units + 1));
+					R.vm_par = 1; R.vm_ord = ctx->vm_ord.p; R.vm_flag = ctx->vm_flag.p; R.vm_unit_start = ctx->vm_unit_start.p;
+				}
 			}
 		}
 		R.run_min = (uint32_t)pat->prog.run_min;

@@ -58,6 +58,17 @@ struct ResolveArgs {
 	// walking a huge unit alone.  chain_buf: chain_levels x chain_cap jump tables, then the mark and rank arrays.
 	uint32_t chain, chain_levels, chain_cap;
 	uint32_t *chain_buf;
+	// general patterns on the chain path (vm_par): patterns whose attempts do not depend on where the subject begins
+	// (Program::vm_start_free) with many candidates per unit.  One anchored VM attempt per candidate, all at once
+	// (k_vm_attempts: outcome and match length into ord[].pad / .len), the candidates that matched are compacted into
+	// vm_ord / vm_unit_start (exclusive scan of vm_flag), and the chain kernels run over those: the selected matches of a
+	// unit are the chain from its first matching candidate, next(i) = first matching candidate at or after where the loop
+	// resumes behind i.  A candidate whose match has a capturing group set (Q2) or that ran into the VM's limits ends its
+	// unit's chain there and is not reported (grab.cc:179: rc <= 0 => break).
+	uint32_t vm_par;
+	OutRec *vm_ord;           // [total_cand] the candidates with pad != 0, (unit, pos) order
+	uint32_t *vm_unit_start;  // [n_units + 1] into vm_ord
+	uint32_t *vm_flag;        // [total_cand] pad != 0, then its exclusive scan
 	uint32_t vm_dense;    // general pattern without a candidate filter: no candidate list, the walk offers every position whose byte
 	                      // is in `bitmap` (the first-byte set) to the VM
 	uint32_t flat;        // ALL mode, RUN or a FIXED pattern whose matches can never overlap, no VM: every candidate of a unit is a

@@ -1128,6 +1128,12 @@ bool compile_pattern(const char *pat, size_t len, uint32_t flags, Program &out, 
 		std::vector<Pref> pf;
 		out.use_vm = true;
 		out.vm_code = g.code;
+		out.vm_start_free = true;
+		for (size_t i = 0; i + 2 < out.vm_code.size(); i += 3) {
+			const uint32_t op = out.vm_code[i] & 0xffu, kind = (out.vm_code[i] >> 8) & 0xffu;
+			if (op == VM_ASSERT && (kind == VM_A_BOL || kind == VM_A_SOS || kind == VM_A_WORDB || kind == VM_A_NWORDB || kind == VM_A_MBOL)) out.vm_start_free = false;
+			if (op == VM_LOOK && (kind == VM_LK_BEHIND || kind == VM_LK_BEHIND_NEG)) out.vm_start_free = false;
+		}
 		for (auto &s : g.sets) for (int i = 0; i < 8; i++) out.vm_sets.push_back(s.w[i]);
 		bool dense = !prefixes(root.get(), 4, pf) || pf.empty();
 		seqs.clear();

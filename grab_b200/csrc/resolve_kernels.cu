@@ -385,23 +385,41 @@ __global__ void k_chain_next(const ResolveArgs R)
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= R.totals[0]) return;
 	const OutRec c = R.ord[i];
+	if (R.vm_par && c.pad >= 2u) { chain_level(R, 0)[i] = kChainEnd; return; } // this match ends its unit's loop (Q2 / VM limit)
 	const DevUnit du = R.units[c.unit];
 	const uint64_t ulen = du.len;
+	const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
+	const bool run = R.engine == GSCAN_ENGINE_RUN;
 	uint64_t stop = (uint64_t)c.pos + c.len;
+	if (run) { // greedy: the match reaches the end of the run, wherever inside the run it began (kept for the later passes)
+		stop = (uint64_t)c.pos + R.run_min;
+		while (stop < ulen && in_class(R, data[stop])) stop++;
+		R.ord[i].len = (uint32_t)(stop - c.pos);
+	}
 	if (R.mode == GSCAN_MODE_LINE) {
-		const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
 		uint32_t a = 0;
 		while (stop + a < ulen && a < 511 && data[stop + a] != '\n') a++;
 		stop += a;
 	}
+	if (run) R.ord[i].pad = (uint32_t)stop; // where the search resumes behind this match (k_chain_entry)
 	uint32_t nx = kChainEnd;
 	if (stop + R.minlen < ulen) {
+		// RUN: the search may resume INSIDE a run (behind a line remainder); if what is left of that run is long enough the
+		// leftmost match is at `stop` itself -- it ends where the run's own candidate ends, so the chain goes on from that
+		// candidate and only the reported start differs (chain_entry)
+		bool inside = false;
+		if (run && stop > 0 && in_class(R, data[stop - 1]) && in_class(R, data[stop])) {
+			uint64_t e = stop;
+			while (e < ulen && in_class(R, data[e])) e++;
+			inside = e - stop >= R.run_min;
+		}
 		uint32_t lo = i + 1, hi = R.unit_start[c.unit + 1]; // candidates are ordered by position inside the unit
 		while (lo < hi) {
 			const uint32_t mid = lo + ((hi - lo) >> 1);
 			if (R.ord[mid].pos < stop) lo = mid + 1; else hi = mid;
 		}
-		if (lo < R.unit_start[c.unit + 1]) nx = lo;
+		if (inside) nx = lo - 1; // the run that holds `stop`: the last one that starts before it (behind i's own run)
+		else if (lo < R.unit_start[c.unit + 1]) nx = lo;
 	}
 	chain_level(R, 0)[i] = nx;
 }
@@ -436,6 +454,35 @@ __global__ void k_chain_spread(const ResolveArgs R, uint32_t k)
 	if (j != kChainEnd) chain_mark(R)[j] = 1u;
 }
 
+// RUN: where every chain member's match is reported -- at its run's first byte, or, when its predecessor's search resumed
+// inside the run, there (level 1 of the jump tables is free once the marks are spread: it holds the entry positions)
+__device__ __forceinline__ uint32_t *chain_entry(const ResolveArgs &R) { return chain_level(R, 1); }
+__global__ void k_chain_entry_init(const ResolveArgs R)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= R.totals[0]) return;
+	chain_entry(R)[i] = R.ord[i].pos;
+}
+__global__ void k_chain_entry(const ResolveArgs R)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= R.totals[0]) return;
+	if (!chain_mark(R)[i]) return;
+	const uint32_t nx = chain_level(R, 0)[i];
+	if (nx == kChainEnd) return;
+	const uint32_t stop = R.ord[i].pad;
+	if (stop > R.ord[nx].pos) chain_entry(R)[nx] = stop; // one marked predecessor per chain member: no two writers
+}
+
+// vm_par: a candidate that ends its unit's loop (pad 2: a capturing group was set, pcre_exec returns 0; pad 3: VM limit,
+// pcre_exec returns an error) is on the chain -- nothing behind it is -- but is not a reported match
+__global__ void k_chain_unmark(const ResolveArgs R)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= R.totals[0]) return;
+	if (R.ord[i].pad >= 2u) chain_mark(R)[i] = 0u;
+}
+
 // matches per unit from the exclusive scan of the marks (rank)
 __global__ void k_chain_count(const ResolveArgs R)
 {
@@ -455,11 +502,50 @@ __global__ void k_chain_write(const ResolveArgs R)
 	const OutRec c = R.ord[i];
 	const DevUnit du = R.units[c.unit];
 	const uint32_t k = chain_rank(R)[i] - chain_rank(R)[R.unit_start[c.unit]];
+	const uint32_t from = R.engine == GSCAN_ENGINE_RUN ? chain_entry(R)[i] : c.pos;
 	FinalRec r;
-	r.start = du.base_off + c.pos;
+	r.start = du.base_off + from;
 	r.file_id = du.file_id;
-	r.len = c.len;
+	r.len = c.pos + c.len - from;
 	R.out[R.unit_out[c.unit] + k] = r;
+}
+
+// ---- general patterns on the chain path (ResolveArgs::vm_par) ----
+// One anchored attempt per candidate, every candidate of the batch at once.  The subject of the attempt begins at the
+// candidate itself: for a start-free program (no ^, \A, \b, \B, (?m)^, look-behind) the result is the one pcre_exec
+// reaches from any search start at or before the candidate (grab.cc:178).
+__global__ void __launch_bounds__(64, 4) k_vm_attempts(const ResolveArgs R)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= R.totals[0]) return;
+	const OutRec c = R.ord[i];
+	const DevUnit du = R.units[c.unit];
+	const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
+	VmBudget budget(du.len);
+	uint32_t e = 0;
+	int rc = vm_exec(R, data + c.pos, du.len - c.pos, 0u, &e, budget);
+	if (rc < 0) { atomicOr(R.totals + 2, 1u); rc = 3; }
+	R.ord[i].len = e;             // the subject began at the candidate: the end offset is the match length
+	R.ord[i].pad = (uint32_t)rc;  // 0: no match here, 1: match, 2: match with a capturing group set (Q2), 3: VM limit
+	R.vm_flag[i] = rc != 0 ? 1u : 0u;
+}
+
+// vm_flag holds its own exclusive scan by now: the candidates that matched, in order
+__global__ void k_vm_compact(const ResolveArgs R)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= R.totals[0]) return;
+	const OutRec c = R.ord[i];
+	if (c.pad) R.vm_ord[R.vm_flag[i]] = c;
+}
+
+// first matching candidate of every unit (R.totals[4]: how many matched in all)
+__global__ void k_vm_unit_starts(const ResolveArgs R)
+{
+	const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+	if (u > R.n_units) return;
+	const uint32_t s = R.unit_start[u];
+	R.vm_unit_start[u] = s < R.totals[0] ? R.vm_flag[s] : R.totals[4];
 }
 
 // general patterns: every match starts at a candidate (a leading-byte prefix hit).  The count pass runs the VM
@@ -616,6 +702,14 @@ __global__ void k_fill_zero(uint32_t *p, uint32_t n)
 	if (i + gridDim.x * blockDim.x < n) p[i + gridDim.x * blockDim.x] = 0u;
 }
 static uint32_t *chain_mark_host(const ResolveArgs &R) { return R.chain_buf + (size_t)R.chain_levels * R.chain_cap; }
+// what the chain kernels see: the candidate list itself, or (vm_par) the compacted list of the candidates that matched with
+// its own count (totals[4]) and rank-total scratch (totals[7])
+static ResolveArgs chain_view(const ResolveArgs &R)
+{
+	ResolveArgs C = R;
+	if (R.vm_par) { C.ord = R.vm_ord; C.unit_start = R.vm_unit_start; C.totals = R.totals + 4; }
+	return C;
+}
 
 cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t *launches)
 {
@@ -632,16 +726,34 @@ cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t
 		// grids cover the reserved candidate slots; the kernels stop at the exact count (totals[0], on the device by now)
 		const uint32_t nb_c = (R.chain_cap + 255) / 256, nb_cs = (R.chain_cap + kPerBlock - 1) / kPerBlock;
 		uint32_t *blk3 = blk2 + nb_u + 1;
-		k_fill_zero<<<nb_c, 256, 0, st>>>(chain_mark_host(R), 2u * R.chain_cap); nl++; // marks and ranks
-		k_chain_next<<<nb_c, 256, 0, st>>>(R); nl++;
-		for (uint32_t k = 1; k < R.chain_levels; k++) { k_chain_double<<<nb_c, 256, 0, st>>>(R, k); nl++; }
-		k_chain_heads<<<(R.n_units + 255) / 256, 256, 0, st>>>(R); nl++;
-		for (uint32_t k = R.chain_levels; k-- > 0;) { k_chain_spread<<<nb_c, 256, 0, st>>>(R, k); nl++; }
-		cudaMemcpyAsync(chain_mark_host(R) + R.chain_cap, chain_mark_host(R), (size_t)R.chain_cap * 4, cudaMemcpyDeviceToDevice, st);
-		k_u32_sums<<<nb_cs, kScanBlock, 0, st>>>(chain_mark_host(R) + R.chain_cap, R.chain_cap, blk3); nl++;
-		k_scan_blk<<<1, kScanBlock, 0, st>>>(blk3, nb_cs, R.totals + 3, nullptr); nl++;
-		k_u32_exclusive<<<nb_cs, kScanBlock, 0, st>>>(chain_mark_host(R) + R.chain_cap, R.chain_cap, blk3); nl++;
-		k_chain_count<<<(R.n_units + 255) / 256, 256, 0, st>>>(R); nl++;
+		if (R.vm_par) {
+			k_fill_zero<<<nb_c, 256, 0, st>>>(R.vm_flag, R.chain_cap); nl++;
+			k_vm_attempts<<<(R.chain_cap + 63) / 64, 64, 0, st>>>(R); nl++;
+			k_u32_sums<<<nb_cs, kScanBlock, 0, st>>>(R.vm_flag, R.chain_cap, blk3); nl++;
+			k_scan_blk<<<1, kScanBlock, 0, st>>>(blk3, nb_cs, R.totals + 4, nullptr); nl++;
+			k_u32_exclusive<<<nb_cs, kScanBlock, 0, st>>>(R.vm_flag, R.chain_cap, blk3); nl++;
+			k_vm_compact<<<nb_c, 256, 0, st>>>(R); nl++;
+			k_vm_unit_starts<<<(R.n_units + 1 + 255) / 256, 256, 0, st>>>(R); nl++;
+		}
+		const ResolveArgs C = chain_view(R);
+		const bool follow = R.mode != GSCAN_MODE_FIRST; // FIRST: the head of every unit's chain is all there is
+		k_fill_zero<<<nb_c, 256, 0, st>>>(chain_mark_host(C), 2u * C.chain_cap); nl++; // marks and ranks
+		if (follow) {
+			k_chain_next<<<nb_c, 256, 0, st>>>(C); nl++;
+			for (uint32_t k = 1; k < C.chain_levels; k++) { k_chain_double<<<nb_c, 256, 0, st>>>(C, k); nl++; }
+		}
+		k_chain_heads<<<(C.n_units + 255) / 256, 256, 0, st>>>(C); nl++;
+		if (follow) for (uint32_t k = C.chain_levels; k-- > 0;) { k_chain_spread<<<nb_c, 256, 0, st>>>(C, k); nl++; }
+		if (R.vm_par) { k_chain_unmark<<<nb_c, 256, 0, st>>>(C); nl++; }
+		if (R.engine == GSCAN_ENGINE_RUN) {
+			k_chain_entry_init<<<nb_c, 256, 0, st>>>(C); nl++;
+			k_chain_entry<<<nb_c, 256, 0, st>>>(C); nl++;
+		}
+		cudaMemcpyAsync(chain_mark_host(C) + C.chain_cap, chain_mark_host(C), (size_t)C.chain_cap * 4, cudaMemcpyDeviceToDevice, st);
+		k_u32_sums<<<nb_cs, kScanBlock, 0, st>>>(chain_mark_host(C) + C.chain_cap, C.chain_cap, blk3); nl++;
+		k_scan_blk<<<1, kScanBlock, 0, st>>>(blk3, nb_cs, C.totals + 3, nullptr); nl++;
+		k_u32_exclusive<<<nb_cs, kScanBlock, 0, st>>>(chain_mark_host(C) + C.chain_cap, C.chain_cap, blk3); nl++;
+		k_chain_count<<<(C.n_units + 255) / 256, 256, 0, st>>>(C); nl++;
 	} else {
 		if (R.engine == GSCAN_ENGINE_VM) k_walk_vm<false><<<(R.n_units + 63) / 64, 64, 0, st>>>(R);
 		else k_walk<false><<<(R.n_units + 127) / 128, 128, 0, st>>>(R);
@@ -657,7 +769,7 @@ cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t
 cudaError_t launch_resolve_write(const ResolveArgs &R, cudaStream_t st, uint32_t *launches)
 {
 	if (R.chain) {
-		k_chain_write<<<(R.total_cand + 255) / 256, 256, 0, st>>>(R);
+		k_chain_write<<<(R.total_cand + 255) / 256, 256, 0, st>>>(chain_view(R));
 		if (launches) *launches = 1;
 		return cudaGetLastError();
 	}

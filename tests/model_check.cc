@@ -121,7 +121,7 @@ static void candidates(const Program &p, const uint8_t *s, size_t len, std::vect
 	}
 }
 
-static int g_flat_checks = 0, g_chain_checks = 0;
+static int g_flat_checks = 0, g_chain_checks = 0, g_vmpar_checks = 0;
 // count pass, slot scan (one unit: slot 0), write pass -- the device code of resolve_kernels.cu, on the host.
 // 0 ok, -1 VM limit
 static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, std::vector<M> &out)
@@ -180,9 +180,9 @@ static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, s
 		g_flat_checks++;
 	}
 	// the chain path (pointer doubling over the candidates) wherever it applies: same records as the serial replay
-	if (!p.use_vm && p.kind == ENGINE_FIXED && (mode == GSCAN_MODE_ALL || mode == GSCAN_MODE_LINE) && !ord.empty()) {
+	if (!p.use_vm && ((p.kind == ENGINE_FIXED && (mode == GSCAN_MODE_ALL || mode == GSCAN_MODE_LINE)) || (p.kind == ENGINE_RUN && mode == GSCAN_MODE_LINE)) && !ord.empty()) {
 		const uint32_t cap = (uint32_t)ord.size();
-		uint32_t levels = 1;
+		uint32_t levels = 2;
 		while ((1u << levels) < cap) levels++;
 		std::vector<uint32_t> buf((size_t)(levels + 2) * cap, 0u);
 		R.flat = 0;
@@ -195,6 +195,7 @@ static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, s
 		model_threadIdx.x = 0;
 		k_chain_heads(R);
 		for (uint32_t k = levels; k-- > 0;) each([&] { k_chain_spread(R, k); });
+		if (p.kind == ENGINE_RUN) { each([&] { k_chain_entry_init(R); }); each([&] { k_chain_entry(R); }); }
 		uint32_t *mark = buf.data() + (size_t)levels * cap, *rank = mark + cap;
 		uint32_t acc = 0;
 		for (uint32_t i = 0; i < cap; i++) { rank[i] = acc; acc += mark[i]; } // the device uses its block-scan kernels here
@@ -209,6 +210,57 @@ static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, s
 		for (uint32_t i = 0; same && i < n; i++) same = fc[i].start == fin[i].start && fc[i].len == fin[i].len;
 		if (!same) return -4;
 		g_chain_checks++;
+	}
+	// general patterns on the chain path (vm_par): one attempt per candidate, compaction of the candidates that matched,
+	// chain over those -- wherever the engine may choose it (start-free program, candidates from the leading-sequence
+	// filter), in every mode: same records as the serial replay
+	if (p.use_vm && !p.vm_dense && !p.vm_runstart && p.vm_start_free && !ord.empty()) {
+		std::vector<OutRec> cand;
+		candidates(p, s, len, cand); // fresh: the serial count pass above recorded its outcomes in ord
+		const uint32_t cap = (uint32_t)cand.size();
+		uint32_t levels = 2;
+		while ((1u << levels) < cap) levels++;
+		std::vector<uint32_t> buf((size_t)(levels + 2) * cap, 0u), flag(cap, 0u);
+		std::vector<OutRec> vord(cap);
+		uint32_t vus[2] = {0, 0}, us2[2] = {0, cap}, tot[8] = {cap, 0, 0, 0, 0, 0, 0, 0}, uo[1] = {0};
+		ResolveArgs V = R;
+		V.flat = 0;
+		V.ord = cand.data(); V.unit_start = us2; V.unit_out = uo; V.totals = tot; V.out = nullptr; V.total_cand = cap;
+		V.chain = 1; V.chain_levels = levels; V.chain_cap = cap; V.chain_buf = buf.data();
+		V.vm_par = 1; V.vm_ord = vord.data(); V.vm_flag = flag.data(); V.vm_unit_start = vus;
+		auto each = [&](auto fn) { for (uint32_t i = 0; i < cap; i++) { model_threadIdx.x = i; fn(); } model_threadIdx.x = 0; };
+		each([&] { k_vm_attempts(V); });
+		if (tot[2]) return -1;
+		uint32_t acc = 0;
+		for (uint32_t i = 0; i < cap; i++) { const uint32_t f = flag[i]; flag[i] = acc; acc += f; } // device: block-scan kernels
+		tot[4] = acc;
+		each([&] { k_vm_compact(V); });
+		for (uint32_t u = 0; u <= 1; u++) { model_threadIdx.x = u; k_vm_unit_starts(V); }
+		model_threadIdx.x = 0;
+		ResolveArgs C = V;
+		C.ord = V.vm_ord; C.unit_start = V.vm_unit_start; C.totals = V.totals + 4; // chain_view() of resolve_kernels.cu
+		const bool follow = mode != GSCAN_MODE_FIRST;
+		if (follow) {
+			each([&] { k_chain_next(C); });
+			for (uint32_t k = 1; k < levels; k++) each([&] { k_chain_double(C, k); });
+		}
+		model_threadIdx.x = 0;
+		k_chain_heads(C);
+		if (follow) for (uint32_t k = levels; k-- > 0;) each([&] { k_chain_spread(C, k); });
+		each([&] { k_chain_unmark(C); });
+		uint32_t *mark = buf.data() + (size_t)levels * cap, *rank = mark + cap;
+		acc = 0;
+		for (uint32_t i = 0; i < cap; i++) { rank[i] = acc; acc += mark[i]; }
+		k_chain_count(C);
+		const uint32_t nc = uo[0];
+		uo[0] = 0;
+		std::vector<FinalRec> fc(nc + 1);
+		C.out = fc.data();
+		each([&] { k_chain_write(C); });
+		bool same = nc == n;
+		for (uint32_t i = 0; same && i < n; i++) same = fc[i].start == fin[i].start && fc[i].len == fin[i].len;
+		if (!same) return -5;
+		g_vmpar_checks++;
 	}
 	return 0;
 }
@@ -226,6 +278,16 @@ int main(int argc, char **argv)
 		const size_t na = strlen(al), ln = (size_t)lens[k % 13];
 		std::vector<uint8_t> b(ln);
 		for (auto &c : b) c = (uint8_t)al[rnd() % na];
+		subjects.push_back(b);
+	}
+	// lines longer than the 511 bytes the reference prints behind a match (grab.cc:194-196): in LINE mode the search resumes
+	// in the middle of the line, for class runs possibly in the middle of a run
+	for (int k = 0; k < 6; k++) {
+		const char *al = k % 3 == 0 ? "ab" : (k % 3 == 1 ? "abc " : "aab_1 ");
+		const size_t na = strlen(al), ln = k < 3 ? 700 : 1500;
+		std::vector<uint8_t> b(ln);
+		for (auto &c : b) c = (uint8_t)al[rnd() % na];
+		if (k >= 3) b[ln / 2] = '\n';
 		subjects.push_back(b);
 	}
 	int n_dense = 0, n_pat = 0, n_served = 0, n_vm = 0, n_cmp = 0, n_walk = 0, n_limit = 0, bad = 0, n_strict = 0;
@@ -271,6 +333,12 @@ int main(int argc, char **argv)
 				const int wrc = walk(p, sb.data(), sb.size(), dmodes[m], g2);
 				if (wrc == -3) { printf("FLAT WALK MISMATCH %s\n", pat.c_str()); bad++; go_matches_free(&w2); continue; }
 				if (wrc == -4) { printf("CHAIN WALK MISMATCH %s mode %d\n", pat.c_str(), m); bad++; go_matches_free(&w2); continue; }
+				if (wrc == -5) {
+					printf("VM CHAIN MISMATCH %s mode %d on \"", pat.c_str(), m);
+					for (uint8_t c : sb) printf(c == '\n' ? "\\n" : c == '\t' ? "\\t" : "%c", c);
+					printf("\"\n");
+					bad++; go_matches_free(&w2); continue;
+				}
 				if (wrc != 0) { go_matches_free(&w2); n_limit++; continue; }
 				bool ok = g2.size() == w2.n;
 				for (size_t i = 0; ok && i < g2.size(); i++) ok = g2[i].pos == w2.v[i].start && g2[i].len == w2.v[i].len;
@@ -299,7 +367,9 @@ int main(int argc, char **argv)
 						go_matches w2 = {0, 0, 0};
 						if (go_scan_window(re, sb.data(), sb.size(), 0, 0, modes[m], 1, &w2) != 0) { go_matches_free(&w2); continue; }
 						std::vector<M> g2;
-						if (ps.kind != ENGINE_NONE && walk(ps, sb.data(), sb.size(), dmodes[m], g2) != 0) { go_matches_free(&w2); n_limit++; continue; }
+						const int src = ps.kind != ENGINE_NONE ? walk(ps, sb.data(), sb.size(), dmodes[m], g2) : 0;
+						if (src == -5) { printf("STRICT VM CHAIN MISMATCH %s mode %d\n", pat.c_str(), m); bad++; go_matches_free(&w2); continue; }
+						if (src != 0) { go_matches_free(&w2); n_limit++; continue; }
 						bool ok = g2.size() == w2.n;
 						for (size_t i = 0; ok && i < g2.size(); i++) ok = g2[i].pos == w2.v[i].start && g2[i].len == w2.v[i].len;
 						n_walk++;
@@ -317,7 +387,7 @@ int main(int argc, char **argv)
 		}
 		go_free(re);
 	}
-	printf("chain checks %d; dense VM patterns %d; ", g_chain_checks, n_dense);
+	printf("vm chain checks %d; chain checks %d; dense VM patterns %d; ", g_vmpar_checks, g_chain_checks, n_dense);
 	printf("flat write checks %d; strict (Q2) patterns %d; ", g_flat_checks, n_strict);
 	printf("patterns %d, served %d (%d through the VM), comparisons %d + %d through the walk kernels, limit skips %d, mismatches %d\n", n_pat, n_served, n_vm, n_cmp, n_walk, n_limit, bad);
 	if (bad == 0) printf("model ok\n");

@@ -87,6 +87,20 @@ class Regex:
             raise OracleError("scan error (empty-matchable pattern?)")
         return out
 
+    def scan_window_np(self, data, base_off=0, mode=MODE_ALL, strict_q2=True):
+        """scan_window() for big windows: `data` a contiguous numpy uint8 array (not copied), the result a structured numpy
+        array with fields start / len / unit (millions of matches without millions of Python tuples)."""
+        import numpy as np
+        a = np.ascontiguousarray(data, dtype=np.uint8)
+        m = _Matches()
+        rc = _lib.go_scan_window(self._h, ctypes.cast(a.ctypes.data, ctypes.c_char_p), a.size, base_off, 0, mode, int(strict_q2), ctypes.byref(m))
+        dt = np.dtype([("start", "<u8"), ("len", "<u4"), ("unit", "<u4")])
+        out = np.frombuffer(ctypes.string_at(m.v, m.n * dt.itemsize), dtype=dt).copy() if m.n else np.zeros(0, dtype=dt)
+        _lib.go_matches_free(ctypes.byref(m))
+        if rc < 0:
+            raise OracleError("scan error (empty-matchable pattern?)")
+        return out
+
     def scan_file(self, data, chunk_size=1 << 30, mode=MODE_ALL, strict_q2=True):
         """All windows of grab.cc:154-159 over an in-memory file; duplicates in overlaps are kept (Q3).
         FIRST mode stops at the first window that printed something (grab.cc:232-233)."""

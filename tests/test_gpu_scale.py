@@ -94,6 +94,36 @@ def test_maximum_window_one_gib():
         ctx.close()
 
 
+@pytest.mark.parametrize("pat,mode", [("e", G.MODE_ALL), ("e", G.MODE_LINE), ("[A-Za-z0-9_]{16,}", G.MODE_ALL), ("[A-Za-z0-9_]{16,}", G.MODE_LINE),
+                                      ("ee|e", G.MODE_ALL)], ids=["e-all", "e-line", "run16-all", "run16-line", "overlap-all"])
+def test_maximum_window_one_gib_dense(pat, mode):
+    """The reference's largest window (1 GiB) as ONE unit of synthetic text with DENSE matches: `e` has ~12 million
+    candidates, `[A-Za-z0-9_]{16,}` ~440 000.  The resolve pass must not replay them on one thread: ALL mode takes the flat
+    write pass (one thread per candidate), LINE mode and overlapping alternatives the chain pass (pointer doubling over all
+    candidates).  Records equal the oracle's on the same bytes (generated on the device, copied back for the oracle), and
+    the resolve stays a fraction of the scan (printed; asserted loosely: well below the one-thread replay's seconds)."""
+    ctx = G.Context(0)
+    n = 1 << 30
+    d = ctx.device_alloc(n)
+    try:
+        ctx.synth_corpus(d, 13, 7, 1, n)
+        host = ctx.d2h(d, n)
+        units = G.Context.device_units(d, 1, n)
+        p = G.Pattern(pat)
+        r = ctx.scan_units(p, units, mode)
+        r = ctx.scan_units(p, units, mode)  # second call: buffers sized, timings steady
+        st = ctx.stats()
+        want = O.Regex(pat).scan_window_np(host, mode={G.MODE_ALL: O.MODE_ALL, G.MODE_LINE: O.MODE_LINE}[mode])
+        assert len(r) == len(want) and len(r) > 100000
+        assert np.array_equal(r["start"], want["start"]) and np.array_equal(r["match_len"], want["len"])
+        print("one 1 GiB unit, %s mode %d: %d candidates, %d matches, scan %.3f ms, resolve %.3f ms, %d launches"
+              % (pat, mode, st["n_candidates"], len(r), st["scan_kernel_ms"], st["resolve_ms"], st["total_launches"]))
+        assert st["resolve_ms"] < 50.0  # one thread walking 10^7 dependent candidates takes seconds
+    finally:
+        ctx.device_free(d)
+        ctx.close()
+
+
 def test_oversized_unit_is_rejected_loudly():
     ctx = G.Context(0)
     u = np.zeros(1, dtype=G.UNIT_DTYPE)
