@@ -106,6 +106,7 @@ struct gscan_ctx {
 	std::vector<ResultBuf> results;
 	DevBuf<uint32_t> unit_start, unit_out, blk, chain, vm_flag, vm_unit_start;
 	DevBuf<OutRec> vm_ord;
+	DevBuf<unsigned long long> vm_budget;
 	DevBuf<unsigned long long> cursor; // [0] cursor, then 2 x u32 totals behind it
 	DevBuf<uint8_t> pat_tables, hash_tables, vm_tables;
 	const uint32_t *vm_code = nullptr, *vm_sets = nullptr;
@@ -119,6 +120,7 @@ struct gscan_ctx {
 	// two pinned bounce buffers and two events
 	struct StageLane { cudaStream_t stream = nullptr; void *buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; };
 	std::vector<StageLane> lanes;
+	std::vector<void *> stage_slabs; // the lanes' bounce buffers are carved out of few big pinned allocations (one cudaHostAlloc per growth, not two per lane)
 	// pools behind the transient batches of gscan_scan_batch (grow-only: no cudaMalloc/cudaFree per call)
 	DevBuf<uint8_t> pool_arena;
 	DevBuf<TileDesc> pool_tiles;
@@ -404,15 +406,16 @@ extern "C" void gscan_close(gscan_ctx *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->segs.release(); c->cand.release(); c->scratch.release(); c->ord.release(); c->out.release();
-	c->unit_start.release(); c->unit_out.release(); c->blk.release(); c->chain.release(); c->vm_flag.release(); c->vm_unit_start.release(); c->vm_ord.release(); c->cursor.release(); c->pat_tables.release(); c->hash_tables.release(); c->vm_tables.release();
+	c->unit_start.release(); c->unit_out.release(); c->blk.release(); c->chain.release(); c->vm_flag.release(); c->vm_unit_start.release(); c->vm_ord.release(); c->vm_budget.release(); c->cursor.release(); c->pat_tables.release(); c->hash_tables.release(); c->vm_tables.release();
 	c->probe_sum.release(); c->needle.release();
 	c->pool_arena.release(); c->pool_tiles.release(); c->pool_units.release();
 	c->readback.release();
 	for (auto &rb : c->results) if (rb.p) cudaFreeHost(rb.p);
 	for (auto &l : c->lanes) {
-		for (int i = 0; i < 2; i++) { if (l.buf[i]) cudaFreeHost(l.buf[i]); if (l.ev[i]) cudaEventDestroy(l.ev[i]); }
+		for (int i = 0; i < 2; i++) if (l.ev[i]) cudaEventDestroy(l.ev[i]);
 		if (l.stream) cudaStreamDestroy(l.stream);
 	}
+	for (void *slab : c->stage_slabs) cudaFreeHost(slab);
 	for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
 	cudaStreamDestroy(c->stream);
 	delete c;
@@ -475,14 +478,22 @@ static int stage_pageable(gscan_ctx *ctx, const std::vector<StagePiece> &pieces)
 	if (hw > 0 && want > hw) want = hw;
 	if (want < 1 || total < (16u << 20)) want = 1;
 	if ((size_t)want > jobs.size()) want = (int)jobs.size();
-	while ((int)ctx->lanes.size() < want) {
-		gscan_ctx::StageLane l;
-		CK(ctx, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
-		for (int i = 0; i < 2; i++) {
-			CK(ctx, cudaHostAlloc(&l.buf[i], kStageChunk, cudaHostAllocDefault));
-			CK(ctx, cudaEventCreateWithFlags(&l.ev[i], cudaEventDisableTiming));
+	if ((int)ctx->lanes.size() < want) {
+		// all missing lanes' buffers in ONE pinned allocation instead of two per lane (the first batch of a process spends
+		// 40-80 ms staging against 8 ms for the following ones: allocations, not copies)
+		const size_t missing = (size_t)want - ctx->lanes.size();
+		void *slab = nullptr;
+		CK(ctx, cudaHostAlloc(&slab, missing * 2 * kStageChunk, cudaHostAllocDefault));
+		ctx->stage_slabs.push_back(slab);
+		for (size_t m = 0; m < missing; m++) {
+			gscan_ctx::StageLane l;
+			CK(ctx, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+			for (int i = 0; i < 2; i++) {
+				l.buf[i] = static_cast<uint8_t *>(slab) + (2 * m + (size_t)i) * kStageChunk;
+				CK(ctx, cudaEventCreateWithFlags(&l.ev[i], cudaEventDisableTiming));
+			}
+			ctx->lanes.push_back(l);
 		}
-		ctx->lanes.push_back(l);
 	}
 	std::atomic<int> err{(int)cudaSuccess};
 	std::atomic<int> io_errno{0}; // first pread failure (GSCAN_UNIT_FD units); -1: the file ended early
@@ -898,7 +909,7 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		// chain path: FIXED patterns whose replay is sequential (overlapping matches, or LINE mode) with many candidates per
 		// unit -- one thread per unit would walk them alone (a 1 GiB window of a log file with a million hits: seconds)
 		R.chain = 0; R.chain_levels = 0; R.chain_cap = 0; R.chain_buf = nullptr;
-		R.vm_par = 0; R.vm_ord = nullptr; R.vm_unit_start = nullptr; R.vm_flag = nullptr;
+		R.vm_par = 0; R.vm_ord = nullptr; R.vm_unit_start = nullptr; R.vm_flag = nullptr; R.vm_budget = nullptr;
 		{
 			// general patterns take the same path when their attempts do not depend on the search start (vm_start_free) and
 			// the candidates come from a leading-sequence filter: one VM attempt per candidate, all at once, then the chain
@@ -920,6 +931,8 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 					CK(ctx, ctx->vm_ord.ensure((size_t)total_cand));
 					CK(ctx, ctx->vm_flag.ensure((size_t)total_cand));
 					CK(ctx, ctx->vm_unit_start.ensure((size_t)b->n_units + 1));
+					CK(ctx, ctx->vm_budget.ensure((size_t)b->n_units));
+					R.vm_budget = ctx->vm_budget.p;
 					R.vm_par = 1; R.vm_ord = ctx->vm_ord.p; R.vm_flag = ctx->vm_flag.p; R.vm_unit_start = ctx->vm_unit_start.p;
 				}
 			}

@@ -69,6 +69,7 @@ struct ResolveArgs {
 	OutRec *vm_ord;           // [total_cand] the candidates with pad != 0, (unit, pos) order
 	uint32_t *vm_unit_start;  // [n_units + 1] into vm_ord
 	uint32_t *vm_flag;        // [total_cand] pad != 0, then its exclusive scan
+	unsigned long long *vm_budget; // [n_units] VM steps the unit's attempts may still take, all of them together
 	uint32_t vm_dense;    // general pattern without a candidate filter: no candidate list, the walk offers every position whose byte
 	                      // is in `bitmap` (the first-byte set) to the VM
 	uint32_t flat;        // ALL mode, RUN or a FIXED pattern whose matches can never overlap, no VM: every candidate of a unit is a

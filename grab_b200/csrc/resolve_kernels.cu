@@ -158,8 +158,28 @@ __device__ bool vm_assert(uint32_t kind, const uint8_t *s, uint32_t len, uint32_
 struct VmBudget {
 	// both budgets grow with the unit (a linear scan of a big window must never trip them): + 64 steps per byte
 	unsigned long long search, unit, per_search;
-	__device__ explicit VmBudget(unsigned long long ulen) : search(kVmSearchSteps + 64ull * ulen), unit(kVmUnitSteps + 128ull * ulen), per_search(kVmSearchSteps + 64ull * ulen) {}
+	// parallel attempts (k_vm_attempts): all attempts of a unit draw on ONE unit budget in device memory, a slice at a time,
+	// and hand back what they did not use -- the work a pathological pattern can cause stays bounded per unit exactly as on
+	// the serial walk, however many attempts run at once (signed arithmetic: an overdrawn counter stays negative)
+	unsigned long long *shared;
+	__device__ explicit VmBudget(unsigned long long ulen) : search(kVmSearchSteps + 64ull * ulen), unit(kVmUnitSteps + 128ull * ulen), per_search(kVmSearchSteps + 64ull * ulen), shared(nullptr) {}
+	__device__ VmBudget(unsigned long long ulen, unsigned long long *unit_budget) : search(kVmSearchSteps + 64ull * ulen), unit(0), per_search(kVmSearchSteps + 64ull * ulen), shared(unit_budget) {}
+	__device__ static unsigned long long unit_total(unsigned long long ulen) { return kVmUnitSteps + 128ull * ulen; }
 	__device__ void new_search() { search = per_search; }
+	__device__ bool refill()
+	{
+		if (!shared) return false;
+		constexpr unsigned long long kSlice = 4096;
+		const long long before = (long long)atomicAdd(shared, (unsigned long long)(-(long long)kSlice));
+		if (before <= 0) return false;
+		unit = before < (long long)kSlice ? (unsigned long long)before : kSlice;
+		return true;
+	}
+	__device__ void give_back()
+	{
+		if (shared && unit) atomicAdd(shared, unit);
+		unit = 0;
+	}
 };
 
 __device__ int vm_exec(const ResolveArgs &R, const uint8_t *s, uint32_t len, uint32_t at, uint32_t *end, VmBudget &budget)
@@ -169,7 +189,7 @@ __device__ int vm_exec(const ResolveArgs &R, const uint8_t *s, uint32_t len, uin
 	int top = 0;
 	uint32_t pc = 0, sp = at, cap = 0;
 	for (;;) {
-		if (budget.search == 0 || budget.unit == 0) return -1;
+		if (budget.search == 0 || (budget.unit == 0 && !budget.refill())) return -1;
 		budget.search--;
 		budget.unit--;
 		const uint32_t w0 = R.vm_code[3 * pc], a = R.vm_code[3 * pc + 1], b = R.vm_code[3 * pc + 2];
@@ -521,13 +541,21 @@ __global__ void __launch_bounds__(64, 4) k_vm_attempts(const ResolveArgs R)
 	const OutRec c = R.ord[i];
 	const DevUnit du = R.units[c.unit];
 	const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
-	VmBudget budget(du.len);
+	VmBudget budget(du.len, R.vm_budget + c.unit);
 	uint32_t e = 0;
 	int rc = vm_exec(R, data + c.pos, du.len - c.pos, 0u, &e, budget);
+	budget.give_back();
 	if (rc < 0) { atomicOr(R.totals + 2, 1u); rc = 3; }
 	R.ord[i].len = e;             // the subject began at the candidate: the end offset is the match length
 	R.ord[i].pad = (uint32_t)rc;  // 0: no match here, 1: match, 2: match with a capturing group set (Q2), 3: VM limit
 	R.vm_flag[i] = rc != 0 ? 1u : 0u;
+}
+
+__global__ void k_vm_budget_init(const ResolveArgs R)
+{
+	const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= R.n_units) return;
+	R.vm_budget[u] = VmBudget::unit_total(R.units[u].len);
 }
 
 // vm_flag holds its own exclusive scan by now: the candidates that matched, in order
@@ -728,6 +756,7 @@ cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t
 		uint32_t *blk3 = blk2 + nb_u + 1;
 		if (R.vm_par) {
 			k_fill_zero<<<nb_c, 256, 0, st>>>(R.vm_flag, R.chain_cap); nl++;
+			k_vm_budget_init<<<(R.n_units + 255) / 256, 256, 0, st>>>(R); nl++;
 			k_vm_attempts<<<(R.chain_cap + 63) / 64, 64, 0, st>>>(R); nl++;
 			k_u32_sums<<<nb_cs, kScanBlock, 0, st>>>(R.vm_flag, R.chain_cap, blk3); nl++;
 			k_scan_blk<<<1, kScanBlock, 0, st>>>(blk3, nb_cs, R.totals + 4, nullptr); nl++;

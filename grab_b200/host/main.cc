@@ -235,7 +235,8 @@ public:
 		}
 		for (Member &m : crew) {
 			pthread_join(m.tid, nullptr);
-			m.grep.reset(); // prints what is still queued
+			m.grep->flush();          // prints what is still queued
+			(void)m.grep.release();   // lanes, engine contexts and pinned buffers go with the process (see main)
 		}
 	}
 
@@ -290,6 +291,7 @@ int run_single(Invocation &inv)
 	}
 	if (inv.settings.count("recursive")) {
 		if (grep->find_recursive(inv.paths[0]) < 0) { std::cerr << grep->why() << std::endl; status = kFailure; }
+		(void)grep.release(); // everything is printed (find_recursive flushes): lanes, engine contexts and pinned buffers go with the process
 		return status;
 	}
 	if (inv.paths.size() > 1) grep->show_path(true);
@@ -302,6 +304,7 @@ int run_single(Invocation &inv)
 		}
 	}
 	if (grep->flush() < 0) { std::cerr << grep->why() << std::endl; status = kFailure; }
+	(void)grep.release();
 	return status;
 }
 
@@ -333,8 +336,9 @@ int main(int argc, char **argv)
 	inv.settings["chunk_size"] = inv.chunk;
 	inv.settings["fd_budget"] = descriptor_budget(inv.workers);
 	const int status = inv.workers > 1 ? run_crew(inv) : run_single(inv);
-	// Everything is printed and every engine context is closed: leave without the CUDA runtime's exit handlers (the orderly
-	// teardown of the primary context costs 0.1-0.3 s that the kernel's own cleanup at process exit makes redundant)
+	// Everything is printed: leave without closing the engine contexts (two dozen cudaFreeHost / cudaFree calls) and without
+	// the CUDA runtime's exit handlers -- 0.2 s of orderly teardown (tools/feed_bench.py: last print at 599 ms, process gone at
+	// 816 ms) that the kernel's own cleanup at process exit makes redundant
 	std::cout.flush();
 	std::cerr.flush();
 	fflush(nullptr);

@@ -38,6 +38,7 @@ static ModelIdx model_blockIdx{0}, model_blockDim{1}, model_threadIdx{0};
 #define blockDim model_blockDim
 #define threadIdx model_threadIdx
 static inline uint32_t atomicOr(uint32_t *p, uint32_t v) { const uint32_t o = *p; *p |= v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }
 #include "vm_snippet.inc"
 #undef blockIdx
 #undef blockDim
@@ -227,10 +228,15 @@ static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, s
 		V.flat = 0;
 		V.ord = cand.data(); V.unit_start = us2; V.unit_out = uo; V.totals = tot; V.out = nullptr; V.total_cand = cap;
 		V.chain = 1; V.chain_levels = levels; V.chain_cap = cap; V.chain_buf = buf.data();
-		V.vm_par = 1; V.vm_ord = vord.data(); V.vm_flag = flag.data(); V.vm_unit_start = vus;
+		unsigned long long vbud[1] = {0};
+		V.vm_par = 1; V.vm_ord = vord.data(); V.vm_flag = flag.data(); V.vm_unit_start = vus; V.vm_budget = vbud;
+		model_threadIdx.x = 0;
+		k_vm_budget_init(V);
+		const unsigned long long bud0 = vbud[0];
 		auto each = [&](auto fn) { for (uint32_t i = 0; i < cap; i++) { model_threadIdx.x = i; fn(); } model_threadIdx.x = 0; };
 		each([&] { k_vm_attempts(V); });
 		if (tot[2]) return -1;
+		if (vbud[0] > bud0 || vbud[0] == 0) return -5; // every attempt hands back what it did not use: never more than there was
 		uint32_t acc = 0;
 		for (uint32_t i = 0; i < cap; i++) { const uint32_t f = flag[i]; flag[i] = acc; acc += f; } // device: block-scan kernels
 		tot[4] = acc;
