@@ -941,12 +941,57 @@ extern "C" int gscan_batch_scan(gscan_ctx *ctx, const gscan_pattern *pat, gscan_
 		for (int i = 0; i < 8; i++) R.bitmap[i] = dense ? pat->prog.first_set.w[i] : pat->prog.run_class.w[i];
 		R.vm_dense = dense ? 1u : 0u;
 		R.total_cand = (uint32_t)total_cand;
+		R.vm_ready = 0; R.dense_blocks = 0; R.dense_tile_shift = b->tile_shift;
 		uint32_t nl = 0;
-		CK(ctx, launch_resolve_count(R, ctx->stream, &nl));
-		S.total_launches += nl;
 		uint32_t *h_tot = reinterpret_cast<uint32_t *>((uint8_t *)ctx->readback.p + 16);
-		CK(ctx, cudaMemcpyAsync(h_tot, R.totals, 12, cudaMemcpyDeviceToHost, ctx->stream));
-		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		bool resolved_empty = false;
+		if (dense && pat->prog.vm_start_free) {
+			// dense general pattern, big units: the attempts of all positions in parallel (k_vm_dense, twice: count / write), then
+			// the chain over the matching positions -- one thread per unit would walk a 1 GiB window for minutes
+			const uint64_t blocks = (uint64_t)b->n_tiles << (b->tile_shift - 6);
+			bool want = b->bytes / std::max<uint64_t>(b->n_units, 1) >= (1u << 20);
+			if (const char *e = getenv("GSCAN_CHAIN")) want = *e == '1'; // tests: force the path on small inputs / switch it off
+			if (want && b->bytes <= (4ull << 30) && blocks < (1ull << 31)) {
+				const uint32_t nb_u = (uint32_t)((b->n_units + 2047) / 2048);
+				CK(ctx, ctx->vm_flag.ensure((size_t)blocks + 1));
+				CK(ctx, ctx->vm_budget.ensure((size_t)b->n_units));
+				CK(ctx, ctx->vm_unit_start.ensure((size_t)b->n_units + 1));
+				CK(ctx, ctx->blk.ensure((size_t)(blocks / 2048 + 2) + nb_u + 16));
+				R.blk = ctx->blk.p;
+				R.dense_blocks = (uint32_t)blocks;
+				R.vm_flag = ctx->vm_flag.p; R.vm_budget = ctx->vm_budget.p; R.vm_unit_start = ctx->vm_unit_start.p;
+				CK(ctx, launch_vm_dense_count(R, ctx->stream, &nl));
+				S.total_launches += nl;
+				uint32_t *h8 = reinterpret_cast<uint32_t *>((uint8_t *)ctx->readback.p + 32);
+				CK(ctx, cudaMemcpyAsync(h8, R.totals, 32, cudaMemcpyDeviceToHost, ctx->stream));
+				CK(ctx, cudaStreamSynchronize(ctx->stream));
+				const uint64_t hits = h8[4];
+				uint32_t levels = 2;
+				while ((1ull << levels) < hits) levels++;
+				if (hits == 0) {
+					h_tot[0] = 0; h_tot[1] = 0; h_tot[2] = h8[2];
+					resolved_empty = true;
+				} else if ((uint64_t)(levels + 2) * hits * 4 <= (4ull << 30)) {
+					CK(ctx, ctx->vm_ord.ensure((size_t)hits));
+					CK(ctx, ctx->chain.ensure((size_t)(levels + 2) * (size_t)hits));
+					CK(ctx, ctx->blk.ensure((size_t)(blocks / 2048 + 2) + nb_u + (size_t)(hits / 2048 + 2) + 16));
+					R.blk = ctx->blk.p;
+					R.vm_ord = ctx->vm_ord.p;
+					CK(ctx, launch_vm_dense_write(R, ctx->stream, &nl));
+					S.total_launches += nl;
+					R.vm_par = 1; R.vm_ready = 1; R.vm_dense = 0;
+					R.chain = 1; R.chain_levels = levels; R.chain_cap = (uint32_t)hits; R.chain_buf = ctx->chain.p;
+					R.total_cand = (uint32_t)hits;
+					S.n_candidates = hits; // positions where an attempt matched
+				} // else: more matching positions than the chain tables may hold -- the per-unit walk below serves the batch
+			}
+		}
+		if (!resolved_empty) {
+			CK(ctx, launch_resolve_count(R, ctx->stream, &nl));
+			S.total_launches += nl;
+			CK(ctx, cudaMemcpyAsync(h_tot, R.totals, 12, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(ctx, cudaStreamSynchronize(ctx->stream));
+		}
 		// a unit on which the backtracking VM ran out of stack or steps stops there, like the reference's loop when
 		// pcre_exec reports a match-limit error (rc < 0 => break, grab.cc:179, quirk Q5); the other units are unaffected
 		S.vm_limit_hit = h_tot[2] ? 1u : 0u;

@@ -70,6 +70,13 @@ struct ResolveArgs {
 	uint32_t *vm_unit_start;  // [n_units + 1] into vm_ord
 	uint32_t *vm_flag;        // [total_cand] pad != 0, then its exclusive scan
 	unsigned long long *vm_budget; // [n_units] VM steps the unit's attempts may still take, all of them together
+	// dense general patterns on the chain path (vm_ready): start-free programs without a candidate filter, units big enough
+	// that one thread per unit would walk for seconds.  k_vm_dense runs the anchored attempts of 64 consecutive positions
+	// per thread over the whole batch, twice like the serial walk (count, prefix sum, write): what comes out IS the compacted
+	// list of vm_par (vm_ord / vm_unit_start, totals[4]), and the chain kernels take it from there.
+	uint32_t vm_ready;        // vm_ord / vm_unit_start are filled already: no segments, no gather, no k_vm_attempts
+	uint32_t dense_blocks;    // 64-position blocks of the batch = n_tiles << (dense_tile_shift - 6)
+	uint32_t dense_tile_shift;
 	uint32_t vm_dense;    // general pattern without a candidate filter: no candidate list, the walk offers every position whose byte
 	                      // is in `bitmap` (the first-byte set) to the VM
 	uint32_t flat;        // ALL mode, RUN or a FIXED pattern whose matches can never overlap, no VM: every candidate of a unit is a
@@ -80,6 +87,10 @@ struct ResolveArgs {
 cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t *launches); // vm_dense: no segments, no gather
 // write pass: per-unit replay that writes R.out
 cudaError_t launch_resolve_write(const ResolveArgs &R, cudaStream_t st, uint32_t *launches);
+// dense general patterns, parallel: count pass (matching positions per 64-position block into vm_flag, exclusive scan, total
+// into totals[4]) and, once the host has sized vm_ord, the write pass (+ vm_unit_start)
+cudaError_t launch_vm_dense_count(const ResolveArgs &R, cudaStream_t st, uint32_t *launches);
+cudaError_t launch_vm_dense_write(const ResolveArgs &R, cudaStream_t st, uint32_t *launches);
 
 cudaError_t launch_synth_corpus(uint8_t *dptr, uint64_t seed, uint64_t first_file_id, uint64_t n_files, uint64_t file_len,
                                 uint64_t stride, const uint8_t *d_needle, uint32_t needle_len, uint32_t needle_every,

@@ -576,6 +576,63 @@ __global__ void k_vm_unit_starts(const ResolveArgs R)
 	R.vm_unit_start[u] = s < R.totals[0] ? R.vm_flag[s] : R.totals[4];
 }
 
+// ---- dense general patterns on the chain path (ResolveArgs::vm_ready) ----
+// No candidate list: every position whose byte can start a match gets its anchored attempt (what pcre_exec's own search
+// loop does, grab.cc:178), 64 consecutive positions per thread, all blocks of the batch at once.  The count pass leaves the
+// number of matching positions per block in vm_flag; after the exclusive scan the write pass replays the attempts and
+// writes the matching positions in order -- the compacted list the chain kernels expect.  Both passes start from the same
+// per-unit step budget; should the budget run out (nondeterministically, the attempts of a unit share it) the write pass
+// never writes more than was counted and pads what is missing with chain-ending entries.
+constexpr uint32_t kDenseShift = 6;
+template <bool WRITE>
+__global__ void __launch_bounds__(64, 4) k_vm_dense(const ResolveArgs R)
+{
+	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= R.dense_blocks) return;
+	const uint32_t bpt = R.dense_tile_shift - kDenseShift; // log2(blocks per tile)
+	const TileDesc td = R.tiles[b >> bpt];
+	const uint32_t lo = td.off + ((b & ((1u << bpt) - 1u)) << kDenseShift), tile_end = td.off + td.len;
+	uint32_t n = 0;
+	const uint32_t cnt = WRITE ? ((b + 1 < R.dense_blocks ? R.vm_flag[b + 1] : R.totals[4]) - R.vm_flag[b]) : 0u;
+	OutRec *o = WRITE ? R.vm_ord + R.vm_flag[b] : nullptr;
+	if (lo < tile_end && (!WRITE || cnt)) {
+		const DevUnit du = R.units[td.unit];
+		const uint8_t *data = reinterpret_cast<const uint8_t *>(du.ptr);
+		const uint32_t ulen = du.len;
+		const uint32_t hi = lo + (1u << kDenseShift) < tile_end ? lo + (1u << kDenseShift) : tile_end;
+		VmBudget budget(ulen, R.vm_budget + td.unit);
+		for (uint32_t pos = lo; pos < hi; pos++) {
+			if ((uint64_t)pos + R.minlen > ulen) break;                                 // an attempt with fewer bytes left cannot succeed
+			if (!in_class(R, data[pos])) continue;
+			uint32_t e = 0;
+			int rc = vm_exec(R, data + pos, ulen - pos, 0u, &e, budget);
+			budget.new_search();
+			if (rc < 0) { atomicOr(R.totals + 2, 1u); rc = 3; }
+			if (rc == 0) continue;
+			if (WRITE) {
+				if (n == cnt) break;
+				OutRec r;
+				r.unit = td.unit; r.pos = pos; r.len = e; r.pad = (uint32_t)rc;
+				o[n] = r;
+			}
+			n++;
+		}
+		budget.give_back();
+		if (WRITE) for (; n < cnt; n++) { OutRec r; r.unit = td.unit; r.pos = hi - 1u; r.len = 0; r.pad = 3u; o[n] = r; }
+	}
+	if (!WRITE) R.vm_flag[b] = n;
+}
+
+// first matching position of every unit in vm_ord: the offset of the unit's first block
+__global__ void k_vm_dense_unit_starts(const ResolveArgs R)
+{
+	const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+	if (u > R.n_units) return;
+	if (u == R.n_units) { R.vm_unit_start[u] = R.totals[4]; return; }
+	const uint32_t blk0 = R.units[u].first_tile << (R.dense_tile_shift - kDenseShift);
+	R.vm_unit_start[u] = blk0 < R.dense_blocks ? R.vm_flag[blk0] : R.totals[4];
+}
+
 // general patterns: every match starts at a candidate (a leading-byte prefix hit).  The count pass runs the VM
 // and records the outcome in the candidate array, the write pass only copies.  Own kernel: the VM's backtrack
 // stack is thread-local memory, so occupancy is capped to keep the reservation small.
@@ -742,8 +799,8 @@ static ResolveArgs chain_view(const ResolveArgs &R)
 cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t *launches)
 {
 	uint32_t nl = 0;
-	const uint32_t nb_seg = R.vm_dense ? 0u : (R.n_segs + kPerBlock - 1) / kPerBlock;
-	if (!R.vm_dense) {
+	const uint32_t nb_seg = (R.vm_dense || R.vm_ready) ? 0u : (R.n_segs + kPerBlock - 1) / kPerBlock;
+	if (!R.vm_dense && !R.vm_ready) {
 		k_seg_sums<<<nb_seg, kScanBlock, 0, st>>>(R.segs, R.n_segs, R.tag, R.blk); nl++;
 		k_scan_blk<<<1, kScanBlock, 0, st>>>(R.blk, nb_seg, R.totals, R.unit_start + R.n_units); nl++;
 		k_gather<<<nb_seg, kScanBlock, 0, st>>>(R); nl++;
@@ -754,7 +811,7 @@ cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t
 		// grids cover the reserved candidate slots; the kernels stop at the exact count (totals[0], on the device by now)
 		const uint32_t nb_c = (R.chain_cap + 255) / 256, nb_cs = (R.chain_cap + kPerBlock - 1) / kPerBlock;
 		uint32_t *blk3 = blk2 + nb_u + 1;
-		if (R.vm_par) {
+		if (R.vm_par && !R.vm_ready) {
 			k_fill_zero<<<nb_c, 256, 0, st>>>(R.vm_flag, R.chain_cap); nl++;
 			k_vm_budget_init<<<(R.n_units + 255) / 256, 256, 0, st>>>(R); nl++;
 			k_vm_attempts<<<(R.chain_cap + 63) / 64, 64, 0, st>>>(R); nl++;
@@ -792,6 +849,27 @@ cudaError_t launch_resolve_count(const ResolveArgs &R, cudaStream_t st, uint32_t
 	k_scan_blk<<<1, kScanBlock, 0, st>>>(blk2, nb_u, R.totals + 1, nullptr); nl++;
 	k_u32_exclusive<<<nb_u, kScanBlock, 0, st>>>(R.unit_out, R.n_units, blk2); nl++;
 	if (launches) *launches = nl;
+	return cudaGetLastError();
+}
+
+cudaError_t launch_vm_dense_count(const ResolveArgs &R, cudaStream_t st, uint32_t *launches)
+{
+	const uint32_t nb = (R.dense_blocks + kPerBlock - 1) / kPerBlock;
+	k_vm_budget_init<<<(R.n_units + 255) / 256, 256, 0, st>>>(R);
+	k_vm_dense<false><<<(R.dense_blocks + 63) / 64, 64, 0, st>>>(R);
+	k_u32_sums<<<nb, kScanBlock, 0, st>>>(R.vm_flag, R.dense_blocks, R.blk);
+	k_scan_blk<<<1, kScanBlock, 0, st>>>(R.blk, nb, R.totals + 4, nullptr);
+	k_u32_exclusive<<<nb, kScanBlock, 0, st>>>(R.vm_flag, R.dense_blocks, R.blk);
+	if (launches) *launches = 5;
+	return cudaGetLastError();
+}
+
+cudaError_t launch_vm_dense_write(const ResolveArgs &R, cudaStream_t st, uint32_t *launches)
+{
+	k_vm_budget_init<<<(R.n_units + 255) / 256, 256, 0, st>>>(R);
+	k_vm_dense<true><<<(R.dense_blocks + 63) / 64, 64, 0, st>>>(R);
+	k_vm_dense_unit_starts<<<(R.n_units + 1 + 255) / 256, 256, 0, st>>>(R);
+	if (launches) *launches = 3;
 	return cudaGetLastError();
 }
 

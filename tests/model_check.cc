@@ -122,7 +122,7 @@ static void candidates(const Program &p, const uint8_t *s, size_t len, std::vect
 	}
 }
 
-static int g_flat_checks = 0, g_chain_checks = 0, g_vmpar_checks = 0;
+static int g_flat_checks = 0, g_chain_checks = 0, g_vmpar_checks = 0, g_densepar_checks = 0;
 // count pass, slot scan (one unit: slot 0), write pass -- the device code of resolve_kernels.cu, on the host.
 // 0 ok, -1 VM limit
 static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, std::vector<M> &out)
@@ -268,6 +268,71 @@ static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, s
 		if (!same) return -5;
 		g_vmpar_checks++;
 	}
+	// dense general patterns on the chain path (vm_ready): the attempts of all positions in blocks of 64 (count pass, prefix
+	// sum, write pass), then the chain over the matching positions -- wherever the engine may choose it (start-free program
+	// without a candidate filter), in every mode: same records as the serial walk
+	if (p.use_vm && p.vm_dense && p.vm_start_free) {
+		TileDesc td;
+		memset(&td, 0, sizeof td);
+		td.src = du.ptr; td.unit = 0; td.off = 0; td.len = (uint32_t)len; td.ulen = (uint32_t)len;
+		const uint32_t blocks = 1u << (12 - 6); // one 4 KiB tile
+		std::vector<uint32_t> flag(blocks + 1, 0u);
+		uint32_t vus[2] = {0, 0}, tot[8] = {0, 0, 0, 0, 0, 0, 0, 0}, uo[1] = {0};
+		unsigned long long vbud[1] = {0};
+		ResolveArgs V = R;
+		V.flat = 0; V.vm_dense = 0; V.tiles = &td; V.dense_tile_shift = 12; V.dense_blocks = blocks;
+		V.unit_out = uo; V.totals = tot; V.out = nullptr;
+		V.vm_flag = flag.data(); V.vm_unit_start = vus; V.vm_budget = vbud;
+		auto blocks_each = [&](auto fn) { for (uint32_t b = 0; b < blocks; b++) { model_threadIdx.x = b; fn(); } model_threadIdx.x = 0; };
+		model_threadIdx.x = 0;
+		k_vm_budget_init(V);
+		blocks_each([&] { k_vm_dense<false>(V); });
+		if (tot[2]) return -1;
+		uint32_t acc = 0;
+		for (uint32_t b = 0; b < blocks; b++) { const uint32_t f = flag[b]; flag[b] = acc; acc += f; }
+		tot[4] = acc;
+		const uint32_t cap = acc;
+		std::vector<FinalRec> fc(1);
+		uint32_t nc = 0;
+		if (cap) {
+			std::vector<OutRec> vord(cap);
+			uint32_t levels = 2;
+			while ((1u << levels) < cap) levels++;
+			std::vector<uint32_t> buf((size_t)(levels + 2) * cap, 0u);
+			V.vm_ord = vord.data();
+			k_vm_budget_init(V);
+			blocks_each([&] { k_vm_dense<true>(V); });
+			for (uint32_t u = 0; u <= 1; u++) { model_threadIdx.x = u; k_vm_dense_unit_starts(V); }
+			model_threadIdx.x = 0;
+			V.vm_par = 1; V.vm_ready = 1;
+			V.chain = 1; V.chain_levels = levels; V.chain_cap = cap; V.chain_buf = buf.data(); V.total_cand = cap;
+			ResolveArgs C = V;
+			C.ord = V.vm_ord; C.unit_start = V.vm_unit_start; C.totals = V.totals + 4;
+			auto each = [&](auto fn) { for (uint32_t i = 0; i < cap; i++) { model_threadIdx.x = i; fn(); } model_threadIdx.x = 0; };
+			const bool follow = mode != GSCAN_MODE_FIRST;
+			if (follow) {
+				each([&] { k_chain_next(C); });
+				for (uint32_t k = 1; k < levels; k++) each([&] { k_chain_double(C, k); });
+			}
+			model_threadIdx.x = 0;
+			k_chain_heads(C);
+			if (follow) for (uint32_t k = levels; k-- > 0;) each([&] { k_chain_spread(C, k); });
+			each([&] { k_chain_unmark(C); });
+			uint32_t *mark = buf.data() + (size_t)levels * cap, *rank = mark + cap;
+			acc = 0;
+			for (uint32_t i = 0; i < cap; i++) { rank[i] = acc; acc += mark[i]; }
+			k_chain_count(C);
+			nc = uo[0];
+			uo[0] = 0;
+			fc.resize(nc + 1);
+			C.out = fc.data();
+			each([&] { k_chain_write(C); });
+		}
+		bool same = nc == n;
+		for (uint32_t i = 0; same && i < n; i++) same = fc[i].start == fin[i].start && fc[i].len == fin[i].len;
+		if (!same) return -6;
+		g_densepar_checks++;
+	}
 	return 0;
 }
 
@@ -339,6 +404,12 @@ int main(int argc, char **argv)
 				const int wrc = walk(p, sb.data(), sb.size(), dmodes[m], g2);
 				if (wrc == -3) { printf("FLAT WALK MISMATCH %s\n", pat.c_str()); bad++; go_matches_free(&w2); continue; }
 				if (wrc == -4) { printf("CHAIN WALK MISMATCH %s mode %d\n", pat.c_str(), m); bad++; go_matches_free(&w2); continue; }
+				if (wrc == -6) {
+					printf("DENSE VM CHAIN MISMATCH %s mode %d on \"", pat.c_str(), m);
+					for (uint8_t c : sb) printf(c == '\n' ? "\\n" : c == '\t' ? "\\t" : "%c", c);
+					printf("\"\n");
+					bad++; go_matches_free(&w2); continue;
+				}
 				if (wrc == -5) {
 					printf("VM CHAIN MISMATCH %s mode %d on \"", pat.c_str(), m);
 					for (uint8_t c : sb) printf(c == '\n' ? "\\n" : c == '\t' ? "\\t" : "%c", c);
@@ -374,6 +445,7 @@ int main(int argc, char **argv)
 						if (go_scan_window(re, sb.data(), sb.size(), 0, 0, modes[m], 1, &w2) != 0) { go_matches_free(&w2); continue; }
 						std::vector<M> g2;
 						const int src = ps.kind != ENGINE_NONE ? walk(ps, sb.data(), sb.size(), dmodes[m], g2) : 0;
+						if (src == -6) { printf("STRICT DENSE VM CHAIN MISMATCH %s mode %d\n", pat.c_str(), m); bad++; go_matches_free(&w2); continue; }
 						if (src == -5) { printf("STRICT VM CHAIN MISMATCH %s mode %d\n", pat.c_str(), m); bad++; go_matches_free(&w2); continue; }
 						if (src != 0) { go_matches_free(&w2); n_limit++; continue; }
 						bool ok = g2.size() == w2.n;
@@ -393,7 +465,7 @@ int main(int argc, char **argv)
 		}
 		go_free(re);
 	}
-	printf("vm chain checks %d; chain checks %d; dense VM patterns %d; ", g_vmpar_checks, g_chain_checks, n_dense);
+	printf("dense vm chain checks %d; vm chain checks %d; chain checks %d; dense VM patterns %d; ", g_densepar_checks, g_vmpar_checks, g_chain_checks, n_dense);
 	printf("flat write checks %d; strict (Q2) patterns %d; ", g_flat_checks, n_strict);
 	printf("patterns %d, served %d (%d through the VM), comparisons %d + %d through the walk kernels, limit skips %d, mismatches %d\n", n_pat, n_served, n_vm, n_cmp, n_walk, n_limit, bad);
 	if (bad == 0) printf("model ok\n");
