@@ -223,7 +223,14 @@ extern "C" int gscan_compile(const char *pattern, size_t len, uint32_t flags, gs
 		}
 		F.anchor = (uint32_t)pr.anchor;
 		F.nseq = (uint32_t)pr.seqs.size();
-		F.maxlen = (uint32_t)pr.maxlen;
+		// the longest candidate sequence: what a verification may read behind a candidate decides between the slice in shared
+		// memory and global memory.  NOT pr.maxlen: for general patterns (the sequences are only the leading bytes) that is -1,
+		// which made every verification read shared memory -- past the resident slice for a candidate on a slice's last bytes,
+		// i.e. whatever an earlier slice had left there: a candidate lost or invented per few thousand, depending on history
+		// (found by tools/tile_edge_diag.py in round 2; FIXED patterns proper were never affected)
+		size_t longest = 0;
+		for (auto &s : pr.seqs) longest = std::max(longest, s.size());
+		F.maxlen = (uint32_t)longest;
 		bool uniform = true;
 		for (auto &s : pr.seqs) uniform = uniform && s.size() == pr.seqs[0].size();
 		F.uniform_len = uniform ? (uint32_t)pr.seqs[0].size() : 0u;

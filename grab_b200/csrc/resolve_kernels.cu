@@ -162,6 +162,7 @@ struct VmBudget {
 	// and hand back what they did not use -- the work a pathological pattern can cause stays bounded per unit exactly as on
 	// the serial walk, however many attempts run at once (signed arithmetic: an overdrawn counter stays negative)
 	unsigned long long *shared;
+	unsigned long long slice = 32;
 	__device__ explicit VmBudget(unsigned long long ulen) : search(kVmSearchSteps + 64ull * ulen), unit(kVmUnitSteps + 128ull * ulen), per_search(kVmSearchSteps + 64ull * ulen), shared(nullptr) {}
 	__device__ VmBudget(unsigned long long ulen, unsigned long long *unit_budget) : search(kVmSearchSteps + 64ull * ulen), unit(0), per_search(kVmSearchSteps + 64ull * ulen), shared(unit_budget) {}
 	__device__ static unsigned long long unit_total(unsigned long long ulen) { return kVmUnitSteps + 128ull * ulen; }
@@ -169,10 +170,15 @@ struct VmBudget {
 	__device__ bool refill()
 	{
 		if (!shared) return false;
-		constexpr unsigned long long kSlice = 4096;
-		const long long before = (long long)atomicAdd(shared, (unsigned long long)(-(long long)kSlice));
-		if (before <= 0) return false;
-		unit = before < (long long)kSlice ? (unsigned long long)before : kSlice;
+		// slices grow with the attempt (32, 64, ... 512 steps): the attempts in flight -- tens of thousands of short ones on a
+		// big unit -- must not hold the whole budget between them while each uses a few dozen steps of its slice (with 4096-step
+		// slices 37 000 resident threads parked 155 M steps: every unit below 1 MiB "ran out" at once)
+		const unsigned long long want = slice;
+		if (slice < 512) slice <<= 1;
+		const long long before = (long long)atomicAdd(shared, (unsigned long long)(-(long long)want));
+		if (before <= 0) { atomicAdd(shared, want); return false; } // nothing left: undo, so that what others hand back counts
+		unit = before < (long long)want ? (unsigned long long)before : want;
+		if (before < (long long)want) atomicAdd(shared, want - unit); // took the rest only
 		return true;
 	}
 	__device__ void give_back()

@@ -2,8 +2,9 @@
 """Feed path of the command line: the same tmpfs tree through grab-b200 with the descriptor feed
 (windows read by the engine's staging threads, GSCAN_UNIT_FD) and with the mapped feed (GRAB_B200_FEED=mmap: the
 reference's mmap windows, page faults in the staging threads, munmap after the scan).  Per variant: wall time (best of
-3), and from the GRAB_B200_TRACE milestones the time until the engine context is open (CUDA start-up) and the rate
-between the first and the last batch (steady state).  Usage: python tools/feed_bench.py [n_files]"""
+3), and from the GRAB_B200_TRACE / GSCAN_TRACE_OPEN milestones the time until the engine context is open (CUDA start-up) and the rate
+between the first and the last batch (steady state).  Also a staging-thread sweep and the same runs with the driver kept warm by another process that holds a CUDA context.
+Usage: python tools/feed_bench.py [n_files] [quick]"""
 import os
 import re
 import shutil
@@ -16,12 +17,14 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+quick = len(sys.argv) > 2 and sys.argv[2] == "quick"  # the default and the warm-driver variants only
 d = bench.materialise(bench.baseline_configs()[1], n)
 ours = os.path.join(ROOT, "grab_b200", "bin", "grab-b200")
 nbytes = n * bench.FILE_LEN
 try:
     variants = [("descriptor feed", {}), ("mapped feed", {"GRAB_B200_FEED": "mmap"})]
-    variants += [("descriptor feed, %d staging threads" % t, {"GSCAN_STAGE_THREADS": str(t)}) for t in (6, 8, 16, 24, 32)]
+    if not quick:
+        variants += [("descriptor feed, %d staging threads" % t, {"GSCAN_STAGE_THREADS": str(t)}) for t in (6, 8, 16, 24, 32)]
     # the same with the driver kept warm: another process holds a CUDA context on the GPU meanwhile (what persistence mode
     # or any long-lived CUDA process gives a production box; nothing about the GPU's clocks or settings is touched)
     holder = None
