@@ -7,6 +7,7 @@
 // extraction) fed with the candidates the scan kernels deliver by contract, in all three modes (ALL / FIRST / LINE).  Also checks that the candidate filter of general patterns (leading-byte sequences / run
 // starts) never rejects a position where the VM matches.
 // Usage: model_check PATTERN_FILE   (one pattern per line)
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -272,15 +273,23 @@ static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, s
 	// sum, write pass), then the chain over the matching positions -- wherever the engine may choose it (start-free program
 	// without a candidate filter), in every mode: same records as the serial walk
 	if (p.use_vm && p.vm_dense && p.vm_start_free) {
-		TileDesc td;
-		memset(&td, 0, sizeof td);
-		td.src = du.ptr; td.unit = 0; td.off = 0; td.len = (uint32_t)len; td.ulen = (uint32_t)len;
-		const uint32_t blocks = 1u << (12 - 6); // one 4 KiB tile
+		// tiles of 256 bytes (the device's are 4 .. 64 KiB; the block -> tile -> unit arithmetic is the same): the longer
+		// subjects span several tiles, the last one partly filled
+		const uint32_t tshift = 8;
+		std::vector<TileDesc> tds;
+		for (size_t off = 0; off < len || tds.empty(); off += (size_t)1 << tshift) {
+			TileDesc t;
+			memset(&t, 0, sizeof t);
+			t.src = du.ptr + off; t.unit = 0; t.off = (uint32_t)off;
+			t.len = (uint32_t)std::min<size_t>((size_t)1 << tshift, len - off); t.ulen = (uint32_t)len;
+			tds.push_back(t);
+		}
+		const uint32_t blocks = (uint32_t)tds.size() << (tshift - 6);
 		std::vector<uint32_t> flag(blocks + 1, 0u);
 		uint32_t vus[2] = {0, 0}, tot[8] = {0, 0, 0, 0, 0, 0, 0, 0}, uo[1] = {0};
 		unsigned long long vbud[1] = {0};
 		ResolveArgs V = R;
-		V.flat = 0; V.vm_dense = 0; V.tiles = &td; V.dense_tile_shift = 12; V.dense_blocks = blocks;
+		V.flat = 0; V.vm_dense = 0; V.tiles = tds.data(); V.dense_tile_shift = tshift; V.dense_blocks = blocks;
 		V.unit_out = uo; V.totals = tot; V.out = nullptr;
 		V.vm_flag = flag.data(); V.vm_unit_start = vus; V.vm_budget = vbud;
 		auto blocks_each = [&](auto fn) { for (uint32_t b = 0; b < blocks; b++) { model_threadIdx.x = b; fn(); } model_threadIdx.x = 0; };
@@ -333,6 +342,92 @@ static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, s
 		if (!same) return -6;
 		g_densepar_checks++;
 	}
+	return 0;
+}
+
+// Two units in one batch on the chain paths (candidate chain, class runs in LINE mode, parallel VM attempts): the unit borders
+// in the binary search, the heads, the ranks and the output slots.  Expected: the per-unit serial walks (checked against
+// the oracle by the caller).  0 ok / not applicable, -1 VM limit, -7 mismatch
+static int g_two_unit_checks = 0;
+static int walk2(const Program &p, const std::vector<uint8_t> &a, const std::vector<uint8_t> &b, uint32_t mode)
+{
+	const bool fixed_chain = !p.use_vm && ((p.kind == ENGINE_FIXED && (mode == GSCAN_MODE_ALL || mode == GSCAN_MODE_LINE)) || (p.kind == ENGINE_RUN && mode == GSCAN_MODE_LINE));
+	const bool vm_chain = p.use_vm && !p.vm_dense && !p.vm_runstart && p.vm_start_free;
+	if (!fixed_chain && !vm_chain) return 0;
+	std::vector<M> want[2];
+	if (walk(p, a.data(), a.size(), mode, want[0]) != 0 || walk(p, b.data(), b.size(), mode, want[1]) != 0) return -1;
+	const std::vector<uint8_t> *subj[2] = {&a, &b};
+	DevUnit du[2];
+	std::vector<OutRec> ord;
+	uint32_t unit_start[3] = {0, 0, 0};
+	for (uint32_t u = 0; u < 2; u++) {
+		memset(&du[u], 0, sizeof du[u]);
+		du[u].ptr = (uint64_t)(uintptr_t)subj[u]->data();
+		du[u].len = (uint32_t)subj[u]->size();
+		du[u].base_off = 1000u * u; // absolute offsets differ per unit
+		du[u].file_id = 7 + u;
+		std::vector<OutRec> c;
+		candidates(p, subj[u]->data(), subj[u]->size(), c);
+		for (auto &o : c) { o.unit = u; ord.push_back(o); }
+		unit_start[u + 1] = (uint32_t)ord.size();
+	}
+	if (ord.empty()) return 0;
+	const uint32_t cap = (uint32_t)ord.size();
+	uint32_t levels = 2;
+	while ((1u << levels) < cap) levels++;
+	std::vector<uint32_t> buf((size_t)(levels + 2) * cap, 0u), flag(cap, 0u);
+	std::vector<OutRec> vord(cap);
+	uint32_t vus[3] = {0, 0, 0}, tot[8] = {cap, 0, 0, 0, 0, 0, 0, 0}, uo[2] = {0, 0};
+	unsigned long long vbud[2] = {0, 0};
+	ResolveArgs R;
+	memset(&R, 0, sizeof R);
+	R.units = du; R.n_units = 2; R.ord = ord.data(); R.unit_start = unit_start; R.unit_out = uo; R.totals = tot;
+	R.mode = mode; R.minlen = (uint32_t)p.minlen; R.engine = p.use_vm ? (uint32_t)GSCAN_ENGINE_VM : (uint32_t)p.kind; R.run_min = (uint32_t)p.run_min;
+	for (int i = 0; i < 8; i++) R.bitmap[i] = p.run_class.w[i];
+	R.vm_code = p.vm_code.data(); R.vm_sets = p.vm_sets.data();
+	R.chain = 1; R.chain_levels = levels; R.chain_cap = cap; R.chain_buf = buf.data(); R.total_cand = cap;
+	auto each = [&](auto fn) { for (uint32_t i = 0; i < cap; i++) { model_threadIdx.x = i; fn(); } model_threadIdx.x = 0; };
+	auto units_each = [&](uint32_t n, auto fn) { for (uint32_t u = 0; u < n; u++) { model_threadIdx.x = u; fn(); } model_threadIdx.x = 0; };
+	ResolveArgs C = R;
+	if (vm_chain) {
+		R.vm_par = 1; R.vm_ord = vord.data(); R.vm_flag = flag.data(); R.vm_unit_start = vus; R.vm_budget = vbud;
+		units_each(2, [&] { k_vm_budget_init(R); });
+		each([&] { k_vm_attempts(R); });
+		if (tot[2]) return -1;
+		uint32_t acc = 0;
+		for (uint32_t i = 0; i < cap; i++) { const uint32_t f = flag[i]; flag[i] = acc; acc += f; }
+		tot[4] = acc;
+		each([&] { k_vm_compact(R); });
+		units_each(3, [&] { k_vm_unit_starts(R); });
+		C = R;
+		C.ord = R.vm_ord; C.unit_start = R.vm_unit_start; C.totals = R.totals + 4;
+	}
+	const bool follow = mode != GSCAN_MODE_FIRST;
+	if (follow) {
+		each([&] { k_chain_next(C); });
+		for (uint32_t k = 1; k < levels; k++) each([&] { k_chain_double(C, k); });
+	}
+	units_each(2, [&] { k_chain_heads(C); });
+	if (follow) for (uint32_t k = levels; k-- > 0;) each([&] { k_chain_spread(C, k); });
+	if (vm_chain) each([&] { k_chain_unmark(C); });
+	if (!vm_chain && p.kind == ENGINE_RUN) { each([&] { k_chain_entry_init(C); }); each([&] { k_chain_entry(C); }); }
+	uint32_t *mark = buf.data() + (size_t)levels * cap, *rank = mark + cap;
+	uint32_t acc = 0;
+	for (uint32_t i = 0; i < cap; i++) { rank[i] = acc; acc += mark[i]; }
+	units_each(2, [&] { k_chain_count(C); });
+	const uint32_t n0 = uo[0], n1 = uo[1];
+	uo[0] = 0; uo[1] = n0; // the device: exclusive scan of the per-unit counts
+	std::vector<FinalRec> out(n0 + n1 + 1);
+	C.out = out.data();
+	each([&] { k_chain_write(C); });
+	bool same = n0 == want[0].size() && n1 == want[1].size();
+	for (uint32_t u = 0; same && u < 2; u++)
+		for (size_t i = 0; same && i < want[u].size(); i++) {
+			const FinalRec &r = out[(u ? n0 : 0) + i];
+			same = r.start == du[u].base_off + want[u][i].pos && r.len == want[u][i].len && r.file_id == du[u].file_id;
+		}
+	if (!same) return -7;
+	g_two_unit_checks++;
 	return 0;
 }
 
@@ -430,6 +525,14 @@ int main(int argc, char **argv)
 				go_matches_free(&w2);
 			}
 		}
+		// two units in one batch on the chain paths: consecutive subjects pairwise, all modes
+		for (size_t k = 0; k + 1 < subjects.size(); k += 5) {
+			const uint32_t dmodes[3] = {GSCAN_MODE_ALL, GSCAN_MODE_FIRST, GSCAN_MODE_LINE};
+			for (int m = 0; m < 3; m++) {
+				const int rc2 = walk2(p, subjects[k], subjects[k + 1], dmodes[m]);
+				if (rc2 == -7) { printf("TWO-UNIT CHAIN MISMATCH %s mode %d subjects %zu,%zu\n", pat.c_str(), m, k, k + 1); bad++; }
+			}
+		}
 		// Q2 in full (STRICT_REF): patterns with capturing groups -- the first match in which a group took part ends the
 		// window; the device walk kernels against the oracle with strict_q2 on
 		if (p.captures > 0) {
@@ -465,7 +568,7 @@ int main(int argc, char **argv)
 		}
 		go_free(re);
 	}
-	printf("dense vm chain checks %d; vm chain checks %d; chain checks %d; dense VM patterns %d; ", g_densepar_checks, g_vmpar_checks, g_chain_checks, n_dense);
+	printf("two-unit chain checks %d; dense vm chain checks %d; vm chain checks %d; chain checks %d; dense VM patterns %d; ", g_two_unit_checks, g_densepar_checks, g_vmpar_checks, g_chain_checks, n_dense);
 	printf("flat write checks %d; strict (Q2) patterns %d; ", g_flat_checks, n_strict);
 	printf("patterns %d, served %d (%d through the VM), comparisons %d + %d through the walk kernels, limit skips %d, mismatches %d\n", n_pat, n_served, n_vm, n_cmp, n_walk, n_limit, bad);
 	if (bad == 0) printf("model ok\n");

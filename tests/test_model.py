@@ -47,7 +47,8 @@ def test_compiled_programs_match_the_oracle(tmp_path):
     assert int(tail.split("flat write checks ")[1].split(";")[0]) >= 1000, tail
     assert int(tail.split("; chain checks ")[1].split(";")[0]) >= 1000, tail
     assert int(tail.split("; vm chain checks ")[1].split(";")[0]) >= 1000, tail
-    assert int(tail.split("dense vm chain checks ")[1].split(";")[0]) >= 1000, tail
+    assert int(tail.split("; dense vm chain checks ")[1].split(";")[0]) >= 1000, tail
+    assert int(tail.split("two-unit chain checks ")[1].split(";")[0]) >= 1000, tail
     served = int(tail.split("served ")[1].split(" ")[0])
     vm = int(tail.split("served ")[1].split("(")[1].split(" ")[0])
     assert served > 300 and vm > 100, tail
