@@ -26,6 +26,17 @@ def test_library_exports_every_declared_symbol():
     assert G.lib().gscan_abi_version() == 2
 
 
+def test_flag_values_match_the_header():
+    """The constants the ctypes face passes are the header's (unit flags, modes, compile flags)."""
+    hdr = open(os.path.join(ROOT, "include", "gscan.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(GSCAN_[A-Z_0-9]+)\s+(\d+)u?\b", hdr)}
+    assert defs["GSCAN_UNIT_DEVICE"] == G.UNIT_DEVICE and defs["GSCAN_UNIT_FD"] == G.UNIT_FD
+    assert (defs["GSCAN_MODE_ALL"], defs["GSCAN_MODE_FIRST"], defs["GSCAN_MODE_LINE"]) == (G.MODE_ALL, G.MODE_FIRST, G.MODE_LINE)
+    assert defs["GSCAN_LITERAL"] == G.LITERAL and defs["GSCAN_STRICT_REF"] == G.STRICT_REF
+    u = G.Context.fd_units([(5, 4096, 100)], file_ids=[9])
+    assert (int(u[0]["ptr"]), int(u[0]["len"]), int(u[0]["base_off"]), int(u[0]["file_id"]), int(u[0]["flags"])) == (5, 100, 4096, 9, G.UNIT_FD)
+
+
 def test_struct_layouts():
     assert ctypes.sizeof(G.Unit) == 32 and G.UNIT_DTYPE.itemsize == 32
     assert ctypes.sizeof(G.Match) == 16 and G.MATCH_DTYPE.itemsize == 16

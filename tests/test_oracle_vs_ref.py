@@ -121,3 +121,31 @@ def test_second_opinion_gnu_grep_P(tmp_path):
             want = [int(l.split(b":", 1)[0]) for l in g.stdout.split(b"\n") if l]
             got = [s for s, _ in o.scan_window(data)]
             assert got == want, (pat, data)
+
+
+@needs_ref
+def test_long_lines_line_mode_against_reference(tmp_path):
+    """Line output on lines longer than the 511 bytes the reference prints behind a match (grab.cc:194-196): the next search
+    resumes in the middle of the line -- for class runs possibly in the middle of a run, where PCRE then reports a match at
+    the resume point itself.  The resolve pass's chain path for class runs (k_chain_next / k_chain_entry) is built on
+    exactly this behaviour of the oracle: pinned here against the unmodified reference's stdout, line mode and -O."""
+    rnd = random.Random(511)
+    inputs = []
+    for alpha, n, newline_every in ((b"ab", 700, 0), (b"ab", 3000, 0), (b"aab_ 1", 2500, 0), (b"abc ", 4000, 1300), (b"aab_1 \n", 3000, 0),
+                                    (b"a", 1200, 0), (b"ab", 511, 0), (b"ab", 512, 0), (b"ab", 1023, 0), (b"ab", 1024, 0)):
+        b = bytearray(rnd.choice(alpha) for _ in range(n))
+        if newline_every:
+            for i in range(newline_every, n, newline_every):
+                b[i] = 10
+        inputs.append(bytes(b))
+    pats = ["[ab]{2,}", "[ab]{5,}", "a{3,}", "\\w{3,}", "[^b]{2,}", "[a_1]{2,}", "[ab\\n]{4,}", "ab", "aa|ab", "ab+a", "a[ab]*b", "\\w+ ", "a+"]
+    checked = 0
+    for pat in pats:
+        o = O.Regex(pat)
+        for i, data in enumerate(inputs):
+            path = tmp_path / ("long%d" % i)
+            path.write_bytes(data)
+            for flags, kw in (((), dict()), (("-O",), dict(offsets=True)), (("-O", "-l"), dict(offsets=True, line=False))):
+                assert o.grab(data, **kw) == ref_offsets(pat, str(path), flags), (pat, flags, i, len(data))
+                checked += 1
+    assert checked == len(pats) * len(inputs) * 3
