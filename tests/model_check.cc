@@ -309,6 +309,24 @@ static int walk(const Program &p, const uint8_t *s, size_t len, uint32_t mode, s
 			while ((1u << levels) < cap) levels++;
 			std::vector<uint32_t> buf((size_t)(levels + 2) * cap, 0u);
 			V.vm_ord = vord.data();
+			{ // the write pass with LESS budget than the count pass had (the attempts of a unit share it: on the device the two
+			  // passes can run out at different places): never more records than counted, what is missing padded with
+			  // chain-ending entries, nothing written past the list, the limit reported
+				std::vector<OutRec> guarded(cap + 4);
+				for (auto &g : guarded) g = OutRec{0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu};
+				ResolveArgs W = V;
+				uint32_t wtot[8];
+				memcpy(wtot, tot, sizeof wtot);
+				wtot[2] = 0;
+				W.totals = wtot;
+				W.vm_ord = guarded.data();
+				vbud[0] = 40; // steps for the whole unit
+				blocks_each([&] { k_vm_dense<true>(W); });
+				bool ok = true; // (40 steps can be enough for a tiny subject: then nothing is flagged and the list is complete)
+				for (uint32_t i = 0; ok && i < cap; i++) ok = guarded[i].unit == 0 && guarded[i].pos < len && guarded[i].pad >= 1 && guarded[i].pad <= 3;
+				for (uint32_t i = cap; ok && i < cap + 4; i++) ok = guarded[i].unit == 0xdeadbeefu;
+				if (!ok) return -6;
+			}
 			k_vm_budget_init(V);
 			blocks_each([&] { k_vm_dense<true>(V); });
 			for (uint32_t u = 0; u <= 1; u++) { model_threadIdx.x = u; k_vm_dense_unit_starts(V); }
